@@ -1,0 +1,157 @@
+/*
+ * rtb200.h -- C-ABI of librtb200.so: the B200 (sm_100a) compute path of the RaytracerGPU path tracer.
+ *
+ * This is the drop-in boundary.  The reference (silvercorked/RaytracerGPU_MastersProject) has no FFI: its
+ * renderer hosts call C++ wrapper classes over raw Vulkan.  Every entry point below replaces one of those
+ * call sites; the reference file:line it stands in for is cited per function (paths relative to
+ * RaytracerGPU_MastersProject/).  Plain pointers and sizes only; no C++ / torch types.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; rtb_last_error() describes the last failure
+ *    of the calling thread (the reference throws std::runtime_error at the same places, e.g.
+ *    RaytracerBVH.cpp:263-264, RaytracerBVH.hpp:398-404; the C++ shims in host/ re-throw).
+ *  - one CUDA stream per context; all kernel entry points are asynchronous on that stream and ordered,
+ *    rtb_sync() is the fence wait (vkQueueSubmit + vkWaitForFences, RaytracerBVH.hpp:398-404,474-478).
+ *  - a context is not thread-safe (neither is the reference: single host thread, one frame in flight).
+ *  - "device pointer" arguments may come from rtb_alloc or from any other allocator of the same CUDA
+ *    primary context (e.g. a torch tensor's data_ptr()).
+ *  - there is NO CPU fallback: without a CUDA device rtb_ctx_create fails.
+ *
+ * Record layouts are the reference's std430/std140 layouts byte for byte
+ * (shaders/include/definitions.glsl:6-77 == VulkanWrapper/SceneTypes.hpp:32-123).
+ */
+#ifndef RTB200_H
+#define RTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_VERSION 100
+
+/* ---- record layouts ------------------------------------------------------------------------------- */
+typedef struct { float m[16]; } rtb_model;                         /* mat4 column-major, 64 B (definitions.glsl:6-8) */
+typedef struct { float v0[4], v1[4], v2[4]; uint32_t materialIndex, modelIndex, _pad[2]; } rtb_triangle; /* 64 B (:15-21) */
+typedef struct { float center[4]; float radius; uint32_t materialIndex, modelIndex, _pad; } rtb_sphere;   /* 32 B (:23-28) */
+typedef struct { float albedo[4]; uint32_t materialType, _pad[3]; } rtb_material;                         /* 32 B (:10-13) */
+typedef struct { float minX, maxX, minY, maxY, minZ, maxZ; } rtb_aabb;                                     /* 24 B (:52-56) */
+typedef struct { rtb_aabb aabb; uint32_t leftIndex, rightIndex, primitiveIndex, primitiveType; } rtb_bvh_node; /* 40 B (:66-72) */
+typedef struct { uint32_t code, primitiveIndex, primitiveType; } rtb_morton_primitive;                    /* 12 B (:58-62) */
+typedef struct { uint32_t parent; int32_t visitationCount; } rtb_construction_info;                       /*  8 B (:74-77) */
+typedef struct { float eMin[4], eMax[4]; } rtb_enclosing_box;                  /* 32 B (GetEnclosingAABB.comp:25-28) */
+
+/* RaytracingUniformBufferObject, 80 B std140 (RaytracerBVH.hpp:31-42 == raytraceBVH.comp:7-18) */
+typedef struct {
+    float camPos[4], camLookAt[4], camUpDir[4];
+    float verticalFOV;
+    uint32_t numTriangles, numSpheres, numMaterials, numLights, maxRayTraceDepth, randomState;
+    uint32_t _pad;
+} rtb_ubo;
+
+enum { RTB_LIGHT = 0, RTB_DIFFUSE = 1, RTB_METALLIC = 2, RTB_DIELECTRIC = 3 };  /* definitions.glsl:79-82 */
+enum { RTB_SPHERE_PRIMITIVE = 0, RTB_TRIANGLE_PRIMITIVE = 1 };                  /* definitions.glsl:84-85 */
+
+/* flags for rtb_trace_args.flags */
+enum {
+    RTB_TRACE_COUNT = 1u << 0,          /* instrumented variant: fill `counters` (same traversal, same results) */
+    RTB_TRACE_EXT_MATERIALS = 1u << 1,  /* extension N1: metal / dielectric scatter (NOT reference behaviour) */
+    RTB_TRACE_ENCLOSING_INF = 1u << 2   /* build option: enclosing-AABB locals start at +-inf instead of pin U4 (0.0) */
+};
+
+/* Device-side work counters (u64 each), see DESIGN.md "roofline": rays = hitBVH calls, nodeVisits = nodes
+ * whose box was tested (reference-equivalent count), triTests / sphTests = leaf primitive tests,
+ * matReads = hits that read a material, samples = (pixel, sample) pairs. */
+typedef struct { uint64_t rays, nodeVisits, triTests, sphTests, matReads, samples; } rtb_counters;
+
+/* What one S2 submission renders (the raysPerPixel dispatch loop of RaytracerBVH.cpp:1025-1050).
+ * The image buffer is RGBA32F, `localRows` x imageWidth, row-major, local row j holding global image row
+ *     y(j) = ((j / bandRows) * bandStep + bandFirst) * bandRows + j % bandRows          (rows y >= H untouched)
+ * Single GPU: bandRows = imageHeight, bandFirst = 0, bandStep = 1, localRows = imageHeight.
+ * Tile sharding over n ranks: bandStep = n, bandFirst = rank.
+ * sampleSkip = number of links of the per-pixel alpha seed chain (raytraceBVH.comp:349-352,372) to
+ * fast-forward, starting from the alpha currently in the image, before the first rendered sample
+ * (sample-range sharding: cleared image + sampleSkip = first sample index of this rank). */
+typedef struct {
+    uint32_t imageWidth, imageHeight;   /* full image: defines the camera and the RNG seeds */
+    uint32_t localRows;
+    uint32_t bandRows, bandFirst, bandStep;
+    uint32_t sampleSkip, sampleCount;
+    uint32_t flags;
+    uint32_t _pad;
+    void* hitPrim;      /* optional device u32[localRows*W]: leaf primitive of the primary ray of the first rendered
+                           sample (triangle g < T, sphere T + idx, 0xFFFFFFFF miss) */
+    void* hitT;         /* optional device f32[localRows*W] */
+    void* rngOut;       /* optional device u32[localRows*W]: rngState after the last rendered sample */
+    void* counters;     /* device rtb_counters*, required with RTB_TRACE_COUNT (accumulated into) */
+} rtb_trace_args;
+
+typedef struct rtb_ctx rtb_ctx;
+
+/* ---- context == Device + compute queue (VulkanWrapper/Device.hpp:27-113, Device.cpp:115-231) ------ */
+const char* rtb_last_error(void);
+int rtb_version(void);
+int rtb_device_count(int* count);
+/* `stream`: a cudaStream_t to launch on (e.g. torch's current stream) or NULL to create a private one. */
+int rtb_ctx_create(int device, void* stream, rtb_ctx** out);
+int rtb_ctx_destroy(rtb_ctx* ctx);
+int rtb_sync(rtb_ctx* ctx);                                   /* vkWaitForFences: RaytracerBVH.hpp:402,476 */
+int rtb_device_name(rtb_ctx* ctx, char* buf, size_t len);     /* Device.cpp:137 prints it */
+int rtb_sm_count(rtb_ctx* ctx, int* count);
+
+/* ---- Buffer (VulkanWrapper/Buffer.hpp:23-57) + Device::copyBuffer (Device.hpp:102) ---------------- */
+int rtb_alloc(rtb_ctx* ctx, size_t bytes, void** dptr);       /* Buffer(device, size, count, STORAGE, DEVICE_LOCAL) */
+int rtb_free(rtb_ctx* ctx, void* dptr);                       /* Buffer::~Buffer (Buffer.cpp:36-40) */
+int rtb_upload(rtb_ctx* ctx, void* dst, const void* host, size_t bytes);    /* staging map/write + copyBuffer (RaytraceScene.hpp:139-178) */
+int rtb_download(rtb_ctx* ctx, void* host, const void* src, size_t bytes);  /* DEBUGgetDeployedBufferAs (RaytracerBVH.hpp:575-617) */
+int rtb_memset(rtb_ctx* ctx, void* dst, int byte, size_t bytes);
+int rtb_host_alloc(size_t bytes, void** hptr);                /* pinned staging memory (HOST_VISIBLE|HOST_COHERENT) */
+int rtb_host_free(void* hptr);
+/* CUDA-event timing on the context's stream (the reference uses std::chrono around submit+wait,
+ * RaytracerBVH.hpp:394-408,470-478) */
+int rtb_timer_start(rtb_ctx* ctx);
+int rtb_timer_stop_ms(rtb_ctx* ctx, float* ms);               /* synchronises */
+
+/* ---- S1: BVH build, one entry point per dispatch; argument order = descriptor binding order -------- */
+/* K1 ModelSpaceToWorldSpace.comp (bindings RaytracerBVH.cpp:638-643, dispatch :789): in place */
+int rtb_model_to_world(rtb_ctx* ctx, const rtb_ubo* ubo, const void* models, void* triangles, void* spheres);
+/* K2 GetEnclosingAABB.comp (bindings :644-650, dispatch :842) */
+int rtb_enclosing_aabb(rtb_ctx* ctx, const rtb_ubo* ubo, void* enclosing, const void* triangles, const void* spheres, uint32_t flags);
+/* K3 GenerateMortonCodesOfPrimitives.comp (bindings :651-658, dispatch :879) */
+int rtb_morton_codes(rtb_ctx* ctx, const rtb_ubo* ubo, const void* enclosing, const void* triangles, const void* spheres, void* morton1);
+/* K4 RadixSortSimple.comp (bindings :659-663, dispatch :916): stable ascending by code, result in morton1 */
+int rtb_sort_morton(rtb_ctx* ctx, const rtb_ubo* ubo, void* morton1, void* morton2);
+/* K5 ConstructHLBVH.comp (bindings :664-671, dispatch :954) */
+int rtb_build_hlbvh(rtb_ctx* ctx, const rtb_ubo* ubo, const void* triangles, const void* spheres, const void* morton1, void* nodes, void* constructionInfo);
+/* K6 ConstructAABBsOfInternalNodes.comp (bindings :672-676, dispatch :991) */
+int rtb_refit_aabbs(rtb_ctx* ctx, const rtb_ubo* ubo, void* nodes, void* constructionInfo);
+/* Whole S1 command buffer (recordComputeS1CommandBuffer, RaytracerBVH.cpp:734-997) minus the image clear.
+ * Any of enclosing / morton1 / morton2 / constructionInfo may be NULL (context scratch is used); `nodes`
+ * (reference 40-byte layout, 2N-1 records) may be NULL when the caller does not need the array.
+ * Also binds the result for rtb_raytrace (see rtb_bind_trace_buffers). */
+int rtb_build_bvh(rtb_ctx* ctx, const rtb_ubo* ubo, const void* models, void* triangles, void* spheres,
+                  const void* materials, void* enclosing, void* morton1, void* morton2, void* nodes,
+                  void* constructionInfo, uint32_t flags);
+
+/* ---- S2: trace ------------------------------------------------------------------------------------ */
+/* vkCmdClearColorImage to (0,0,0,1) (RaytracerBVH.cpp:772-776) */
+int rtb_clear_image(rtb_ctx* ctx, void* image, uint32_t width, uint32_t rows);
+/* DescriptorWriter.writeBuffer for the raytrace set (RaytracerBVH.cpp:677-685): binds world-space
+ * triangles / spheres, materials and the reference-layout node array, and derives the 16-byte-aligned
+ * traversal records the kernel actually fetches (DESIGN.md "data layout"). */
+int rtb_bind_trace_buffers(rtb_ctx* ctx, const rtb_ubo* ubo, const void* triangles, const void* spheres,
+                           const void* materials, const void* nodes);
+/* recordComputeS2CommandBuffer + submit (RaytracerBVH.cpp:998-1050): all samples of args->sampleCount in
+ * one persistent launch; bit-identical to sampleCount dispatches of raytraceBVH.comp. */
+int rtb_raytrace(rtb_ctx* ctx, const rtb_ubo* ubo, void* image, const rtb_trace_args* args);
+/* SingleTriangleFullScreen.frag:13-21 (+ FragmentUniformBufferObject RaytracerBVH.hpp:47-49) -> RGBA8 */
+int rtb_resolve_rgba8(rtb_ctx* ctx, const void* image, uint32_t width, uint32_t rows, uint32_t raysPerPixel, void* outRgba8);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int rtb_launch_count(rtb_ctx* ctx, uint64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

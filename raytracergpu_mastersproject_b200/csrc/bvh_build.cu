@@ -1,0 +1,381 @@
+// bvh_build.cu -- S1 of the frame: the reference's five BVH-build dispatches + ModelToWorld as sm_100a kernels
+// (K1..K3, K5, K6 of DESIGN.md; K4, the sort, is radix_sort.cu), plus the kernels that derive the 16-byte
+// aligned traversal records from the reference-layout arrays.
+//
+// Output contract: the HLBVHNode[2N-1] / MortonPrimitive[N] / enclosing-AABB buffers are bit-identical to what
+// the reference's shaders leave in their SSBOs (as pinned in DESIGN.md); every kernel cites the shader it replaces.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rtb {
+
+// ---------------------------------------------------------------------------------------------------------
+// K1  ModelSpaceToWorldSpace.comp:32-48 -- in place; one thread per primitive; grid covers T+S
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 mat_mul_point(const float4 c0, const float4 c1, const float4 c2, const float4 c3, float4 p) {
+    // mat4 * vec4(p.xyz, 1.0), per component ((c0*x + c1*y) + c2*z) + c3*w
+    const float x = p.x, y = p.y, z = p.z, w = 1.0f;
+    float4 r;
+    r.x = ((c0.x * x + c1.x * y) + c2.x * z) + c3.x * w;
+    r.y = ((c0.y * x + c1.y * y) + c2.y * z) + c3.y * w;
+    r.z = ((c0.z * x + c1.z * y) + c2.z * z) + c3.z * w;
+    r.w = ((c0.w * x + c1.w * y) + c2.w * z) + c3.w * w;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) model_to_world_kernel(const float4* __restrict__ models, float4* tris, uint32_t T,
+                                                             float4* sphs, uint32_t S) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T) {
+        float4* t = tris + 4ull * i;                       // 64-byte record: v0 v1 v2 (mat, model, pad, pad)
+        const uint4 idx = *reinterpret_cast<const uint4*>(t + 3);
+        const float4* m = models + 4ull * idx.y;
+        const float4 c0 = __ldg(m), c1 = __ldg(m + 1), c2 = __ldg(m + 2), c3 = __ldg(m + 3);
+        t[0] = mat_mul_point(c0, c1, c2, c3, t[0]);
+        t[1] = mat_mul_point(c0, c1, c2, c3, t[1]);
+        t[2] = mat_mul_point(c0, c1, c2, c3, t[2]);
+    } else if (i < T + S) {
+        float4* s = sphs + 2ull * (i - T);                 // 32-byte record: center (radius, mat, model, pad)
+        const uint4 idx = *reinterpret_cast<const uint4*>(s + 1);
+        const float4* m = models + 4ull * idx.z;
+        s[0] = mat_mul_point(__ldg(m), __ldg(m + 1), __ldg(m + 2), __ldg(m + 3), s[0]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2  GetEnclosingAABB.comp:64-110 -- the reference reduces in ONE workgroup with a spin semaphore; here a
+// grid-wide reduction: registers -> warp redux -> global atomics on order-preserving integer images of the
+// floats (total order, -0 < +0, so the result is independent of the reduction order).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+__device__ __forceinline__ f3 prim_center(const float4* __restrict__ tris, uint32_t T, const float4* __restrict__ sphs, uint32_t i) {
+    if (i < T) {  // getTriangleCenter: ((v0 + v1 + v2) / 3).xyz  (GetEnclosingAABB.comp:40-42)
+        const float4 a = tris[4ull * i], b = tris[4ull * i + 1], c = tris[4ull * i + 2];
+        return F3(((a.x + b.x) + c.x) / 3.0f, ((a.y + b.y) + c.y) / 3.0f, ((a.z + b.z) + c.z) / 3.0f);
+    }
+    return xyz(sphs[2ull * (i - T)]);
+}
+
+__global__ void enclosing_init_kernel(uint32_t* red, int initInf) {
+    // pin U4: the shader's localMin/localMax are never initialised (:69-70) -> read as 0.0
+    const float lo = initInf ? __int_as_float(0x7f800000) : 0.0f;
+    const float hi = initInf ? __int_as_float(0xff800000) : 0.0f;
+    if (threadIdx.x < 3) red[threadIdx.x] = f2ord(lo);
+    else if (threadIdx.x < 6) red[threadIdx.x] = f2ord(hi);
+}
+
+__global__ void __launch_bounds__(256) enclosing_reduce_kernel(const float4* __restrict__ tris, uint32_t T,
+                                                               const float4* __restrict__ sphs, uint32_t S, uint32_t* red) {
+    uint32_t lo[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, hi[3] = { 0u, 0u, 0u };
+    const uint32_t n = T + S;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const f3 c = prim_center(tris, T, sphs, i);
+        const uint32_t ox = f2ord(c.x), oy = f2ord(c.y), oz = f2ord(c.z);
+        lo[0] = min(lo[0], ox); lo[1] = min(lo[1], oy); lo[2] = min(lo[2], oz);
+        hi[0] = max(hi[0], ox); hi[1] = max(hi[1], oy); hi[2] = max(hi[2], oz);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        lo[k] = __reduce_min_sync(0xFFFFFFFFu, lo[k]);
+        hi[k] = __reduce_max_sync(0xFFFFFFFFu, hi[k]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (lo[k] != 0xFFFFFFFFu) atomicMin(&red[k], lo[k]);
+            if (hi[k] != 0u) atomicMax(&red[3 + k], hi[k]);
+        }
+    }
+}
+
+__global__ void enclosing_finalize_kernel(const uint32_t* __restrict__ red, float4* enclosing) {
+    if (threadIdx.x != 0) return;
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; k++) {
+        // the shader presets eMin/eMax to +-1e9 (:73-74) and folds the subgroup results in with min/max
+        float a = ord2f(red[k]), b = ord2f(red[3 + k]);
+        lo[k] = (a < 1000000000.0f) ? a : 1000000000.0f;
+        hi[k] = (b > -1000000000.0f) ? b : -1000000000.0f;
+        if (hi[k] - lo[k] < 0.001f) { lo[k] -= 0.0005f; hi[k] += 0.0005f; }   // padAABB :49-62
+    }
+    enclosing[0] = make_float4(lo[0], lo[1], lo[2], 0.0f);   // w lanes: min(1e9, 0) / max(-1e9, 0)
+    enclosing[1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3  GenerateMortonCodesOfPrimitives.comp:41-94
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t separate_bits_by3(uint32_t v) {   // :41-50
+    if (v == 1024u) v--;
+    v = (v | (v << 16)) & 50331903u;
+    v = (v | (v << 8)) & 50393103u;
+    v = (v | (v << 4)) & 51130563u;
+    v = (v | (v << 2)) & 153391689u;
+    return v;
+}
+__device__ __forceinline__ uint32_t morton_of(f3 c, float4 eMin, float4 eMax) {
+    // quantizeForMorton :60-65 divides the coordinate itself (not coord - eMin) by the span: follow the code (U5)
+    const float sx = eMax.x - eMin.x, sy = eMax.y - eMin.y, sz = eMax.z - eMin.z;
+    const uint32_t qx = __float2uint_rz((c.x / sx) * 1024.0f);   // F2I.U32 saturates, NaN -> 0
+    const uint32_t qy = __float2uint_rz((c.y / sy) * 1024.0f);
+    const uint32_t qz = __float2uint_rz((c.z / sz) * 1024.0f);
+    return separate_bits_by3(qz) << 2 | separate_bits_by3(qy) << 1 | separate_bits_by3(qx);
+}
+
+// writes either the 12-byte MortonPrimitive records (morton != nullptr) or the SoA key/value arrays the sort uses
+__global__ void __launch_bounds__(256) morton_kernel(const float4* __restrict__ tris, uint32_t T, const float4* __restrict__ sphs,
+                                                     uint32_t S, const float4* __restrict__ enclosing, uint32_t* morton,
+                                                     uint32_t* keys, uint32_t* vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T + S) return;
+    const uint32_t code = morton_of(prim_center(tris, T, sphs, i), __ldg(enclosing), __ldg(enclosing + 1));
+    if (morton) {
+        morton[3ull * i] = code;
+        morton[3ull * i + 1] = i < T ? i : i - T;
+        morton[3ull * i + 2] = i < T ? RTB_TRIANGLE_PRIMITIVE : RTB_SPHERE_PRIMITIVE;
+    }
+    if (keys) { keys[i] = code; vals[i] = i; }
+}
+
+// MortonPrimitive records <-> SoA (code, global primitive id)
+__global__ void __launch_bounds__(256) morton_unpack_kernel(const uint32_t* __restrict__ morton, uint32_t n, uint32_t T,
+                                                            uint32_t* keys, uint32_t* vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = morton[3ull * i];
+    vals[i] = morton[3ull * i + 1] + (morton[3ull * i + 2] == RTB_SPHERE_PRIMITIVE ? T : 0u);
+}
+__global__ void __launch_bounds__(256) morton_repack_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                            uint32_t n, uint32_t T, uint32_t* morton) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t g = vals[i];
+    morton[3ull * i] = keys[i];
+    morton[3ull * i + 1] = g < T ? g : g - T;
+    morton[3ull * i + 2] = g < T ? RTB_TRIANGLE_PRIMITIVE : RTB_SPHERE_PRIMITIVE;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5  ConstructHLBVH.comp -- Karras topology over the sorted codes + leaf boxes in ORIGINAL primitive order
+// ---------------------------------------------------------------------------------------------------------
+struct Codes {
+    const uint32_t* __restrict__ p; uint32_t stride; int n;
+    __device__ __forceinline__ uint32_t operator[](int i) const { return __ldg(p + (size_t)i * stride); }
+};
+// countLeadingZeroesFromDifference :58-70 ; 31 - findMSB(x) == clz(x) for x != 0
+__device__ __forceinline__ int delta(const Codes& c, int i, uint32_t codeI, int j) {
+    if (j < 0 || j > c.n - 1) return -1;
+    const uint32_t codeJ = c[j];
+    if (codeI == codeJ) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clz(codeI ^ codeJ);
+}
+
+__device__ __forceinline__ void pad_axis(float& lo, float& hi) {          // padAABB :41-54
+    if (hi - lo < 0.001f) { lo -= 0.0005f; hi += 0.0005f; }
+}
+
+__global__ void __launch_bounds__(256) hlbvh_kernel(const float4* __restrict__ tris, uint32_t T, const float4* __restrict__ sphs,
+                                                    uint32_t S, Codes codes, uint32_t* nodes /*10 words each*/, uint2* cinfo) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = (int)(T + S);
+    const int leafOffset = n - 1;
+    if (g < (uint32_t)n) {  // leaf :152-169
+        float mnx, mxx, mny, mxy, mnz, mxz;
+        uint32_t type, prim;
+        if (g < T) {        // getTriangleAABB :132-143 : min(v0, min(v1, v2))
+            const float4 a = tris[4ull * g], b = tris[4ull * g + 1], c = tris[4ull * g + 2];
+            mnx = gmin(a.x, gmin(b.x, c.x)); mxx = gmax(a.x, gmax(b.x, c.x));
+            mny = gmin(a.y, gmin(b.y, c.y)); mxy = gmax(a.y, gmax(b.y, c.y));
+            mnz = gmin(a.z, gmin(b.z, c.z)); mxz = gmax(a.z, gmax(b.z, c.z));
+            type = RTB_TRIANGLE_PRIMITIVE; prim = g;
+        } else {            // getSphereAABB :117-130
+            const float4 c = sphs[2ull * (g - T)];
+            const float r = sphs[2ull * (g - T) + 1].x;
+            const float lx = c.x - r, ly = c.y - r, lz = c.z - r, rx = c.x + r, ry = c.y + r, rz = c.z + r;
+            mnx = gmin(lx, rx); mxx = gmax(lx, rx);
+            mny = gmin(ly, ry); mxy = gmax(ly, ry);
+            mnz = gmin(lz, rz); mxz = gmax(lz, rz);
+            type = RTB_SPHERE_PRIMITIVE; prim = g - T;
+        }
+        pad_axis(mnx, mxx); pad_axis(mny, mxy); pad_axis(mnz, mxz);
+        uint32_t* nd = nodes + 10ull * (uint32_t)(leafOffset + (int)g);   // 40-byte records: 8-byte aligned
+        reinterpret_cast<float2*>(nd)[0] = make_float2(mnx, mxx);
+        reinterpret_cast<float2*>(nd)[1] = make_float2(mny, mxy);
+        reinterpret_cast<float2*>(nd)[2] = make_float2(mnz, mxz);
+        reinterpret_cast<uint2*>(nd)[3] = make_uint2(0u, 0u);
+        reinterpret_cast<uint2*>(nd)[4] = make_uint2(prim, type);
+    }
+    if ((int)g < n - 1) {   // internal :172-209
+        const int id = (int)g;
+        const uint32_t codeI = codes[id];
+        // determineRange :72-96
+        const int deltaL = delta(codes, id, codeI, id - 1);
+        const int deltaR = delta(codes, id, codeI, id + 1);
+        const int dir = (deltaR >= deltaL) ? 1 : -1;
+        const int deltaMin = min(deltaL, deltaR);
+        int lMax = 2;
+        while (delta(codes, id, codeI, id + lMax * dir) > deltaMin) lMax <<= 1;
+        int l = 0;
+        for (int t = lMax >> 1; t > 0; t >>= 1)
+            if (delta(codes, id, codeI, id + (l + t) * dir) > deltaMin) l += t;
+        const int endId = id + l * dir;
+        const int first = min(id, endId), last = max(id, endId);
+        // findSplit :98-115
+        const uint32_t codeF = codes[first];
+        const int commonPrefix = delta(codes, first, codeF, last);
+        int split = first, stride = last - first;
+        do {
+            stride = (stride + 1) >> 1;
+            const int newSplit = split + stride;
+            if (newSplit < last && delta(codes, first, codeF, newSplit) > commonPrefix) split = newSplit;
+        } while (stride > 1);
+        const int leftChild = (split == first) ? leafOffset + split : split;
+        const int rightChild = (split + 1 == last) ? leafOffset + split + 1 : split + 1;
+        uint32_t* nd = nodes + 10ull * g;
+        reinterpret_cast<float2*>(nd)[0] = make_float2(0.f, 0.f);
+        reinterpret_cast<float2*>(nd)[1] = make_float2(0.f, 0.f);
+        reinterpret_cast<float2*>(nd)[2] = make_float2(0.f, 0.f);
+        reinterpret_cast<uint2*>(nd)[3] = make_uint2((uint32_t)leftChild, (uint32_t)rightChild);
+        reinterpret_cast<uint2*>(nd)[4] = make_uint2(0u, 0u);
+        cinfo[leftChild] = make_uint2(g, 0u);
+        cinfo[rightChild] = make_uint2(g, 0u);
+    }
+    if (g == 0) cinfo[0] = make_uint2(0u, 0u);   // :212-214
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K6  ConstructAABBsOfInternalNodes.comp:38-65 -- bottom-up refit; the second arrival at a node unions its
+// children.  The shader relies on `coherent`; here: L2-scoped loads (__ldcg) + __threadfence() before the
+// counter atomic.  fp min/max of fixed operands (left, right) -> deterministic whatever the arrival order.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinfo, uint32_t n) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const uint32_t leafOffset = n - 1;
+    uint32_t nodeId = __ldcg(&cinfo[leafOffset + g]).x;
+    while (true) {
+        const int visitations = atomicAdd(reinterpret_cast<int*>(&cinfo[nodeId]) + 1, 1);
+        if (visitations < 1) return;
+        __threadfence();
+        uint32_t* nd = nodes + 10ull * nodeId;
+        const uint2 ch = __ldcg(reinterpret_cast<const uint2*>(nd) + 3);
+        const float2* L = reinterpret_cast<const float2*>(nodes + 10ull * ch.x);
+        const float2* R = reinterpret_cast<const float2*>(nodes + 10ull * ch.y);
+        const float2 lx = __ldcg(L), ly = __ldcg(L + 1), lz = __ldcg(L + 2);
+        const float2 rx = __ldcg(R), ry = __ldcg(R + 1), rz = __ldcg(R + 2);
+        // combineAABB(left, right) :27-36
+        __stcg(reinterpret_cast<float2*>(nd), make_float2(gmin(lx.x, rx.x), gmax(lx.y, rx.y)));
+        __stcg(reinterpret_cast<float2*>(nd) + 1, make_float2(gmin(ly.x, ry.x), gmax(ly.y, ry.y)));
+        __stcg(reinterpret_cast<float2*>(nd) + 2, make_float2(gmin(lz.x, rz.x), gmax(lz.y, rz.y)));
+        if (nodeId == 0) return;
+        __threadfence();
+        nodeId = __ldcg(&cinfo[nodeId]).x;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Traversal-record derivation (rtb_bind_trace_buffers): reference-layout arrays -> 16-byte aligned records
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_pairs_kernel(const uint32_t* __restrict__ nodes, uint32_t n, float4* pairs, float4* rootBox) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        const float* b = reinterpret_cast<const float*>(nodes);
+        rootBox[0] = make_float4(b[0], b[2], b[4], 0.f);
+        rootBox[1] = make_float4(b[1], b[3], b[5], 0.f);
+    }
+    if (n < 2 || i >= n - 1) return;
+    const uint32_t* nd = nodes + 10ull * i;
+    const uint32_t li = nd[6], ri = nd[7];
+    const float* L = reinterpret_cast<const float*>(nodes + 10ull * li);
+    const float* R = reinterpret_cast<const float*>(nodes + 10ull * ri);
+    float4* out = pairs + 4ull * i;
+    out[0] = make_float4(L[0], L[2], L[4], __uint_as_float(li));
+    out[1] = make_float4(L[1], L[3], L[5], __uint_as_float(ri));
+    out[2] = make_float4(R[0], R[2], R[4], 0.f);
+    out[3] = make_float4(R[1], R[3], R[5], 0.f);
+}
+
+__global__ void __launch_bounds__(256) pack_prims_kernel(const float4* __restrict__ tris, uint32_t T, const float4* __restrict__ sphs,
+                                                         uint32_t S, const float4* __restrict__ mats, uint32_t M, float4* ptris,
+                                                         float4* psphs, uint32_t* sphMat, float4* pmats) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T) {
+        const float4 a = tris[4ull * i], b = tris[4ull * i + 1], c = tris[4ull * i + 2];
+        const uint4 idx = *reinterpret_cast<const uint4*>(tris + 4ull * i + 3);
+        ptris[3ull * i] = make_float4(a.x, a.y, a.z, __uint_as_float(idx.x));
+        ptris[3ull * i + 1] = make_float4(b.x, b.y, b.z, 0.f);
+        ptris[3ull * i + 2] = make_float4(c.x, c.y, c.z, 0.f);
+    }
+    if (i < S) {
+        const float4 c = sphs[2ull * i];
+        const float4 r = sphs[2ull * i + 1];
+        psphs[i] = make_float4(c.x, c.y, c.z, r.x);
+        sphMat[i] = __float_as_uint(r.y);
+    }
+    if (i < M) {
+        const float4 a = mats[2ull * i];
+        const float4 t = mats[2ull * i + 1];
+        pmats[i] = make_float4(a.x, a.y, a.z, t.x);   // t.x carries the materialType bits
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------
+static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+void launch_model_to_world(cudaStream_t st, const void* models, void* tris, uint32_t T, void* sphs, uint32_t S) {
+    if (T + S == 0) return;
+    model_to_world_kernel<<<blocks_for(T + S, 256), 256, 0, st>>>((const float4*)models, (float4*)tris, T, (float4*)sphs, S);
+}
+int launch_enclosing(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, uint32_t* red, void* enclosing,
+                     int initInf, int smCount) {
+    enclosing_init_kernel<<<1, 32, 0, st>>>(red, initInf);
+    const uint64_t n = (uint64_t)T + S;
+    unsigned grid = blocks_for(n, 256);
+    const unsigned cap = (unsigned)smCount * 8u;       // persistent-style grid: a multiple of the SM count
+    if (grid > cap) grid = cap;
+    if (grid) enclosing_reduce_kernel<<<grid, 256, 0, st>>>((const float4*)tris, T, (const float4*)sphs, S, red);
+    enclosing_finalize_kernel<<<1, 32, 0, st>>>(red, (float4*)enclosing);
+    return grid ? 3 : 2;
+}
+void launch_morton(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* enclosing, void* morton,
+                   uint32_t* keys, uint32_t* vals) {
+    morton_kernel<<<blocks_for((uint64_t)T + S, 256), 256, 0, st>>>((const float4*)tris, T, (const float4*)sphs, S,
+                                                                    (const float4*)enclosing, (uint32_t*)morton, keys, vals);
+}
+void launch_morton_unpack(cudaStream_t st, const void* morton, uint32_t n, uint32_t T, uint32_t* keys, uint32_t* vals) {
+    morton_unpack_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t*)morton, n, T, keys, vals);
+}
+void launch_morton_repack(cudaStream_t st, const uint32_t* keys, const uint32_t* vals, uint32_t n, uint32_t T, void* morton) {
+    morton_repack_kernel<<<blocks_for(n, 256), 256, 0, st>>>(keys, vals, n, T, (uint32_t*)morton);
+}
+void launch_hlbvh(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const uint32_t* codes,
+                  uint32_t codeStrideWords, void* nodes, void* cinfo) {
+    Codes c{ codes, codeStrideWords, (int)(T + S) };
+    hlbvh_kernel<<<blocks_for((uint64_t)T + S, 256), 256, 0, st>>>((const float4*)tris, T, (const float4*)sphs, S, c,
+                                                                   (uint32_t*)nodes, (uint2*)cinfo);
+}
+void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n) {
+    refit_kernel<<<blocks_for(n, 256), 256, 0, st>>>((uint32_t*)nodes, (uint2*)cinfo, n);
+}
+void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pairs, void* rootBox) {
+    const uint32_t work = n > 1 ? n - 1 : 1;
+    pack_pairs_kernel<<<blocks_for(work, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (float4*)pairs, (float4*)rootBox);
+}
+void launch_pack_prims(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* mats, uint32_t M,
+                       void* ptris, void* psphs, void* sphMat, void* pmats) {
+    uint32_t m = T > S ? T : S;
+    if (M > m) m = M;
+    if (!m) return;
+    pack_prims_kernel<<<blocks_for(m, 256), 256, 0, st>>>((const float4*)tris, T, (const float4*)sphs, S, (const float4*)mats, M,
+                                                          (float4*)ptris, (float4*)psphs, (uint32_t*)sphMat, (float4*)pmats);
+}
+
+}  // namespace rtb

@@ -1,0 +1,399 @@
+// capi.cu -- the C-ABI of librtb200.so (include/rtb200.h): context, buffers, and one entry point per reference
+// dispatch.  Host-side work here is limited to what the reference does on the host for the same call (filling the
+// UBO-derived camera once per submission, choosing launch shapes) -- all data-path arithmetic runs in the kernels.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace rtb;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(const char* what, cudaError_t e = cudaSuccess) {
+    g_lastError = what;
+    if (e != cudaSuccess) { g_lastError += ": "; g_lastError += cudaGetErrorString(e); }
+    return 1;
+}
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(#call, _e); } while (0)
+#define REQUIRE(cond, msg) do { if (!(cond)) return fail(msg); } while (0)
+
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct rtb_ctx {
+    int device = 0;
+    int smCount = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    char name[256] = { 0 };
+    // build scratch (grow-only)
+    Scratch sortKeys[2], sortVals[2], sortCounts, encRed, enclosing, cinfo, nodes;
+    // the bound raytrace set: traversal records derived from the reference-layout arrays
+    Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag;
+    bool bound = false;
+    uint32_t bT = 0, bS = 0, bM = 0, bN = 0;
+};
+
+namespace {
+
+int ensure(rtb_ctx* c, Scratch& s, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (s.cap >= bytes) return 0;
+    if (s.p) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(s.p)); s.p = nullptr; s.cap = 0; }
+    const size_t want = bytes + bytes / 8;      // a little slack so small growth does not reallocate
+    CK(cudaMalloc(&s.p, want));
+    CK(cudaMemsetAsync(s.p, 0, want, c->stream));
+    s.cap = want;
+    return 0;
+}
+void release(Scratch& s) { if (s.p) cudaFree(s.p); s.p = nullptr; s.cap = 0; }
+
+int check_launch(rtb_ctx* c, int n, const char* what) {
+    c->launches += (uint64_t)n;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(what, e);
+    return 0;
+}
+
+struct Activate {   // make the context's device current for the duration of a call
+    int prev = -1;
+    explicit Activate(const rtb_ctx* c) { cudaGetDevice(&prev); if (prev != c->device) cudaSetDevice(c->device); else prev = -1; }
+    ~Activate() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Camera globals of raytraceBVH.comp:50-81, evaluated once on the host in binary32 with the shader's operation
+// order (compiled with -ffp-contract=off); tan() is libm's tanf.
+Camera make_camera(const rtb_ubo* ubo, uint32_t W, uint32_t H) {
+    const float FOCAL = 10.0f;
+    const float aspect = (float)W / (float)H;
+    const float theta = ubo->verticalFOV * 0.017453292519943295f;
+    const float h = tanf(theta / 2);
+    const float viewportHeight = 2.0f * h * FOCAL;
+    const float viewportWidth = viewportHeight * aspect;
+    const f3 camPos = F3(ubo->camPos[0], ubo->camPos[1], ubo->camPos[2]);
+    const f3 lookAt = F3(ubo->camLookAt[0], ubo->camLookAt[1], ubo->camLookAt[2]);
+    const f3 up = F3(ubo->camUpDir[0], ubo->camUpDir[1], ubo->camUpDir[2]);
+    const f3 camW = normalize(camPos - lookAt);
+    const f3 camU = normalize(cross(up, camW));
+    const f3 camV = cross(camW, camU);
+    const f3 viewportU = viewportWidth * camU;
+    const f3 viewportV = viewportHeight * (-camV);
+    Camera cam;
+    cam.deltaU = viewportU / (float)W;
+    cam.deltaV = viewportV / (float)H;
+    const f3 upperLeft = ((camPos - FOCAL * camW) - viewportU / 2.0f) - viewportV / 2.0f;
+    cam.pixel00 = upperLeft + 0.5f * (cam.deltaU + cam.deltaV);
+    cam.origin = camPos;
+    return cam;
+}
+
+int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tris, const void* sphs, const void* mats, const void* nodes) {
+    const uint32_t N = T + S;
+    if (ensure(c, c->pairs, sizeof(float4) * 4ull * (N > 1 ? N - 1 : 1))) return 1;
+    if (ensure(c, c->ptris, sizeof(float4) * 3ull * T)) return 1;
+    if (ensure(c, c->psphs, sizeof(float4) * (size_t)S)) return 1;
+    if (ensure(c, c->psphMat, sizeof(uint32_t) * (size_t)S)) return 1;
+    if (ensure(c, c->pmats, sizeof(float4) * (size_t)M)) return 1;
+    if (ensure(c, c->rootBox, sizeof(float4) * 2)) return 1;
+    if (ensure(c, c->workCounter, 16)) return 1;
+    if (ensure(c, c->errFlag, 16)) return 1;
+    launch_pack_pairs(c->stream, nodes, N, c->pairs.p, c->rootBox.p);
+    launch_pack_prims(c->stream, tris, T, sphs, S, mats, M, c->ptris.p, c->psphs.p, c->psphMat.p, c->pmats.p);
+    if (check_launch(c, 2, "pack traversal records")) return 1;
+    c->bound = true; c->bT = T; c->bS = S; c->bM = M; c->bN = N;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rtb_last_error(void) { return g_lastError.c_str(); }
+int rtb_version(void) { return RTB_VERSION; }
+
+int rtb_device_count(int* count) {
+    REQUIRE(count, "rtb_device_count: null argument");
+    CK(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int rtb_ctx_create(int device, void* stream, rtb_ctx** out) {
+    REQUIRE(out, "rtb_ctx_create: null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail("rtb_ctx_create: no CUDA device (librtb200 has no CPU fallback)", e);
+    REQUIRE(device >= 0 && device < n, "rtb_ctx_create: device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("rtb_ctx_create: librtb200 is built for sm_100a (Blackwell B200) only");
+    rtb_ctx* c = new rtb_ctx();
+    c->device = device;
+    c->smCount = prop.multiProcessorCount;
+    snprintf(c->name, sizeof(c->name), "%s", prop.name);
+    if (stream) { c->stream = (cudaStream_t)stream; c->ownStream = false; }
+    else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return fail("cudaStreamCreate", e); }
+        c->ownStream = true;
+    }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return 0;
+}
+
+int rtb_ctx_destroy(rtb_ctx* c) {
+    if (!c) return 0;
+    Activate act(c);
+    cudaStreamSynchronize(c->stream);
+    for (Scratch* s : { &c->sortKeys[0], &c->sortKeys[1], &c->sortVals[0], &c->sortVals[1], &c->sortCounts, &c->encRed, &c->enclosing,
+                        &c->cinfo, &c->nodes, &c->pairs, &c->ptris, &c->psphs, &c->psphMat, &c->pmats, &c->rootBox, &c->workCounter,
+                        &c->errFlag })
+        release(*s);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    if (c->ownStream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int rtb_sync(rtb_ctx* c) {
+    REQUIRE(c, "rtb_sync: null context");
+    Activate act(c);
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->errFlag.p) {
+        unsigned int f = 0;
+        CK(cudaMemcpy(&f, c->errFlag.p, sizeof(f), cudaMemcpyDeviceToHost));
+        if (f) {
+            cudaMemset(c->errFlag.p, 0, sizeof(f));
+            return fail("rtb_raytrace: traversal stack overflow (tree deeper than 64 levels)");
+        }
+    }
+    return 0;
+}
+
+int rtb_device_name(rtb_ctx* c, char* buf, size_t len) {
+    REQUIRE(c && buf && len, "rtb_device_name: bad argument");
+    snprintf(buf, len, "%s", c->name);
+    return 0;
+}
+int rtb_sm_count(rtb_ctx* c, int* count) { REQUIRE(c && count, "rtb_sm_count: bad argument"); *count = c->smCount; return 0; }
+
+int rtb_alloc(rtb_ctx* c, size_t bytes, void** dptr) {
+    REQUIRE(c && dptr, "rtb_alloc: bad argument");
+    Activate act(c);
+    *dptr = nullptr;
+    CK(cudaMalloc(dptr, bytes ? bytes : 16));
+    return 0;
+}
+int rtb_free(rtb_ctx* c, void* dptr) {
+    REQUIRE(c, "rtb_free: null context");
+    if (!dptr) return 0;
+    Activate act(c);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(dptr));
+    return 0;
+}
+int rtb_upload(rtb_ctx* c, void* dst, const void* host, size_t bytes) {
+    REQUIRE(c && (bytes == 0 || (dst && host)), "rtb_upload: bad argument");
+    Activate act(c);
+    if (bytes) CK(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+int rtb_download(rtb_ctx* c, void* host, const void* src, size_t bytes) {
+    REQUIRE(c && (bytes == 0 || (src && host)), "rtb_download: bad argument");
+    Activate act(c);
+    if (bytes) CK(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int rtb_memset(rtb_ctx* c, void* dst, int byte, size_t bytes) {
+    REQUIRE(c && (bytes == 0 || dst), "rtb_memset: bad argument");
+    Activate act(c);
+    if (bytes) CK(cudaMemsetAsync(dst, byte, bytes, c->stream));
+    return 0;
+}
+int rtb_host_alloc(size_t bytes, void** hptr) {
+    REQUIRE(hptr, "rtb_host_alloc: null argument");
+    CK(cudaMallocHost(hptr, bytes ? bytes : 16));
+    return 0;
+}
+int rtb_host_free(void* hptr) { if (hptr) CK(cudaFreeHost(hptr)); return 0; }
+
+int rtb_timer_start(rtb_ctx* c) {
+    REQUIRE(c, "rtb_timer_start: null context");
+    Activate act(c);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    return 0;
+}
+int rtb_timer_stop_ms(rtb_ctx* c, float* ms) {
+    REQUIRE(c && ms, "rtb_timer_stop_ms: bad argument");
+    Activate act(c);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+int rtb_launch_count(rtb_ctx* c, uint64_t* count) { REQUIRE(c && count, "rtb_launch_count: bad argument"); *count = c->launches; return 0; }
+
+// ---- S1 --------------------------------------------------------------------------------------------------------
+int rtb_model_to_world(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void* triangles, void* spheres) {
+    REQUIRE(c && ubo && models, "rtb_model_to_world: bad argument");
+    REQUIRE((ubo->numTriangles == 0 || triangles) && (ubo->numSpheres == 0 || spheres), "rtb_model_to_world: null primitive buffer");
+    Activate act(c);
+    launch_model_to_world(c->stream, models, triangles, ubo->numTriangles, spheres, ubo->numSpheres);
+    return check_launch(c, 1, "model_to_world_kernel");
+}
+
+int rtb_enclosing_aabb(rtb_ctx* c, const rtb_ubo* ubo, void* enclosing, const void* triangles, const void* spheres, uint32_t flags) {
+    REQUIRE(c && ubo && enclosing, "rtb_enclosing_aabb: bad argument");
+    Activate act(c);
+    if (ensure(c, c->encRed, 32)) return 1;
+    const int n = launch_enclosing(c->stream, triangles, ubo->numTriangles, spheres, ubo->numSpheres, (uint32_t*)c->encRed.p, enclosing,
+                                   (flags & RTB_TRACE_ENCLOSING_INF) ? 1 : 0, c->smCount);
+    return check_launch(c, n, "enclosing_aabb kernels");
+}
+
+int rtb_morton_codes(rtb_ctx* c, const rtb_ubo* ubo, const void* enclosing, const void* triangles, const void* spheres, void* morton1) {
+    REQUIRE(c && ubo && enclosing && morton1, "rtb_morton_codes: bad argument");
+    REQUIRE(ubo->numTriangles + ubo->numSpheres > 0, "rtb_morton_codes: empty scene");
+    Activate act(c);
+    launch_morton(c->stream, triangles, ubo->numTriangles, spheres, ubo->numSpheres, enclosing, morton1, nullptr, nullptr);
+    return check_launch(c, 1, "morton_kernel");
+}
+
+static int sort_scratch(rtb_ctx* c, uint32_t n) {
+    for (int k = 0; k < 2; k++) {
+        if (ensure(c, c->sortKeys[k], sizeof(uint32_t) * (size_t)n)) return 1;
+        if (ensure(c, c->sortVals[k], sizeof(uint32_t) * (size_t)n)) return 1;
+    }
+    return ensure(c, c->sortCounts, radix_sort_counts_bytes(n));
+}
+
+int rtb_sort_morton(rtb_ctx* c, const rtb_ubo* ubo, void* morton1, void* morton2) {
+    REQUIRE(c && ubo && morton1, "rtb_sort_morton: bad argument");
+    (void)morton2;   // the reference ping-pongs through morton2; its final content is never read (RadixSortSimple.comp:146-151)
+    const uint32_t T = ubo->numTriangles, n = T + ubo->numSpheres;
+    if (n == 0) return 0;
+    Activate act(c);
+    if (sort_scratch(c, n)) return 1;
+    uint32_t *k0 = (uint32_t*)c->sortKeys[0].p, *k1 = (uint32_t*)c->sortKeys[1].p;
+    uint32_t *v0 = (uint32_t*)c->sortVals[0].p, *v1 = (uint32_t*)c->sortVals[1].p;
+    launch_morton_unpack(c->stream, morton1, n, T, k0, v0);
+    const int ls = launch_radix_sort(c->stream, k0, v0, k1, v1, n, (uint32_t*)c->sortCounts.p);
+    launch_morton_repack(c->stream, k0, v0, n, T, morton1);
+    return check_launch(c, ls + 2, "radix sort kernels");
+}
+
+int rtb_build_hlbvh(rtb_ctx* c, const rtb_ubo* ubo, const void* triangles, const void* spheres, const void* morton1, void* nodes, void* cinfo) {
+    REQUIRE(c && ubo && morton1 && nodes && cinfo, "rtb_build_hlbvh: bad argument");
+    REQUIRE(ubo->numTriangles + ubo->numSpheres > 0, "rtb_build_hlbvh: empty scene");
+    Activate act(c);
+    launch_hlbvh(c->stream, triangles, ubo->numTriangles, spheres, ubo->numSpheres, (const uint32_t*)morton1, 3, nodes, cinfo);
+    return check_launch(c, 1, "hlbvh_kernel");
+}
+
+int rtb_refit_aabbs(rtb_ctx* c, const rtb_ubo* ubo, void* nodes, void* cinfo) {
+    REQUIRE(c && ubo && nodes && cinfo, "rtb_refit_aabbs: bad argument");
+    Activate act(c);
+    launch_refit(c->stream, nodes, cinfo, ubo->numTriangles + ubo->numSpheres);
+    return check_launch(c, 1, "refit_kernel");
+}
+
+int rtb_build_bvh(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void* triangles, void* spheres, const void* materials, void* enclosing,
+                  void* morton1, void* morton2, void* nodes, void* cinfo, uint32_t flags) {
+    REQUIRE(c && ubo && models && materials, "rtb_build_bvh: bad argument");
+    (void)morton2;
+    const uint32_t T = ubo->numTriangles, S = ubo->numSpheres, N = T + S;
+    REQUIRE(N > 0, "rtb_build_bvh: empty scene");
+    REQUIRE((T == 0 || triangles) && (S == 0 || spheres), "rtb_build_bvh: null primitive buffer");
+    Activate act(c);
+    if (!enclosing) { if (ensure(c, c->enclosing, 32)) return 1; enclosing = c->enclosing.p; }
+    if (!cinfo) { if (ensure(c, c->cinfo, 8ull * (2ull * N - 1))) return 1; cinfo = c->cinfo.p; }
+    if (!nodes) { if (ensure(c, c->nodes, 40ull * (2ull * N - 1))) return 1; nodes = c->nodes.p; }
+    if (ensure(c, c->encRed, 32)) return 1;
+    if (sort_scratch(c, N)) return 1;
+    uint32_t *k0 = (uint32_t*)c->sortKeys[0].p, *k1 = (uint32_t*)c->sortKeys[1].p;
+    uint32_t *v0 = (uint32_t*)c->sortVals[0].p, *v1 = (uint32_t*)c->sortVals[1].p;
+    int launches = 0;
+    launch_model_to_world(c->stream, models, triangles, T, spheres, S); launches++;                             // K1
+    launches += launch_enclosing(c->stream, triangles, T, spheres, S, (uint32_t*)c->encRed.p, enclosing,
+                                 (flags & RTB_TRACE_ENCLOSING_INF) ? 1 : 0, c->smCount);                          // K2
+    launch_morton(c->stream, triangles, T, spheres, S, enclosing, nullptr, k0, v0); launches++;                  // K3 (SoA out)
+    launches += launch_radix_sort(c->stream, k0, v0, k1, v1, N, (uint32_t*)c->sortCounts.p);                      // K4
+    if (morton1) { launch_morton_repack(c->stream, k0, v0, N, T, morton1); launches++; }
+    launch_hlbvh(c->stream, triangles, T, spheres, S, k0, 1, nodes, cinfo); launches++;                           // K5
+    launch_refit(c->stream, nodes, cinfo, N); launches++;                                                         // K6
+    if (check_launch(c, launches, "BVH build kernels")) return 1;
+    return bind_internal(c, T, S, ubo->numMaterials, triangles, spheres, materials, nodes);
+}
+
+// ---- S2 --------------------------------------------------------------------------------------------------------
+int rtb_clear_image(rtb_ctx* c, void* image, uint32_t width, uint32_t rows) {
+    REQUIRE(c && image, "rtb_clear_image: bad argument");
+    Activate act(c);
+    launch_clear_image(c->stream, image, (size_t)width * rows, c->smCount);
+    return check_launch(c, 1, "clear_image_kernel");
+}
+
+int rtb_bind_trace_buffers(rtb_ctx* c, const rtb_ubo* ubo, const void* triangles, const void* spheres, const void* materials, const void* nodes) {
+    REQUIRE(c && ubo && materials && nodes, "rtb_bind_trace_buffers: bad argument");
+    REQUIRE(ubo->numTriangles + ubo->numSpheres > 0, "rtb_bind_trace_buffers: empty scene");
+    Activate act(c);
+    return bind_internal(c, ubo->numTriangles, ubo->numSpheres, ubo->numMaterials, triangles, spheres, materials, nodes);
+}
+
+int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_args* a) {
+    REQUIRE(c && ubo && image && a, "rtb_raytrace: bad argument");
+    REQUIRE(c->bound, "rtb_raytrace: no buffers bound (call rtb_build_bvh or rtb_bind_trace_buffers first)");
+    REQUIRE(ubo->numTriangles == c->bT && ubo->numSpheres == c->bS, "rtb_raytrace: UBO primitive counts differ from the bound set");
+    REQUIRE(a->imageWidth && a->imageHeight && a->bandRows && a->bandStep, "rtb_raytrace: bad image / band description");
+    REQUIRE(!(a->flags & RTB_TRACE_COUNT) || a->counters, "rtb_raytrace: RTB_TRACE_COUNT needs a counters buffer");
+    if (a->sampleCount == 0 || a->localRows == 0) return 0;
+    Activate act(c);
+    TraceParams p;
+    memset(&p, 0, sizeof(p));
+    p.sc.pairs = (const float4*)c->pairs.p;
+    p.sc.tris = (const float4*)c->ptris.p;
+    p.sc.sphs = (const float4*)c->psphs.p;
+    p.sc.sphMat = (const uint32_t*)c->psphMat.p;
+    p.sc.mats = (const float4*)c->pmats.p;
+    p.sc.rootBox = (const float4*)c->rootBox.p;
+    p.sc.T = c->bT; p.sc.S = c->bS; p.sc.N = c->bN;
+    p.cam = make_camera(ubo, a->imageWidth, a->imageHeight);
+    p.image = (float4*)image;
+    p.W = a->imageWidth; p.H = a->imageHeight; p.localRows = a->localRows;
+    p.bandRows = a->bandRows; p.bandFirst = a->bandFirst; p.bandStep = a->bandStep;
+    p.sampleSkip = a->sampleSkip; p.sampleCount = a->sampleCount;
+    p.maxDepth = ubo->maxRayTraceDepth; p.randomState = ubo->randomState;
+    p.hitPrim = (uint32_t*)a->hitPrim; p.hitT = (float*)a->hitT; p.rngOut = (uint32_t*)a->rngOut;
+    p.counters = (unsigned long long*)a->counters;
+    p.workCounter = (unsigned int*)c->workCounter.p;
+    p.errFlag = (unsigned int*)c->errFlag.p;
+    launch_trace(c->stream, p, (a->flags & RTB_TRACE_COUNT) != 0, (a->flags & RTB_TRACE_EXT_MATERIALS) != 0, c->smCount);
+    return check_launch(c, 1, "trace_kernel");
+}
+
+int rtb_resolve_rgba8(rtb_ctx* c, const void* image, uint32_t width, uint32_t rows, uint32_t raysPerPixel, void* out) {
+    REQUIRE(c && image && out && raysPerPixel, "rtb_resolve_rgba8: bad argument");
+    Activate act(c);
+    launch_resolve(c->stream, image, (size_t)width * rows, raysPerPixel, out, c->smCount);
+    return check_launch(c, 1, "resolve_kernel");
+}
+
+}  // extern "C"

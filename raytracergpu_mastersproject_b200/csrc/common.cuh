@@ -1,0 +1,109 @@
+// common.cuh -- device-side arithmetic conventions and internal record layouts of librtb200.
+//
+// Arithmetic contract (must hold for bit-exact parity with the reference shaders as pinned in DESIGN.md):
+//   * this library is compiled with --fmad=false: every + - * below is an individually rounded IEEE-754
+//     binary32 op; '/' and sqrtf are the correctly rounded CUDA defaults (-prec-div/-prec-sqrt=true, no ftz)
+//   * the only fused ops are the explicit fmaf() calls of pin_sincos()
+//   * GLSL min/max are spelled as their defining ternaries (raytraceBVH.comp:188-191 semantics for NaN / -0)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtb200.h"
+
+namespace rtb {
+
+struct f3 { float x, y, z; };
+
+__host__ __device__ __forceinline__ f3 F3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__host__ __device__ __forceinline__ float gmin(float x, float y) { return y < x ? y : x; }  // GLSL min
+__host__ __device__ __forceinline__ float gmax(float x, float y) { return x < y ? y : x; }  // GLSL max
+__host__ __device__ __forceinline__ f3 operator+(f3 a, f3 b) { return F3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ __forceinline__ f3 operator-(f3 a, f3 b) { return F3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ __forceinline__ f3 operator*(f3 a, f3 b) { return F3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__host__ __device__ __forceinline__ f3 operator*(float s, f3 a) { return F3(s * a.x, s * a.y, s * a.z); }
+__host__ __device__ __forceinline__ f3 operator/(f3 a, float s) { return F3(a.x / s, a.y / s, a.z / s); }
+__host__ __device__ __forceinline__ f3 operator-(f3 a) { return F3(-a.x, -a.y, -a.z); }
+__host__ __device__ __forceinline__ float dot(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__host__ __device__ __forceinline__ f3 cross(f3 a, f3 b) {
+    return F3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__host__ __device__ __forceinline__ f3 normalize(f3 a) { return a / sqrtf(dot(a, a)); }
+__device__ __forceinline__ f3 xyz(float4 v) { return F3(v.x, v.y, v.z); }
+
+// ---- RNG: shaders/include/random.glsl:10-27 (PCG RXS-M-XS 32, inc = 1) ---------------------------------
+__host__ __device__ __forceinline__ uint32_t pcg_step(uint32_t s) { return s * 747796405u + 1u; }
+__host__ __device__ __forceinline__ uint32_t pcg_word(uint32_t s) {
+    uint32_t w = ((s >> ((s >> 28) + 4u)) ^ s) * 277803737u;
+    return (w >> 22) ^ w;
+}
+// stepAndOutputRNGFloat: float(word) / 4294967295.0f, whose literal is 2^32 in binary32 -> exact scaling
+__device__ __forceinline__ float pcg_float(uint32_t& s) {
+    s = pcg_step(s);
+    return __uint2float_rn(pcg_word(s)) * 2.3283064365386963e-10f;
+}
+// uint(alpha * 4294967294.0f) (raytraceBVH.comp:350): the literal is 2^32; F2I.U32 saturates (pin U1)
+__device__ __forceinline__ uint32_t alpha_to_u32(float a) { return __float2uint_rz(a * 4294967296.0f); }
+
+// pinned sin/cos on [0, 2*pi] (DESIGN.md "pins", U11) -- explicit fused steps in a fixed order
+__device__ __forceinline__ void pin_sincos(float x, float& s, float& c) {
+    const float q = rintf(x * 0x1.45f306p-1f);
+    float r = fmaf(q, -0x1.921fb4p+0f, x);
+    r = fmaf(q, -0x1.4442d2p-24f, r);
+    const float z = r * r;
+    float ps = fmaf(-0x1.9943f2p-13f, z, 0x1.11073cp-7f);
+    ps = fmaf(ps, z, -0x1.555546p-3f);
+    const float sr = fmaf(ps * z, r, r);
+    float pc = fmaf(0x1.99eb9cp-16f, z, -0x1.6c0c34p-10f);
+    pc = fmaf(pc, z, 0x1.55554ap-5f);
+    const float cr = fmaf(pc, z * z, fmaf(-0.5f, z, 1.0f));
+    const int k = ((int)q) & 3;
+    s = (k & 1) ? cr : sr;
+    c = (k & 1) ? sr : cr;
+    if (k & 2) s = -s;
+    if ((k + 1) & 2) c = -c;
+}
+
+// ---- traversal records (what the trace kernel fetches; derived from the reference-layout arrays) --------
+// One 64-byte, 64-byte-aligned record per INTERNAL node i in [0, N-2]: both child boxes + both child indices,
+// so one visit = four LDG.128 from two adjacent 32-byte sectors.  Leaves need no record: child index
+// c >= N-1 is primitive g = c-(N-1) (triangle g if g < T else sphere g-T; ConstructHLBVH.comp:152-169).
+struct __align__(16) PairNode {
+    float4 lLo;   // left  child box min.xyz , w = bits(left index)
+    float4 lHi;   // left  child box max.xyz , w = bits(right index)
+    float4 rLo;   // right child box min.xyz , w unused
+    float4 rHi;   // right child box max.xyz , w unused
+};
+// packed triangle: 3 x float4 = 48 B : (v0.xyz, bits(materialIndex)), (v1.xyz, 0), (v2.xyz, 0)
+// packed sphere  : 1 x float4        : (center.xyz, radius) + u32 materialIndex in a side array
+// packed material: 1 x float4        : (albedo.xyz, bits(materialType))
+
+struct TraceScene {
+    const float4* __restrict__ pairs;    // [N-1][4]
+    const float4* __restrict__ tris;     // [T][3]
+    const float4* __restrict__ sphs;     // [S]
+    const uint32_t* __restrict__ sphMat; // [S]
+    const float4* __restrict__ mats;     // [M]
+    const float4* __restrict__ rootBox;  // [2]: (min.xyz,0) (max.xyz,0) of node 0
+    uint32_t T, S, N;
+};
+
+struct Camera {            // raytraceBVH.comp:50-81, hoisted to the host (computed once per submission)
+    f3 origin, pixel00, deltaU, deltaV;
+};
+
+struct TraceParams {
+    TraceScene sc;
+    Camera cam;
+    float4* image;
+    uint32_t W, H, localRows, bandRows, bandFirst, bandStep;
+    uint32_t sampleSkip, sampleCount, maxDepth, randomState;
+    uint32_t* hitPrim; float* hitT; uint32_t* rngOut;
+    unsigned long long* counters;      // rtb_counters
+    unsigned int* workCounter;         // persistent-thread tile counter
+    unsigned int* errFlag;             // bit0: traversal stack overflow
+    uint32_t tilesX, tilesY;
+};
+
+}  // namespace rtb

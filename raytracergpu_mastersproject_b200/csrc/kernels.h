@@ -1,0 +1,36 @@
+// kernels.h -- internal launcher interface between capi.cu and the kernel translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace rtb {
+
+struct TraceParams;
+
+// bvh_build.cu
+void launch_model_to_world(cudaStream_t st, const void* models, void* tris, uint32_t T, void* sphs, uint32_t S);
+int launch_enclosing(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, uint32_t* red, void* enclosing,
+                     int initInf, int smCount);
+void launch_morton(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* enclosing, void* morton,
+                   uint32_t* keys, uint32_t* vals);
+void launch_morton_unpack(cudaStream_t st, const void* morton, uint32_t n, uint32_t T, uint32_t* keys, uint32_t* vals);
+void launch_morton_repack(cudaStream_t st, const uint32_t* keys, const uint32_t* vals, uint32_t n, uint32_t T, void* morton);
+void launch_hlbvh(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const uint32_t* codes,
+                  uint32_t codeStrideWords, void* nodes, void* cinfo);
+void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n);
+void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pairs, void* rootBox);
+void launch_pack_prims(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* mats, uint32_t M,
+                       void* ptris, void* psphs, void* sphMat, void* pmats);
+
+// radix_sort.cu
+int launch_radix_sort(cudaStream_t st, uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1, uint32_t n, uint32_t* counts);
+size_t radix_sort_counts_bytes(uint32_t n);
+
+// trace.cu
+void launch_trace(cudaStream_t st, TraceParams p, bool count, bool ext, int smCount);
+void launch_clear_image(cudaStream_t st, void* img, size_t pixels, int smCount);
+void launch_resolve(cudaStream_t st, const void* img, size_t pixels, uint32_t rpp, void* out, int smCount);
+
+}  // namespace rtb
