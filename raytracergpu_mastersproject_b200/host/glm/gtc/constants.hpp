@@ -1,0 +1,3 @@
+// part of the minimal glm stand-in: everything lives in glm/glm.hpp
+#pragma once
+#include "../glm.hpp"
