@@ -58,7 +58,9 @@ enum { RTB_SPHERE_PRIMITIVE = 0, RTB_TRIANGLE_PRIMITIVE = 1 };                  
 enum {
     RTB_TRACE_COUNT = 1u << 0,          /* instrumented variant: fill `counters` (same traversal, same results) */
     RTB_TRACE_EXT_MATERIALS = 1u << 1,  /* extension N1: metal / dielectric scatter (NOT reference behaviour) */
-    RTB_TRACE_ENCLOSING_INF = 1u << 2   /* build option: enclosing-AABB locals start at +-inf instead of pin U4 (0.0) */
+    RTB_TRACE_ENCLOSING_INF = 1u << 2,  /* build option: enclosing-AABB locals start at +-inf instead of pin U4 (0.0) */
+    RTB_TRACE_SIMPLE_KERNEL = 1u << 3   /* run the straightforward one-lane-one-pixel kernel (trace.cu) instead of the
+                                           warp-coherent one (trace_wave.cu); same results, kept for A/B measurements */
 };
 
 /* Device-side work counters (u64 each), see DESIGN.md "roofline": rays = hitBVH calls, nodeVisits = nodes

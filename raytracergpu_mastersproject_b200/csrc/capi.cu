@@ -385,8 +385,10 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     p.counters = (unsigned long long*)a->counters;
     p.workCounter = (unsigned int*)c->workCounter.p;
     p.errFlag = (unsigned int*)c->errFlag.p;
-    launch_trace(c->stream, p, (a->flags & RTB_TRACE_COUNT) != 0, (a->flags & RTB_TRACE_EXT_MATERIALS) != 0, c->smCount);
-    return check_launch(c, 1, "trace_kernel");
+    const bool count = (a->flags & RTB_TRACE_COUNT) != 0, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;
+    if (a->flags & RTB_TRACE_SIMPLE_KERNEL) launch_trace(c->stream, p, count, ext, c->smCount);
+    else launch_trace_wave(c->stream, p, count, ext, c->smCount);
+    return check_launch(c, 1, "trace kernel");
 }
 
 int rtb_resolve_rgba8(rtb_ctx* c, const void* image, uint32_t width, uint32_t rows, uint32_t raysPerPixel, void* out) {

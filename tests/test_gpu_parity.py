@@ -95,9 +95,12 @@ def test_s1_stage_by_stage(device, cfg):
 
 @pytest.mark.parametrize("cfg", SCENES, ids=lambda c: f"seed{c['seed']}")
 @pytest.mark.parametrize("spp", [1, 5])
-def test_frame_bit_exact(device, cfg, spp):
-    """Whole frame (S1 fused + S2): node array, hit ids, RNG states, counters and the fp32 image, all bit-exact."""
+@pytest.mark.parametrize("kernel", ["wave", "simple"])
+def test_frame_bit_exact(device, cfg, spp, kernel):
+    """Whole frame (S1 fused + S2): node array, hit ids, RNG states, counters and the fp32 image, all bit-exact.
+    Both trace kernels: the production warp-coherent one and the straightforward one kept for A/B measurements."""
     from raytracergpu_mastersproject_b200 import Buffer, capi
+    kflag = capi.TRACE_SIMPLE_KERNEL if kernel == "simple" else 0
     W, H = 96, 72
     sc = SU.random_scene(**cfg)
     ubo = SU.make_ubo(sc, max_depth=8, random_state=12345 + cfg["seed"])
@@ -115,7 +118,7 @@ def test_frame_bit_exact(device, cfg, spp):
     hp = Buffer(device, 4, W * H); ht = Buffer(device, 4, W * H); rg = Buffer(device, 4, W * H)
     rt.clear_image()
     rt.counters.zero()
-    rt.raytrace(ubo, spp, flags=capi.TRACE_COUNT, hit_prim=hp, hit_t=ht, rng_out=rg)
+    rt.raytrace(ubo, spp, flags=capi.TRACE_COUNT | kflag, hit_prim=hp, hit_t=ht, rng_out=rg)
     device.wait_idle()
     img = rt.read_image()
     assert np.array_equal(hp.read(np.uint32).reshape(H, W), rr["hit_prim"]), "primary hit primitive ids differ"
@@ -127,7 +130,7 @@ def test_frame_bit_exact(device, cfg, spp):
     assert rt.read_counters() == rr["counters"]
     # the non-instrumented kernel variant must give the same image
     rt.clear_image()
-    rt.raytrace(ubo, spp)
+    rt.raytrace(ubo, spp, flags=kflag)
     device.wait_idle()
     assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"]))
 
