@@ -214,10 +214,9 @@ def run_b200(args):
     ubo_p = ubo.ctypes.data_as(C.c_void_p)
 
     # band sharding of the frame (bit-identical to 1 GPU, tests/test_gpu_parity.py::test_tile_sharding_bit_identical)
-    nbands = (H + BAND_ROWS - 1) // BAND_ROWS
-    bands_per_rank = (nbands + world - 1) // world
-    rows = bands_per_rank * BAND_ROWS if world > 1 else H
-    band_rows = BAND_ROWS if world > 1 else H
+    from raytracergpu_mastersproject_b200.sharding import BandLayout, assemble_gathered, single_gpu_layout
+    layout = BandLayout(H, world, BAND_ROWS) if world > 1 else single_gpu_layout(H)
+    rows, band_rows = layout.local_rows, layout.band_rows
 
     # resident inputs: pristine model-space arrays + working copies (K1 transforms in place, so every frame starts
     # from the model-space data -- the reference re-uploads it, RaytraceScene.cpp:78-113)
@@ -256,9 +255,7 @@ def run_b200(args):
             trace_events[1].record(stream)
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), image.view(-1))
-            # rank r, local band b  ->  global band b*world + r
-            g = gathered.view(world, bands_per_rank, BAND_ROWS, W, 4).permute(1, 0, 2, 3, 4).reshape(-1, W, 4)
-            final.copy_(g[:H])
+            final.copy_(assemble_gathered(gathered, layout))      # rank r, local band b -> global band b*world + r
         capi.check(L.rtb_resolve_rgba8(h, vp(final), W, H, spp, vp(rgba8)))
 
     # ---- work counters (deterministic; one instrumented, untimed frame) ----
@@ -335,6 +332,7 @@ def run_b200(args):
     e0, e1 = ev(), ev()
     e0.record(stream)
     for _ in range(args.steps):
+        flush.zero_()
         frame_e2e()
     e1.record(stream)
     if world > 1:
@@ -360,8 +358,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (trace) ----
     peak, peak_src = peaks()
-    pix_local = sum(1 for j in range(rows) if (((j // band_rows) * (world if world > 1 else 1) + (rank if world > 1 else 0)) * band_rows
-                                               + j % band_rows) < H) * W
+    pix_local = len(layout.owned_rows(rank if world > 1 else 0)) * W
     # per launch (this rank): counters of this rank's launch; at N = 1 the all-reduced counters are this rank's
     if world > 1:
         lc = torch.zeros(6, dtype=torch.int64, device=tdev)

@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_PKG, "librtb200.so")
+_SO = os.environ.get("RTB_LIB") or os.path.join(_PKG, "librtb200.so")   # RTB_LIB: A/B builds of the same library
 _HEADER = os.path.join(os.path.dirname(_PKG), "include", "rtb200.h")
 
 MODEL = np.dtype([("m", "<f4", (16,))])

@@ -3,6 +3,7 @@
 // UBO-derived camera once per submission, choosing launch shapes) -- all data-path arithmetic runs in the kernels.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -385,6 +386,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     p.counters = (unsigned long long*)a->counters;
     p.workCounter = (unsigned int*)c->workCounter.p;
     p.errFlag = (unsigned int*)c->errFlag.p;
+    { const char* e = getenv("RTB_WAVE_TMIN"); p.tMin = e ? (uint32_t)atoi(e) : 0u; }   // tuning knob, results unaffected
     const bool count = (a->flags & RTB_TRACE_COUNT) != 0, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;
     if (a->flags & RTB_TRACE_SIMPLE_KERNEL) launch_trace(c->stream, p, count, ext, c->smCount);
     else launch_trace_wave(c->stream, p, count, ext, c->smCount);

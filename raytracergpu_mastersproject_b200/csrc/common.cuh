@@ -104,6 +104,7 @@ struct TraceParams {
     unsigned int* workCounter;         // persistent-thread tile counter
     unsigned int* errFlag;             // bit0: traversal stack overflow
     uint32_t tilesX, tilesY;
+    uint32_t tMin;                     // wave kernel: minimum stepping lanes to stay in the traverse phase (0 = default)
 };
 
 }  // namespace rtb

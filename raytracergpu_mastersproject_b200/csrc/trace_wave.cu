@@ -19,8 +19,9 @@
 //
 // Box test: t = (bound - origin) * (1/dir) with the per-ray reciprocal, plus an error filter.  Each product is within
 // 3 ulp of the reference's correctly rounded quotient (bound - origin) / dir, so when |tFar - tNear| exceeds
-// 1e-6 * max|t| the comparison tNear < tFar provably has the reference's outcome; otherwise (and for rays with a zero /
-// denormal direction component, where the reference produces inf / NaN) the exact division path of trace_common.cuh runs.
+// 5e-7 * (|tNear| + |tFar|) the comparison tNear < tFar provably has the reference's outcome; otherwise (and for rays
+// with a zero / denormal direction component, where the reference produces inf / NaN) the exact division path of
+// trace_common.cuh runs.
 // Results are bit-identical either way (tests/test_gpu_parity.py compares images, hit ids, RNG states and visit counters).
 #include "kernels.h"
 #include "trace_common.cuh"
@@ -28,10 +29,10 @@
 namespace rtb {
 
 constexpr int WAVE_THREADS = 128;
-constexpr int WAVE_MIN_BLOCKS = 4;
+constexpr int WAVE_MIN_BLOCKS = 6;
 constexpr int SSTACK = 32;                // stack entries kept in shared memory; deeper levels spill to local memory
 constexpr int QCAP = 8;                   // pending-leaf FIFO entries per lane
-constexpr int T_MIN = 20;                 // leave the traverse phase when fewer lanes than this can step
+constexpr int T_MIN_DEFAULT = 20;         // leave the traverse phase when fewer lanes than this can step
 
 struct __align__(16) WaveSmem {
     uint32_t stack[SSTACK][WAVE_THREADS];
@@ -45,8 +46,10 @@ __device__ __forceinline__ int box_filter(const f3 o, const f3 rinv, const float
     const float bx = (hix - o.x) * rinv.x, by = (hiy - o.y) * rinv.y, bz = (hiz - o.z) * rinv.z;
     const float tNear = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
     const float tFar = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-    const float m = fmaxf(fmaxf(fmaxf(fabsf(ax), fabsf(bx)), fmaxf(fabsf(ay), fabsf(by))), fmaxf(fabsf(az), fabsf(bz)));
-    const float e = fmaf(m, 1.0e-6f, 1.0e-36f);
+    // max / min are monotone, so tNear and tFar inherit the 3-ulp relative error of the products with respect to
+    // THEMSELVES; with the rounding of the subtraction: |diff - (tFar - tNear)_reference| <= 4 ulp * (|tNear| + |tFar|)
+    // = 2.4e-7 * (...).  The filter uses 5e-7 (2x margin) plus an absolute term for the subnormal range.
+    const float e = fmaf(fabsf(tNear) + fabsf(tFar), 5.0e-7f, 1.0e-36f);
     const float diff = tFar - tNear;
     if (diff > e) return 1;
     if (diff < -e) return 0;
@@ -180,6 +183,28 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
                     primDir = normalize(normalize(pixelSample - p.cam.origin));
                     rgb = F3(c.x, c.y, c.z);
                     k = 0;
+                    // The primary ray is the same for every sample of the pixel, so its test against the root box is loop
+                    // invariant.  If it fails (or the bounce loop is empty), every sample is: seed, one random(), colour 0.
+                    bool rootPass = false;
+                    if (p.maxDepth != 0) {
+                        const f3 ri = F3(1.0f / primDir.x, 1.0f / primDir.y, 1.0f / primDir.z);
+                        const bool ex = !(fabsf(ri.x) < 3.0e38f && fabsf(ri.y) < 3.0e38f && fabsf(ri.z) < 3.0e38f);
+                        const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
+                        rootPass = box_test(p.cam.origin, primDir, ri, ex, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+                    }
+                    if (!rootPass) {
+                        for (uint32_t s = 0; s < p.sampleCount; s++) {
+                            rng = base + alpha_to_u32(alpha);                              // :350
+                            alpha = pcg_float(rng);                                        // nextRandom :352 -> alpha :372
+                            const f3 col = F3(0.f, 0.f, 0.f) + F3(0.f, 0.f, 0.f) * F3(1.f, 1.f, 1.f);   // :278-279,284
+                            rgb = col + rgb;
+                        }
+                        if (COUNT) { samplesDone += p.sampleCount; if (p.maxDepth != 0) { tl.rays += p.sampleCount; tl.visits += p.sampleCount; } }
+                        p.image[px] = make_float4(rgb.x, rgb.y, rgb.z, alpha);
+                        if (p.rngOut) p.rngOut[px] = rng;
+                        if (p.hitPrim) { p.hitPrim[px] = 0xFFFFFFFFu; if (p.hitT) p.hitT[px] = 0.0f; }
+                        continue;                                                          // next pixel
+                    }
                     havePixel = true;
                 }
                 rng = base + alpha_to_u32(alpha);                                          // :350 (stepRNG :351 is a no-op)
@@ -193,13 +218,11 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
             sp = 0; qHead = 0; qCount = 0; cur = 0xFFFFFFFFu; travDone = true;
             rinv = F3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
             exactOnly = !(fabsf(rinv.x) < 3.0e38f && fabsf(rinv.y) < 3.0e38f && fabsf(rinv.z) < 3.0e38f);
-            if (p.maxDepth != 0) {                                                         // depth 0: the bounce loop never runs
-                if (COUNT) { tl.rays++; tl.visits++; }
-                const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
-                if (box_test(o, d, rinv, exactOnly, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) {
-                    if (sc.N == 1) enqueue(0u);                                            // the root is the only leaf
-                    else { cur = 0; travDone = false; }
-                }
+            if (COUNT) { tl.rays++; tl.visits++; }
+            const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
+            if (box_test(o, d, rinv, exactOnly, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) {
+                if (sc.N == 1) enqueue(0u);                                                // the root is the only leaf
+                else { cur = 0; travDone = false; }
             }
         }
         if (__all_sync(FULL, dead)) break;
@@ -209,41 +232,42 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
             const bool can = rayActive && !travDone && qCount <= QCAP - 2;
             const unsigned bal = __ballot_sync(FULL, can);
             if (bal == 0) break;
-            if (__popc(bal) < T_MIN) {
+            if (__popc(bal) < (int)p.tMin) {
                 const bool waiting = !dead && !can;                       // lanes that L or S could put back to work
                 if (__any_sync(FULL, waiting)) break;
             }
             if (can) {
-                if (cur == 0xFFFFFFFFu) {                                  // resume from the stack
-                    if (sp == 0) travDone = true;
-                    else {
-                        const uint32_t e = pop();
-                        if (e >= leafOffset) enqueue(e - leafOffset); else cur = e;
-                    }
-                } else {
+                if (cur != 0xFFFFFFFFu) {
                     const float4* pr = sc.pairs + 4ull * cur;
                     const float4 lLo = __ldg(pr), lHi = __ldg(pr + 1), rLo = __ldg(pr + 2), rHi = __ldg(pr + 3);
                     if (COUNT) tl.visits += 2;
                     const uint32_t li = __float_as_uint(lLo.w), ri = __float_as_uint(lHi.w);
-                    const bool passR = box_test(o, d, rinv, exactOnly, rLo.x, rLo.y, rLo.z, rHi.x, rHi.y, rHi.z);
-                    const bool passL = box_test(o, d, rinv, exactOnly, lLo.x, lLo.y, lLo.z, lHi.x, lHi.y, lHi.z);
-                    uint32_t next = 0xFFFFFFFFu;
-                    if (passR) {                                           // right subtree first (:241-244)
-                        if (ri >= leafOffset) enqueue(ri - leafOffset); else next = ri;
+                    int fR = box_filter(o, rinv, rLo.x, rLo.y, rLo.z, rHi.x, rHi.y, rHi.z);
+                    int fL = box_filter(o, rinv, lLo.x, lLo.y, lLo.z, lHi.x, lHi.y, lHi.z);
+                    if (exactOnly || (fR | fL) < 0) {                      // rare: some comparison is too close to call
+                        fR = box_hit(o, d, rLo.x, rLo.y, rLo.z, rHi.x, rHi.y, rHi.z) ? 1 : 0;
+                        fL = box_hit(o, d, lLo.x, lLo.y, lLo.z, lHi.x, lHi.y, lHi.z) ? 1 : 0;
                     }
-                    if (passL) {
-                        if (next != 0xFFFFFFFFu) push(li);                 // waits until the right subtree is done
-                        else if (li >= leafOffset) enqueue(li - leafOffset);
-                        else next = li;
-                    }
-                    if (next == 0xFFFFFFFFu && qCount < QCAP) {            // one eager pop keeps the lane moving
-                        if (sp == 0) travDone = true;
-                        else {
-                            const uint32_t e = pop();
-                            if (e >= leafOffset) enqueue(e - leafOffset); else next = e;
-                        }
-                    }
-                    cur = next;
+                    // Reference order (:241-244): the right subtree completely, then the left.  Straight-line bookkeeping:
+                    const bool passR = fR != 0, passL = fL != 0;
+                    const bool leafR = ri >= leafOffset, leafL = li >= leafOffset;
+                    const bool goR = passR && !leafR;                      // descend right now
+                    const bool enqR = passR && leafR;                      // right child is a leaf: test it first
+                    const bool pushL = passL && goR;                       // left waits on the stack until right is done
+                    const bool enqL = passL && !goR && leafL;
+                    const bool goL = passL && !goR && !leafL;
+                    uint32_t tail = (qHead + qCount) & (QCAP - 1);
+                    if (enqR) sm.queue[tail][tid] = ri - leafOffset;
+                    tail = (tail + (enqR ? 1u : 0u)) & (QCAP - 1);
+                    if (enqL) sm.queue[tail][tid] = li - leafOffset;
+                    qCount += (enqR ? 1u : 0u) + (enqL ? 1u : 0u);
+                    if (pushL) push(li);
+                    cur = goR ? ri : (goL ? li : 0xFFFFFFFFu);
+                }
+                while (cur == 0xFFFFFFFFu && qCount < QCAP) {              // resume from the stack (usually 0 or 1 turns)
+                    if (sp == 0) { travDone = true; break; }
+                    const uint32_t e = pop();
+                    if (e >= leafOffset) enqueue(e - leafOffset); else cur = e;
                 }
             }
         }
@@ -294,6 +318,7 @@ void launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, int
     const uint64_t need = (numWarps + WAVE_THREADS / 32 - 1) / (WAVE_THREADS / 32);
     if (grid > need) grid = need;
     if (grid == 0) return;
+    if (p.tMin == 0) p.tMin = T_MIN_DEFAULT;
     cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), st);
     if (count) {
         if (ext) trace_wave_kernel<true, true><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);

@@ -299,7 +299,7 @@ auto SyntheticScenes::heightFieldScene(ScenePtr& scene, u32 nx, u32 nz, u32 seed
 	// Materials are per GameObject, so "x % of the triangles are dielectric" is expressed by cutting the Morton-ordered
 	// list into contiguous chunks (one GameObject each): the flattened order stays globally Morton-sorted.
 	const Mat ground = diffuse(0.55f, 0.5f, 0.4f), glass(glm::vec3(0.9f, 0.95f, 1.0f), MaterialType::DIELECTRIC);
-	const size_t chunk = dielectricPercent ? 4096 : tris.size();
+	const size_t chunk = dielectricPercent ? std::clamp<size_t>(tris.size() / 256, 64, 4096) : tris.size();
 	SceneRng rng(seed ^ 0x5EEDu);
 	for (size_t begin = 0; begin < tris.size(); begin += chunk) {
 		const size_t end = std::min(tris.size(), begin + chunk);
