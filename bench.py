@@ -192,6 +192,8 @@ def run_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on stdout; keep stdout to the one JSON line the contract asks for
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "rtb200_nccl_%h_%p.log"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)

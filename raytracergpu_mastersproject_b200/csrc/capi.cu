@@ -44,6 +44,7 @@ struct rtb_ctx {
     Scratch sortKeys[2], sortVals[2], sortCounts, encRed, enclosing, cinfo, nodes;
     // the bound raytrace set: traversal records derived from the reference-layout arrays
     Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag;
+    Scratch activePix, sampleBuf;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
     bool bound = false;
     uint32_t bT = 0, bS = 0, bM = 0, bN = 0;
 };
@@ -164,7 +165,7 @@ int rtb_ctx_destroy(rtb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (Scratch* s : { &c->sortKeys[0], &c->sortKeys[1], &c->sortVals[0], &c->sortVals[1], &c->sortCounts, &c->encRed, &c->enclosing,
                         &c->cinfo, &c->nodes, &c->pairs, &c->ptris, &c->psphs, &c->psphMat, &c->pmats, &c->rootBox, &c->workCounter,
-                        &c->errFlag })
+                        &c->errFlag, &c->activePix, &c->sampleBuf })
         release(*s);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -388,9 +389,27 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     p.errFlag = (unsigned int*)c->errFlag.p;
     { const char* e = getenv("RTB_WAVE_TMIN"); p.tMin = e ? (uint32_t)atoi(e) : 0u; }   // tuning knob, results unaffected
     const bool count = (a->flags & RTB_TRACE_COUNT) != 0, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;
-    if (a->flags & RTB_TRACE_SIMPLE_KERNEL) launch_trace(c->stream, p, count, ext, c->smCount);
-    else launch_trace_wave(c->stream, p, count, ext, c->smCount);
-    return check_launch(c, 1, "trace kernel");
+    int launches = 1;
+    if (a->flags & RTB_TRACE_SIMPLE_KERNEL) {
+        launch_trace(c->stream, p, count, ext, c->smCount);
+    } else {
+        // per-(sample, pixel) colour slots: as many samples per pass as fit the scratch budget (default 4 GiB)
+        const size_t pixels = (size_t)a->imageWidth * a->localRows;
+        size_t budget = 4ull << 30;
+        if (const char* e = getenv("RTB_WAVE_SAMPLE_BUF_MB")) budget = (size_t)atoll(e) << 20;
+        size_t perPass = budget / (pixels * sizeof(float4));
+        if (perPass < 1) perPass = 1;
+        if (perPass > a->sampleCount) perPass = a->sampleCount;
+        if (ensure(c, c->activePix, pixels * sizeof(uint32_t))) return 1;
+        if (ensure(c, c->sampleBuf, pixels * perPass * sizeof(float4))) return 1;
+        p.workCounter64 = (unsigned long long*)c->workCounter.p;
+        p.activeCount = (unsigned int*)c->workCounter.p + 2;
+        p.activePix = (uint32_t*)c->activePix.p;
+        p.sampleBuf = (float4*)c->sampleBuf.p;
+        p.slotCapacity = (uint32_t)pixels;
+        launches = launch_trace_wave(c->stream, p, count, ext, c->smCount, (uint32_t)perPass);
+    }
+    return check_launch(c, launches, "trace kernel");
 }
 
 int rtb_resolve_rgba8(rtb_ctx* c, const void* image, uint32_t width, uint32_t rows, uint32_t raysPerPixel, void* out) {

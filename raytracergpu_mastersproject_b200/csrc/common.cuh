@@ -105,6 +105,13 @@ struct TraceParams {
     unsigned int* errFlag;             // bit0: traversal stack overflow
     uint32_t tilesX, tilesY;
     uint32_t tMin;                     // wave kernel: minimum stepping lanes to stay in the traverse phase (0 = default)
+    // wave kernel, per pass: (pixel, sample) work items
+    unsigned long long* workCounter64; // [0] work-item counter, [1] (as unsigned*) active-pixel count
+    unsigned int* activeCount;         // = (unsigned*)(workCounter64 + 1)
+    uint32_t* activePix;               // [pixels] local pixel index of every pixel whose primary ray enters the root box
+    float4* sampleBuf;                 // [samplesPerPass][slotCapacity]: (colour.xyz, incoming alpha) per (sample, active pixel)
+    uint32_t slotCapacity;
+    uint32_t firstPass, lastPass;
 };
 
 }  // namespace rtb

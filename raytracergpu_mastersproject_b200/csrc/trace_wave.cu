@@ -12,8 +12,16 @@
 //                 184-193): which leaves a ray visits, and in which order, does not depend on the hits found so far.
 //   L  leaves   : lanes pop their FIFO in order and run the triangle / sphere test with the running closest-so-far, so
 //                 the sequence of primitive tests per ray -- and every tie-break (pin U9) -- is exactly the reference's.
-//   S  shade    : lanes whose ray is finished shade it (emit / diffuse scatter), start the next bounce, the next sample of
-//                 the pixel, or pull the next pixel from a global counter (lane-granular persistent threads).
+//   S  shade    : lanes whose ray is finished shade it (emit / diffuse scatter), start the next bounce, or pull the next
+//                 (pixel, sample) work item from a global counter (lane-granular persistent threads).
+//
+// Work items are (pixel, sample), not pixels: a pixel's samples are sequential only through two scalars -- the alpha seed
+// chain (raytraceBVH.comp:349-352,372), which needs no tracing to advance, and the fp32 running sum.  A pre-pass walks the
+// chain of every pixel and parks each sample's seed in a per-sample slot; the trace kernel fills the slot with that
+// sample's colour; an accumulate pass then adds the slots in sample order (colour_k + sum, exactly the shader's
+// association), so the image is bit-identical to sequential dispatches while no lane is ever tied to a pixel for more
+// than one sample (a hit pixel's 64 samples used to keep one lane busy for ~30 ms: a 70 ms kernel tail at 1080p).
+// Pixels whose primary ray misses the root box (the same ray for every sample: no jitter) never reach the trace kernel.
 // Warp votes (__ballot_sync) decide the phase switches: T runs while at least T_MIN lanes can step; a warp leaves T
 // early only when other lanes are waiting for L or S.
 //
@@ -65,6 +73,116 @@ __device__ __forceinline__ bool box_test(const f3 o, const f3 d, const f3 rinv, 
     return box_hit(o, d, lox, loy, loz, hix, hiy, hiz);
 }
 
+// global image row of local row j (rtb_trace_args: interleaved bands)
+__device__ __forceinline__ uint32_t global_row(const TraceParams& p, uint32_t j) {
+    return ((j / p.bandRows) * p.bandStep + p.bandFirst) * p.bandRows + (j % p.bandRows);
+}
+// getRay :329-342 (no jitter: the same for every sample of a pixel) + rayColor's own normalize :280
+__device__ __forceinline__ f3 primary_direction(const TraceParams& p, uint32_t x, uint32_t y) {
+    const f3 pixelSample = (p.cam.pixel00 + (float)x * p.cam.deltaU) + (float)y * p.cam.deltaV;
+    return normalize(normalize(pixelSample - p.cam.origin));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pre-pass, one thread per local pixel: walk the alpha seed chain for the `passCount` samples of this pass.
+//  * primary ray misses the root box (or maxDepth == 0): every sample is "seed, one random(), colour 0" -> finish the pixel here
+//  * otherwise: append the pixel to the active list and park sample s's incoming alpha in slot (s, pixel).w
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(256) wave_prepass_kernel(const TraceParams p) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t x = idx % p.W, j = idx / p.W;
+    unsigned long long nRays = 0, nSamples = 0;
+    bool activePixel = false;
+    uint32_t y = 0, base = 0;
+    float alpha = 0.f;
+    if (j < p.localRows) {
+        y = global_row(p, j);
+        if (y < p.H) {
+            const float4 c = p.image[idx];                                                  // imageLoad :349
+            base = (600u * x + y) * (p.randomState + 1u);                                   // random.glsl:10
+            alpha = c.w;
+            for (uint32_t s = 0; s < p.sampleSkip; s++) { uint32_t t = base + alpha_to_u32(alpha); alpha = pcg_float(t); }
+            bool rootPass = false;
+            if (p.maxDepth != 0) {
+                const f3 dir = primary_direction(p, x, y);
+                const f3 ri = F3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+                const bool ex = !(fabsf(ri.x) < 3.0e38f && fabsf(ri.y) < 3.0e38f && fabsf(ri.z) < 3.0e38f);
+                const float4 lo = __ldg(p.sc.rootBox), hi = __ldg(p.sc.rootBox + 1);
+                rootPass = box_test(p.cam.origin, dir, ri, ex, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+            }
+            nSamples = p.sampleCount;
+            if (!rootPass) {
+                f3 rgb = F3(c.x, c.y, c.z);
+                uint32_t rng = 0;
+                for (uint32_t s = 0; s < p.sampleCount; s++) {
+                    rng = base + alpha_to_u32(alpha);                                       // :350
+                    alpha = pcg_float(rng);                                                 // nextRandom :352 -> alpha :372
+                    const f3 col = F3(0.f, 0.f, 0.f) + F3(0.f, 0.f, 0.f) * F3(1.f, 1.f, 1.f);   // :278-279,284
+                    rgb = col + rgb;
+                }
+                if (p.maxDepth != 0) nRays = p.sampleCount;
+                p.image[idx] = make_float4(rgb.x, rgb.y, rgb.z, alpha);                     // imageStore :374
+                if (p.rngOut && p.lastPass) p.rngOut[idx] = rng;
+                if (p.hitPrim && p.firstPass) { p.hitPrim[idx] = 0xFFFFFFFFu; if (p.hitT) p.hitT[idx] = 0.0f; }
+            } else {
+                activePixel = true;
+            }
+        }
+    }
+    // warp-aggregated append to the active list
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, activePixel);
+    if (bal) {
+        const unsigned lane = threadIdx.x & 31;
+        uint32_t slot = 0;
+        if (lane == (unsigned)(__ffs(bal) - 1)) slot = atomicAdd(p.activeCount, (unsigned)__popc(bal));
+        slot = __shfl_sync(0xFFFFFFFFu, slot, __ffs(bal) - 1) + __popc(bal & ((1u << lane) - 1u));
+        if (activePixel) {
+            p.activePix[slot] = idx;
+            for (uint32_t s = 0; s < p.sampleCount; s++) {
+                p.sampleBuf[(size_t)s * p.slotCapacity + slot] = make_float4(0.f, 0.f, 0.f, alpha);
+                uint32_t t = base + alpha_to_u32(alpha);
+                alpha = pcg_float(t);
+            }
+        }
+    }
+    if (COUNT) {
+        unsigned long long v[2] = { nRays, nSamples };
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            unsigned long long t = v[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, off);
+            v[i] = t;
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (v[0]) { atomicAdd(p.counters + 0, v[0]); atomicAdd(p.counters + 1, v[0]); }   // rays, node visits (root only)
+            if (v[1]) atomicAdd(p.counters + 5, v[1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Accumulate, one thread per active pixel: rgb = colour_s + rgb for s in order (main() :372), alpha = end of the chain.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wave_accumulate_kernel(const TraceParams p) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= *p.activeCount) return;
+    const uint32_t idx = p.activePix[slot];
+    const uint32_t x = idx % p.W, y = global_row(p, idx / p.W);
+    const float4 c = p.image[idx];
+    f3 rgb = F3(c.x, c.y, c.z);
+    float alphaIn = 0.f;
+    for (uint32_t s = 0; s < p.sampleCount; s++) {
+        const float4 e = p.sampleBuf[(size_t)s * p.slotCapacity + slot];
+        rgb = F3(e.x, e.y, e.z) + rgb;                                                       // pixelColor + currentColor.xyz
+        alphaIn = e.w;
+    }
+    uint32_t t = (600u * x + y) * (p.randomState + 1u) + alpha_to_u32(alphaIn);
+    const float alphaOut = pcg_float(t);                                                     // nextRandom of the last sample
+    p.image[idx] = make_float4(rgb.x, rgb.y, rgb.z, alphaOut);                               // imageStore :374
+}
+
 template <bool COUNT, bool EXT>
 __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kernel(const TraceParams p) {
     __shared__ WaveSmem sm;
@@ -73,15 +191,18 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
     const unsigned lane = tid & 31;
     const TraceScene& sc = p.sc;
     const uint32_t leafOffset = sc.N - 1;
-    const uint32_t totalWork = p.tilesX * p.tilesY * (TILE_W * TILE_H);
+    const uint32_t activeCount = *p.activeCount;
+    // item i -> group of 32 active pixels g = i / (32 * S), sample s = (i % (32 * S)) / 32, pixel slot g * 32 + i % 32:
+    // the 32 items a warp pulls together are the same sample of 32 neighbouring pixels (coherent primary rays)
+    const uint32_t groupItems = 32u * p.sampleCount;
+    const uint64_t totalWork = (uint64_t)((activeCount + 31u) / 32u) * groupItems;
     const float T_MIN_RAY = 0.001f, T_MAX_RAY = 10000000.0f;                    // sceneHit :268-269
 
     // ---- per-lane state -------------------------------------------------------------------------------------------
-    bool dead = false, havePixel = false, rayActive = false, travDone = true, exactOnly = false, hit = false;
-    uint32_t x = 0, y = 0, base = 0, k = 0, depth = 0, rng = 0;
-    size_t px = 0;
-    float alpha = 0.f, nextRandom = 0.f;
-    f3 rgb = F3(0, 0, 0), color = F3(0, 0, 0), att = F3(1, 1, 1), primDir = F3(0, 0, 1);
+    bool dead = false, rayActive = false, travDone = true, exactOnly = false, hit = false;
+    uint32_t depth = 0, rng = 0, pix = 0, smp = 0;
+    size_t slotIndex = 0;
+    f3 color = F3(0, 0, 0), att = F3(1, 1, 1);
     f3 o = F3(0, 0, 0), d = F3(0, 0, 1), rinv = F3(0, 0, 0);
     float closest = T_MAX_RAY;
     Hit rec; rec.t = 0.f; rec.normal = F3(0, 0, 0); rec.mat = 0; rec.prim = 0; rec.back = 0;
@@ -91,7 +212,6 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
     uint32_t lstack[STACK_DEPTH - SSTACK];
     unsigned err = 0;
     Tally tl = { 0, 0, 0, 0, 0 };
-    unsigned long long samplesDone = 0;
 
     auto push = [&](uint32_t v) {
         if (sp < SSTACK) sm.stack[sp][tid] = v;
@@ -111,11 +231,12 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
     while (true) {
         // =========================================== S: shade / generate =========================================
         while (!dead && (!rayActive || (travDone && qCount == 0))) {
+            bool needItem = !rayActive;
             if (rayActive) {                                              // the ray is finished: rayColor loop body :283-307
                 rayActive = false;
-                if (k == 0 && depth == 0 && p.hitPrim) {
-                    p.hitPrim[px] = hit ? rec.prim : 0xFFFFFFFFu;
-                    if (p.hitT) p.hitT[px] = hit ? rec.t : 0.0f;
+                if (depth == 0 && smp == 0 && p.firstPass && p.hitPrim) {
+                    p.hitPrim[pix] = hit ? rec.prim : 0xFFFFFFFFu;
+                    if (p.hitT) p.hitT[pix] = hit ? rec.t : 0.0f;
                 }
                 bool pathEnd = true;
                 if (!hit) {
@@ -141,77 +262,33 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
                     depth++;
                     if (depth >= p.maxDepth) pathEnd = true;               // for (i < maxRayTraceDepth) :282
                 }
-                if (pathEnd) {                                            // main() :372-374 for this sample
-                    rgb = color + rgb;
-                    alpha = nextRandom;
-                    k++;
-                    depth = 0xFFFFFFFFu;                                  // marks "start a new sample"
-                    if (k == p.sampleCount) {
-                        p.image[px] = make_float4(rgb.x, rgb.y, rgb.z, alpha);
-                        if (p.rngOut) p.rngOut[px] = rng;
-                        if (COUNT) samplesDone += p.sampleCount;
-                        havePixel = false;
-                    }
+                if (pathEnd) {                                            // this sample's pixelColor is final
+                    float4* e = p.sampleBuf + slotIndex;
+                    e->x = color.x; e->y = color.y; e->z = color.z;       // .w keeps the sample's incoming alpha
+                    if (p.rngOut && p.lastPass && smp + 1 == p.sampleCount) p.rngOut[pix] = rng;
+                    needItem = true;
                 }
-            } else {
-                depth = 0xFFFFFFFFu;
             }
-            if (depth == 0xFFFFFFFFu) {                                   // need a primary ray
-                if (!havePixel) {                                         // lane-granular persistent threads: next pixel
-                    const unsigned act = __activemask();
-                    const int leader = __ffs(act) - 1;
-                    uint32_t idx = 0;
-                    if ((int)lane == leader) idx = atomicAdd(p.workCounter, (unsigned)__popc(act));
-                    idx = __shfl_sync(act, idx, leader) + __popc(act & ((1u << lane) - 1u));
-                    if (idx >= totalWork) { dead = true; break; }
-                    const uint32_t tile = idx / (TILE_W * TILE_H), within = idx % (TILE_W * TILE_H);
-                    const uint32_t tx = tile % p.tilesX, ty = tile / p.tilesX;
-                    x = tx * TILE_W + (within % TILE_W);
-                    const uint32_t j = ty * TILE_H + (within / TILE_W);
-                    y = ((j / p.bandRows) * p.bandStep + p.bandFirst) * p.bandRows + (j % p.bandRows);
-                    if (x >= p.W || j >= p.localRows || y >= p.H) continue;               // padding of the tile grid
-                    px = (size_t)j * p.W + x;
-                    const float4 c = p.image[px];                                          // imageLoad :349
-                    base = (600u * x + y) * (p.randomState + 1u);                          // random.glsl:10
-                    alpha = c.w;
-                    for (uint32_t s = 0; s < p.sampleSkip; s++) {                          // fast-forward the seed chain
-                        uint32_t t = base + alpha_to_u32(alpha);
-                        alpha = pcg_float(t);
-                    }
-                    // getRay :329-342 (no jitter: the same for every sample) + rayColor's own normalize :280
-                    const f3 pixelSample = (p.cam.pixel00 + (float)x * p.cam.deltaU) + (float)y * p.cam.deltaV;
-                    primDir = normalize(normalize(pixelSample - p.cam.origin));
-                    rgb = F3(c.x, c.y, c.z);
-                    k = 0;
-                    // The primary ray is the same for every sample of the pixel, so its test against the root box is loop
-                    // invariant.  If it fails (or the bounce loop is empty), every sample is: seed, one random(), colour 0.
-                    bool rootPass = false;
-                    if (p.maxDepth != 0) {
-                        const f3 ri = F3(1.0f / primDir.x, 1.0f / primDir.y, 1.0f / primDir.z);
-                        const bool ex = !(fabsf(ri.x) < 3.0e38f && fabsf(ri.y) < 3.0e38f && fabsf(ri.z) < 3.0e38f);
-                        const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
-                        rootPass = box_test(p.cam.origin, primDir, ri, ex, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
-                    }
-                    if (!rootPass) {
-                        for (uint32_t s = 0; s < p.sampleCount; s++) {
-                            rng = base + alpha_to_u32(alpha);                              // :350
-                            alpha = pcg_float(rng);                                        // nextRandom :352 -> alpha :372
-                            const f3 col = F3(0.f, 0.f, 0.f) + F3(0.f, 0.f, 0.f) * F3(1.f, 1.f, 1.f);   // :278-279,284
-                            rgb = col + rgb;
-                        }
-                        if (COUNT) { samplesDone += p.sampleCount; if (p.maxDepth != 0) { tl.rays += p.sampleCount; tl.visits += p.sampleCount; } }
-                        p.image[px] = make_float4(rgb.x, rgb.y, rgb.z, alpha);
-                        if (p.rngOut) p.rngOut[px] = rng;
-                        if (p.hitPrim) { p.hitPrim[px] = 0xFFFFFFFFu; if (p.hitT) p.hitT[px] = 0.0f; }
-                        continue;                                                          // next pixel
-                    }
-                    havePixel = true;
-                }
-                rng = base + alpha_to_u32(alpha);                                          // :350 (stepRNG :351 is a no-op)
-                nextRandom = pcg_float(rng);                                               // :352
+            if (needItem) {                                               // lane-granular persistent threads: next (pixel, sample)
+                const unsigned act = __activemask();
+                const int leader = __ffs(act) - 1;
+                unsigned long long i = 0;
+                if ((int)lane == leader) i = atomicAdd(p.workCounter64, (unsigned long long)__popc(act));
+                i = __shfl_sync(act, i, leader) + (unsigned long long)__popc(act & ((1u << lane) - 1u));
+                if (i >= totalWork) { dead = true; break; }
+                const uint32_t g = (uint32_t)(i / groupItems), r = (uint32_t)(i % groupItems);
+                const uint32_t slot = g * 32u + (r & 31u);
+                if (slot >= activeCount) continue;                        // padding of the last group
+                smp = r >> 5;
+                pix = p.activePix[slot];
+                slotIndex = (size_t)smp * p.slotCapacity + slot;
+                const uint32_t x = pix % p.W, y = global_row(p, pix / p.W);
+                const float alphaIn = p.sampleBuf[slotIndex].w;
+                rng = (600u * x + y) * (p.randomState + 1u) + alpha_to_u32(alphaIn);       // random.glsl:10 + :350 (:351 is a no-op)
+                (void)pcg_float(rng);                                                      // nextRandom :352 (kept by the pre-pass)
                 color = F3(0.f, 0.f, 0.f); att = F3(1.f, 1.f, 1.f);
                 depth = 0;
-                o = p.cam.origin; d = primDir;
+                o = p.cam.origin; d = primary_direction(p, x, y);
             }
             // ---- start the ray (hitBVH prologue :196-201 + the root's own box test) ----
             rayActive = true; hit = false; closest = T_MAX_RAY;
@@ -287,9 +364,9 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
 
     if (err) atomicOr(p.errFlag, err);
     if (COUNT) {
-        unsigned long long v[6] = { tl.rays, tl.visits, tl.tri, tl.sph, tl.mat, samplesDone };
+        unsigned long long v[5] = { tl.rays, tl.visits, tl.tri, tl.sph, tl.mat };
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
+        for (int i = 0; i < 5; i++) {
             unsigned long long s = v[i];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL, s, off);
@@ -310,23 +387,36 @@ static int wave_blocks_per_sm(bool count, bool ext) {
     return nb > 0 ? nb : 1;
 }
 
-void launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, int smCount) {
-    p.tilesX = (p.W + TILE_W - 1) / TILE_W;
-    p.tilesY = (p.localRows + TILE_H - 1) / TILE_H;
-    const uint64_t numWarps = (uint64_t)p.tilesX * p.tilesY;
-    uint64_t grid = (uint64_t)smCount * wave_blocks_per_sm(count, ext);     // persistent: resident CTAs per SM x SMs
-    const uint64_t need = (numWarps + WAVE_THREADS / 32 - 1) / (WAVE_THREADS / 32);
-    if (grid > need) grid = need;
-    if (grid == 0) return;
+// One S2 submission = ceil(sampleCount / samplesPerPass) passes of { pre-pass, trace, accumulate }.  Returns #launches.
+int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, int smCount, uint32_t samplesPerPass) {
     if (p.tMin == 0) p.tMin = T_MIN_DEFAULT;
-    cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), st);
-    if (count) {
-        if (ext) trace_wave_kernel<true, true><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
-        else trace_wave_kernel<true, false><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
-    } else {
-        if (ext) trace_wave_kernel<false, true><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
-        else trace_wave_kernel<false, false><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
+    const uint32_t pixels = p.W * p.localRows;
+    const uint32_t totalSamples = p.sampleCount, skip0 = p.sampleSkip;
+    const int blocksPerSm = wave_blocks_per_sm(count, ext);
+    int launches = 0;
+    for (uint32_t first = 0; first < totalSamples; first += samplesPerPass) {
+        p.sampleCount = (totalSamples - first < samplesPerPass) ? totalSamples - first : samplesPerPass;
+        p.sampleSkip = first == 0 ? skip0 : 0;                              // later passes continue from the image's alpha
+        p.firstPass = first == 0;
+        p.lastPass = first + p.sampleCount >= totalSamples;
+        cudaMemsetAsync(p.workCounter64, 0, 16, st);                        // work counter + active-pixel count
+        if (count) wave_prepass_kernel<true><<<(pixels + 255) / 256, 256, 0, st>>>(p);
+        else wave_prepass_kernel<false><<<(pixels + 255) / 256, 256, 0, st>>>(p);
+        // persistent grid: resident CTAs per SM x SM count, never more lanes than work items in the worst case
+        uint64_t grid = (uint64_t)smCount * blocksPerSm;
+        const uint64_t need = ((uint64_t)pixels * p.sampleCount + WAVE_THREADS - 1) / WAVE_THREADS;
+        if (grid > need) grid = need;
+        if (count) {
+            if (ext) trace_wave_kernel<true, true><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
+            else trace_wave_kernel<true, false><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
+        } else {
+            if (ext) trace_wave_kernel<false, true><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
+            else trace_wave_kernel<false, false><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
+        }
+        wave_accumulate_kernel<<<(pixels + 255) / 256, 256, 0, st>>>(p);
+        launches += 3;
     }
+    return launches;
 }
 
 }  // namespace rtb
