@@ -193,6 +193,9 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on stdout; keep stdout to the one JSON line the contract asks for
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so VERSION is raised to WARN)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "rtb200_nccl_%h_%p.log"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU oracle)")
