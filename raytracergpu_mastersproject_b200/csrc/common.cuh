@@ -65,6 +65,17 @@ __device__ __forceinline__ void pin_sincos(float x, float& s, float& c) {
     if ((k + 1) & 2) c = -c;
 }
 
+// 256-bit read-only global load (sm_100 LDG.E.256): one instruction per 32-byte sector instead of two LDG.128 -- halves the
+// L1TEX wavefronts of the divergent node fetch, which is the unit the trace kernel saturates (profiles/r01_wave_kernel_ncu.txt)
+struct __align__(32) f8 { float4 lo, hi; };
+__device__ __forceinline__ f8 ldg256(const void* p) {
+    f8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+}
+
 // ---- traversal records (what the trace kernel fetches; derived from the reference-layout arrays) --------
 // One 64-byte, 64-byte-aligned record per INTERNAL node i in [0, N-2]: both child boxes + both child indices,
 // so one visit = four LDG.128 from two adjacent 32-byte sectors.  Leaves need no record: child index

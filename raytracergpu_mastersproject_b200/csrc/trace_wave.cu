@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
             if (can) {
                 if (cur != 0xFFFFFFFFu) {
                     const float4* pr = sc.pairs + 4ull * cur;
-                    const float4 lLo = __ldg(pr), lHi = __ldg(pr + 1), rLo = __ldg(pr + 2), rHi = __ldg(pr + 3);
+                    const f8 nl = ldg256(pr), nr = ldg256(pr + 2);          // 64-byte record = two 256-bit loads
+                    const float4 lLo = nl.lo, lHi = nl.hi, rLo = nr.lo, rHi = nr.hi;
                     if (COUNT) tl.visits += 2;
                     const uint32_t li = __float_as_uint(lLo.w), ri = __float_as_uint(lHi.w);
                     int fR = box_filter(o, rinv, rLo.x, rLo.y, rLo.z, rHi.x, rHi.y, rHi.z);
@@ -338,14 +339,26 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
                     tail = (tail + (enqR ? 1u : 0u)) & (QCAP - 1);
                     if (enqL) sm.queue[tail][tid] = li - leafOffset;
                     qCount += (enqR ? 1u : 0u) + (enqL ? 1u : 0u);
-                    if (pushL) push(li);
+                    // push: predicated shared-memory store; the local-memory levels (sp >= SSTACK) are a cold branch
+                    if (pushL && sp < SSTACK) sm.stack[sp][tid] = li;
+                    if (pushL && sp >= SSTACK) {
+                        if (sp < STACK_DEPTH) lstack[sp - SSTACK] = li; else err |= 1u;
+                    }
+                    sp += (pushL && sp < STACK_DEPTH) ? 1 : 0;
                     cur = goR ? ri : (goL ? li : 0xFFFFFFFFu);
                 }
-                while (cur == 0xFFFFFFFFu && qCount < QCAP) {              // resume from the stack (usually 0 or 1 turns)
-                    if (sp == 0) { travDone = true; break; }
-                    const uint32_t e = pop();
-                    if (e >= leafOffset) enqueue(e - leafOffset); else cur = e;
-                }
+                // resume from the stack: one predicated pop per turn (a popped leaf is queued and the lane pops again next turn)
+                const bool needPop = cur == 0xFFFFFFFFu && qCount < QCAP;
+                if (needPop && sp == 0) travDone = true;
+                const bool doPop = needPop && sp > 0;
+                uint32_t e = 0;
+                if (doPop && sp <= SSTACK) e = sm.stack[sp - 1][tid];
+                if (doPop && sp > SSTACK) e = lstack[sp - 1 - SSTACK];
+                sp -= doPop ? 1 : 0;
+                const bool popLeaf = doPop && e >= leafOffset;
+                if (popLeaf) sm.queue[(qHead + qCount) & (QCAP - 1)][tid] = e - leafOffset;
+                qCount += popLeaf ? 1u : 0u;
+                if (doPop && !popLeaf) cur = e;
             }
         }
 
