@@ -308,9 +308,17 @@ __global__ void __launch_bounds__(256) pack_prims_kernel(const float4* __restric
     if (i < T) {
         const float4 a = tris[4ull * i], b = tris[4ull * i + 1], c = tris[4ull * i + 2];
         const uint4 idx = *reinterpret_cast<const uint4*>(tris + 4ull * i + 3);
-        ptris[3ull * i] = make_float4(a.x, a.y, a.z, __uint_as_float(idx.x));
-        ptris[3ull * i + 1] = make_float4(b.x, b.y, b.z, 0.f);
-        ptris[3ull * i + 2] = make_float4(c.x, c.y, c.z, 0.f);
+        // ray-independent prologue of triangleHit (raytraceBVH.comp:119-125), same operation order
+        const f3 v0 = xyz(a);
+        const f3 u = xyz(b) - v0;
+        const f3 v = xyz(c) - v0;
+        const f3 nU = cross(u, v);
+        const f3 n = normalize(nU);
+        const f3 w = nU / dot(nU, nU);
+        ptris[4ull * i] = make_float4(v0.x, v0.y, v0.z, __uint_as_float(idx.x));
+        ptris[4ull * i + 1] = make_float4(n.x, n.y, n.z, u.x);
+        ptris[4ull * i + 2] = make_float4(u.y, u.z, v.x, v.y);
+        ptris[4ull * i + 3] = make_float4(v.z, w.x, w.y, w.z);
     }
     if (i < S) {
         const float4 c = sphs[2ull * i];

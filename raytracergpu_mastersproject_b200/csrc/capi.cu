@@ -105,7 +105,7 @@ Camera make_camera(const rtb_ubo* ubo, uint32_t W, uint32_t H) {
 int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tris, const void* sphs, const void* mats, const void* nodes) {
     const uint32_t N = T + S;
     if (ensure(c, c->pairs, sizeof(float4) * 4ull * (N > 1 ? N - 1 : 1))) return 1;
-    if (ensure(c, c->ptris, sizeof(float4) * 3ull * T)) return 1;
+    if (ensure(c, c->ptris, sizeof(float4) * 4ull * T)) return 1;
     if (ensure(c, c->psphs, sizeof(float4) * (size_t)S)) return 1;
     if (ensure(c, c->psphMat, sizeof(uint32_t) * (size_t)S)) return 1;
     if (ensure(c, c->pmats, sizeof(float4) * (size_t)M)) return 1;

@@ -86,13 +86,14 @@ struct __align__(16) PairNode {
     float4 rLo;   // right child box min.xyz , w unused
     float4 rHi;   // right child box max.xyz , w unused
 };
-// packed triangle: 3 x float4 = 48 B : (v0.xyz, bits(materialIndex)), (v1.xyz, 0), (v2.xyz, 0)
+// packed triangle: 4 x float4 = 64 B : (v0.xyz, bits(materialIndex)) (n.xyz, u.x) (u.yz, v.xy) (v.z, w.xyz) with u = v1-v0,
+//                  v = v2-v0, n = normalize(cross(u,v)), w = cross(u,v)/dot(cross,cross): triangleHit's ray-independent prologue
 // packed sphere  : 1 x float4        : (center.xyz, radius) + u32 materialIndex in a side array
 // packed material: 1 x float4        : (albedo.xyz, bits(materialType))
 
 struct TraceScene {
     const float4* __restrict__ pairs;    // [N-1][4]
-    const float4* __restrict__ tris;     // [T][3]
+    const float4* __restrict__ tris;     // [T][4]
     const float4* __restrict__ sphs;     // [S]
     const uint32_t* __restrict__ sphMat; // [S]
     const float4* __restrict__ mats;     // [M]

@@ -31,17 +31,19 @@ __device__ __forceinline__ bool box_hit(const f3 o, const f3 d, const float lox,
     return tNear < tFar;
 }
 
-// triangleHit, raytraceBVH.comp:118-149
+// triangleHit, raytraceBVH.comp:118-149.  The ray-independent part of the shader's function -- u, v, the normalised normal
+// and w = N / dot(N, N) (:120-125) -- is evaluated once per triangle by pack_prims_kernel with the shader's operation
+// order and fetched here as one 64-byte record (two 256-bit loads); the ray-dependent part is the shader's, verbatim.
 __device__ __forceinline__ bool triangle_hit(const TraceScene& sc, const uint32_t idx, const f3 o, const f3 d, const float tMin,
                                              const float tMax, Hit& rec) {
-    const float4 a = __ldg(sc.tris + 3ull * idx), b = __ldg(sc.tris + 3ull * idx + 1), c = __ldg(sc.tris + 3ull * idx + 2);
-    const f3 v0 = xyz(a);
-    const f3 u = xyz(b) - v0;
-    const f3 v = xyz(c) - v0;
-    const f3 nU = cross(u, v);
-    const f3 n = normalize(nU);
+    const float4* tp = sc.tris + 4ull * idx;
+    const f8 r0 = ldg256(tp), r1 = ldg256(tp + 2);
+    const f3 v0 = xyz(r0.lo);
+    const f3 n = xyz(r0.hi);
+    const f3 u = F3(r0.hi.w, r1.lo.x, r1.lo.y);
+    const f3 v = F3(r1.lo.z, r1.lo.w, r1.hi.x);
+    const f3 w = F3(r1.hi.y, r1.hi.z, r1.hi.w);
     const float D = dot(n, v0);
-    const f3 w = nU / dot(nU, nU);
     const float denom = dot(n, d);
     if (fabsf(denom) < 0.0001f) return false;
     const float t = (D - dot(n, o)) / denom;
@@ -55,7 +57,7 @@ __device__ __forceinline__ bool triangle_hit(const TraceScene& sc, const uint32_
     const int back = dot(d, n) > 0 ? 1 : 0;
     rec.normal = (float)(1 - 2 * back) * n;
     rec.back = back;
-    rec.mat = __float_as_uint(a.w);
+    rec.mat = __float_as_uint(r0.lo.w);
     return true;
 }
 
