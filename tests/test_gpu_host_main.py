@@ -1,0 +1,44 @@
+"""GPU: the C++20 host mirror (host/rtb200_main = the reference's main.cpp shape: Raytracer{} + mainLoop()) renders the
+default scene headless; its frame must equal the oracle's resolve of the same frame bit for bit."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MAIN = os.path.join(ROOT, "raytracergpu_mastersproject_b200", "host", "rtb200_main")
+
+
+def _read_ppm(path):
+    data = open(path, "rb").read()
+    parts = data.split(b"\n", 3)
+    assert parts[0] == b"P6"
+    w, h = map(int, parts[1].split())
+    return np.frombuffer(parts[3], np.uint8).reshape(h, w, 3)
+
+
+@pytest.mark.parametrize("spec,w,h", [("complexScene", 160, 120), ("cornellBoxScene", 96, 96)])
+def test_cpp_host_frame_matches_oracle(tmp_path, spec, w, h):
+    from raytracergpu_mastersproject_b200 import make_ubo, scenes
+    scenes.build()
+    r = subprocess.run([MAIN, spec, str(w), str(h)], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Total BVH Build Time" in r.stdout
+    got = _read_ppm(tmp_path / "frame.ppm")
+    # the host seeds std::mt19937 with Config::Headless::RandomState = 12345 and draws randomState = gen() once per frame
+    random_state = int.from_bytes(np.random.RandomState(12345).bytes(4), "little")
+    sc = scenes.load_scene(spec)
+    ubo = make_ubo(len(sc["triangles"]), len(sc["spheres"]), len(sc["materials"]), sc["max_depth"], random_state, sc["vfov"])
+    b = O.build_bvh(sc["models"], sc["triangles"], sc["spheres"])
+    img = O.raytrace(ubo, w, h, b["tris"], b["sphs"], sc["materials"], b["nodes"], sc["rays_per_pixel"], want_hits=False, want_rng=False)["image"]
+    ref = O.resolve_rgba8(img, sc["rays_per_pixel"])[..., :3]
+    assert np.array_equal(got, ref)
+
+
+def test_cpp_host_reports_errors(tmp_path):
+    r = subprocess.run([MAIN, "noSuchScene"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "unknown scene" in r.stderr
