@@ -59,8 +59,11 @@ enum {
     RTB_TRACE_COUNT = 1u << 0,          /* instrumented variant: fill `counters` (same traversal, same results) */
     RTB_TRACE_EXT_MATERIALS = 1u << 1,  /* extension N1: metal / dielectric scatter (NOT reference behaviour) */
     RTB_TRACE_ENCLOSING_INF = 1u << 2,  /* build option: enclosing-AABB locals start at +-inf instead of pin U4 (0.0) */
-    RTB_TRACE_SIMPLE_KERNEL = 1u << 3   /* run the straightforward one-lane-one-pixel kernel (trace.cu) instead of the
+    RTB_TRACE_SIMPLE_KERNEL = 1u << 3,  /* run the straightforward one-lane-one-pixel kernel (trace.cu) instead of the
                                            warp-coherent one (trace_wave.cu); same results, kept for A/B measurements */
+    RTB_TRACE_LINEAR_SCAN = 1u << 4     /* the NON-BVH program (Config::Programs::Raytracer): raytrace.comp's sceneHit loops
+                                           over all triangles then all spheres (raytrace.comp:167-190), background
+                                           (0.1,0.1,0.3) (:43).  Needs no BVH: bind with nodes = NULL. */
 };
 
 /* Device-side work counters (u64 each), see DESIGN.md "roofline": rays = hitBVH calls, nodeVisits = nodes
@@ -144,7 +147,7 @@ int rtb_clear_image(rtb_ctx* ctx, void* image, uint32_t width, uint32_t rows);
  * triangles / spheres, materials and the reference-layout node array, and derives the 16-byte-aligned
  * traversal records the kernel actually fetches (DESIGN.md "data layout"). */
 int rtb_bind_trace_buffers(rtb_ctx* ctx, const rtb_ubo* ubo, const void* triangles, const void* spheres,
-                           const void* materials, const void* nodes);
+                           const void* materials, const void* nodes /* NULL for the non-BVH program (Raytracer.cpp:394-538) */);
 /* recordComputeS2CommandBuffer + submit (RaytracerBVH.cpp:998-1050): all samples of args->sampleCount in
  * one persistent launch; bit-identical to sampleCount dispatches of raytraceBVH.comp. */
 int rtb_raytrace(rtb_ctx* ctx, const rtb_ubo* ubo, void* image, const rtb_trace_args* args);

@@ -43,7 +43,7 @@ class Counters(C.Structure):
 
 
 class Options(C.Structure):
-    _fields_ = [("enclosingInitInf", C.c_int), ("extMaterials", C.c_int), ("threads", C.c_int)]
+    _fields_ = [("enclosingInitInf", C.c_int), ("extMaterials", C.c_int), ("threads", C.c_int), ("linearScan", C.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -135,8 +135,8 @@ def max_threads(): return int(lib().orc_max_threads())
 
 
 # ---------------------------------------------------------------- S1
-def make_options(enclosing_init_inf=False, ext_materials=False, threads=0):
-    return Options(int(enclosing_init_inf), int(ext_materials), int(threads))
+def make_options(enclosing_init_inf=False, ext_materials=False, threads=0, linear_scan=False):
+    return Options(int(enclosing_init_inf), int(ext_materials), int(threads), int(linear_scan))
 
 
 def model_to_world(models, tris, sphs):
@@ -207,7 +207,7 @@ def raytrace(ubo, W, H, tris_w, sphs_w, mats, nodes, spp, rows=None, image=None,
     opt = opt or make_options()
     ubo = _c(ubo, UBO)
     rc = lib().orc_raytrace(_p(ubo), _p(image), W, H, y0, y1, _p(_c(tris_w, TRIANGLE)), _p(_c(sphs_w, SPHERE)),
-                            _p(_c(mats, MATERIAL)), _p(_c(nodes, NODE)), spp, C.addressof(opt),
+                            _p(_c(mats, MATERIAL)), _p(_c(nodes, NODE)) if nodes is not None else None, spp, C.addressof(opt),
                             _p(hit_prim), _p(hit_t), _p(rng), C.addressof(cnt))
     if rc != 0:
         raise RuntimeError("oracle: traversal stack overflow (MAX_STACK_DEPTH 128)")

@@ -349,9 +349,12 @@ typedef struct {
     const OrcTriangle* tris; const OrcSphere* sphs; const OrcMaterial* mats; const OrcNode* nodes;
     v3 camPos, pixel00, pixelDeltaU, pixelDeltaV;
     int extMaterials;
+    int linearScan;         /* 1: raytrace.comp (the non-BVH program): loop over all primitives */
+    v3 background;          /* _BACKGROUND_COLOR: raytraceBVH.comp:52 = 0 ; raytrace.comp:43 = (0.1, 0.1, 0.3) */
+    uint32_t leafOffset;
 } TraceCtx;
 
-typedef struct { uint64_t rays, nodeVisits, triTests, sphTests, matReads; int stackOverflow; uint32_t lastLeaf; } TraceStats;
+typedef struct { uint64_t rays, nodeVisits, triTests, sphTests, matReads; int stackOverflow; uint32_t lastPrim; } TraceStats;
 
 static v3 point_on_ray(const Ray* r, float t) { return vadd(r->origin, vscale(t, r->direction)); }   /* :84-86 */
 
@@ -428,10 +431,10 @@ static int hit_bvh(const TraceCtx* c, const Ray* r, float tMin, float tMax, HitR
             if (node.leftIndex == 0 && node.rightIndex == 0) {       /* leaf */
                 if (node.primitiveType == ORC_SPHERE) {
                     st->sphTests++;
-                    if (sphere_hit(c, node.primitiveIndex, r, tMin, closestSoFar, rec)) { hit = 1; closestSoFar = rec->t; st->lastLeaf = currentNodeIndex; }
+                    if (sphere_hit(c, node.primitiveIndex, r, tMin, closestSoFar, rec)) { hit = 1; closestSoFar = rec->t; st->lastPrim = currentNodeIndex - c->leafOffset; }
                 } else if (node.primitiveType == ORC_TRIANGLE) {
                     st->triTests++;
-                    if (triangle_hit(c, node.primitiveIndex, r, tMin, closestSoFar, rec)) { hit = 1; closestSoFar = rec->t; st->lastLeaf = currentNodeIndex; }
+                    if (triangle_hit(c, node.primitiveIndex, r, tMin, closestSoFar, rec)) { hit = 1; closestSoFar = rec->t; st->lastPrim = currentNodeIndex - c->leafOffset; }
                 }
                 if (toVisitOffset == 0) break;
                 currentNodeIndex = stack[--toVisitOffset];
@@ -447,7 +450,26 @@ static int hit_bvh(const TraceCtx* c, const Ray* r, float tMin, float tMax, HitR
     }
     return hit;
 }
-static int scene_hit(const TraceCtx* c, const Ray* r, HitRecord* rec, TraceStats* st) {    /* :267-274 */
+/* sceneHit of the non-BVH program, raytrace.comp:167-190: all triangles in index order, then all spheres */
+static int scene_hit_linear(const TraceCtx* c, const Ray* r, HitRecord* rec, TraceStats* st) {
+    const float tMin = 0.001f, tMax = 10000000.0f;
+    HitRecord temp;
+    memset(&temp, 0, sizeof(temp));
+    int hitAny = 0;
+    float closestSoFar = tMax;
+    st->rays++;
+    for (uint32_t i = 0; i < c->ubo->numTriangles; i++) {
+        st->triTests++;
+        if (triangle_hit(c, i, r, tMin, closestSoFar, &temp)) { hitAny = 1; closestSoFar = temp.t; *rec = temp; st->lastPrim = i; }
+    }
+    for (uint32_t i = 0; i < c->ubo->numSpheres; i++) {
+        st->sphTests++;
+        if (sphere_hit(c, i, r, tMin, closestSoFar, &temp)) { hitAny = 1; closestSoFar = temp.t; *rec = temp; st->lastPrim = c->ubo->numTriangles + i; }
+    }
+    return hitAny;
+}
+static int scene_hit(const TraceCtx* c, const Ray* r, HitRecord* rec, TraceStats* st) {    /* raytraceBVH.comp:267-274 */
+    if (c->linearScan) return scene_hit_linear(c, r, rec, st);
     return hit_bvh(c, r, 0.001f, 10000000.0f, rec, st);
 }
 
@@ -496,9 +518,9 @@ static v3 ray_color(const TraceCtx* c, const Ray* rIn, RngCtx* rng, TraceStats* 
     Ray curr; curr.origin = rIn->origin; curr.direction = vnormalize(rIn->direction);
     for (uint32_t i = 0; i < c->ubo->maxRayTraceDepth; i++) {
         int hit = scene_hit(c, &curr, &rec, st);
-        if (i == 0 && firstLeaf) { *firstLeaf = hit ? st->lastLeaf : 0xFFFFFFFFu; if (firstT) *firstT = hit ? rec.t : 0.0f; }
+        if (i == 0 && firstLeaf) { *firstLeaf = hit ? st->lastPrim : 0xFFFFFFFFu; if (firstT) *firstT = hit ? rec.t : 0.0f; }
         if (!hit) {
-            color = vadd(color, vmul(V3(0, 0, 0), globalAttenuation));         /* _BACKGROUND_COLOR = 0 (:52) */
+            color = vadd(color, vmul(c->background, globalAttenuation));        /* _BACKGROUND_COLOR * globalAttenuation (:284) */
             break;
         }
         const OrcMaterial* m = &c->mats[rec.materialIndex];
@@ -564,9 +586,11 @@ int orc_raytrace(const OrcUBO* ubo, float* rgba, uint32_t W, uint32_t H, uint32_
     memset(&c, 0, sizeof(c));
     c.ubo = ubo; c.tris = tris; c.sphs = sphs; c.mats = mats; c.nodes = nodes;
     c.extMaterials = opt ? opt->extMaterials : 0;
+    c.linearScan = opt ? opt->linearScan : 0;
+    c.background = c.linearScan ? V3(0.1f, 0.1f, 0.3f) : V3(0, 0, 0);
     setup_camera(&c, W, H);
     const uint32_t N = ubo->numTriangles + ubo->numSpheres;
-    const uint32_t leafOffset = N - 1;
+    c.leafOffset = N - 1;
     uint64_t rays = 0, visits = 0, tt = 0, stt = 0, mr = 0;
     int overflow = 0;
     int threads = (opt && opt->threads > 0) ? opt->threads : orc_max_threads();
@@ -592,7 +616,7 @@ int orc_raytrace(const OrcUBO* ubo, float* rgba, uint32_t W, uint32_t H, uint32_
                 uint32_t leaf = 0xFFFFFFFFu; float ft = 0.0f;
                 v3 color = ray_color(&c, &r, &rng, &st, (s == 0) ? &leaf : NULL, &ft);
                 px[0] = color.x + cur[0]; px[1] = color.y + cur[1]; px[2] = color.z + cur[2]; px[3] = nextRandom;
-                if (s == 0 && hitPrim) hitPrim[(uint64_t)y * W + x] = (leaf == 0xFFFFFFFFu) ? leaf : leaf - leafOffset;
+                if (s == 0 && hitPrim) hitPrim[(uint64_t)y * W + x] = leaf;
                 if (s == 0 && hitT) hitT[(uint64_t)y * W + x] = ft;
                 if (rngOut && s + 1 == spp) rngOut[(uint64_t)y * W + x] = rng.rng;
                 rays += st.rays; visits += st.nodeVisits; tt += st.triTests; stt += st.sphTests; mr += st.matReads;

@@ -58,6 +58,7 @@ typedef struct {
     int enclosingInitInf;   /* 0: pin U4 (uninitialised localMin/localMax read as 0.0); 1: +-inf */
     int extMaterials;       /* 0: reference behaviour (metal/dielectric absorb, D4); 1: extension N1 */
     int threads;            /* OpenMP threads for orc_raytrace (0 = all) */
+    int linearScan;         /* 0: BVH program (raytraceBVH.comp); 1: non-BVH program (raytrace.comp, nodes unused) */
 } OrcOptions;
 
 /* ---- RNG (shaders/include/random.glsl:10-27) ---- */

@@ -45,7 +45,7 @@ struct rtb_ctx {
     // the bound raytrace set: traversal records derived from the reference-layout arrays
     Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag;
     Scratch activePix, sampleBuf;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
-    bool bound = false;
+    bool bound = false, boundNodes = false;
     uint32_t bT = 0, bS = 0, bM = 0, bN = 0;
 };
 
@@ -112,10 +112,10 @@ int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tr
     if (ensure(c, c->rootBox, sizeof(float4) * 2)) return 1;
     if (ensure(c, c->workCounter, 16)) return 1;
     if (ensure(c, c->errFlag, 16)) return 1;
-    launch_pack_pairs(c->stream, nodes, N, c->pairs.p, c->rootBox.p);
+    if (nodes) launch_pack_pairs(c->stream, nodes, N, c->pairs.p, c->rootBox.p);
     launch_pack_prims(c->stream, tris, T, sphs, S, mats, M, c->ptris.p, c->psphs.p, c->psphMat.p, c->pmats.p);
     if (check_launch(c, 2, "pack traversal records")) return 1;
-    c->bound = true; c->bT = T; c->bS = S; c->bM = M; c->bN = N;
+    c->bound = true; c->boundNodes = nodes != nullptr; c->bT = T; c->bS = S; c->bM = M; c->bN = N;
     return 0;
 }
 
@@ -354,7 +354,7 @@ int rtb_clear_image(rtb_ctx* c, void* image, uint32_t width, uint32_t rows) {
 }
 
 int rtb_bind_trace_buffers(rtb_ctx* c, const rtb_ubo* ubo, const void* triangles, const void* spheres, const void* materials, const void* nodes) {
-    REQUIRE(c && ubo && materials && nodes, "rtb_bind_trace_buffers: bad argument");
+    REQUIRE(c && ubo && materials, "rtb_bind_trace_buffers: bad argument");   // nodes == NULL: the non-BVH program's set
     REQUIRE(ubo->numTriangles + ubo->numSpheres > 0, "rtb_bind_trace_buffers: empty scene");
     Activate act(c);
     return bind_internal(c, ubo->numTriangles, ubo->numSpheres, ubo->numMaterials, triangles, spheres, materials, nodes);
@@ -363,6 +363,7 @@ int rtb_bind_trace_buffers(rtb_ctx* c, const rtb_ubo* ubo, const void* triangles
 int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_args* a) {
     REQUIRE(c && ubo && image && a, "rtb_raytrace: bad argument");
     REQUIRE(c->bound, "rtb_raytrace: no buffers bound (call rtb_build_bvh or rtb_bind_trace_buffers first)");
+    REQUIRE(c->boundNodes || (a->flags & RTB_TRACE_LINEAR_SCAN), "rtb_raytrace: no BVH nodes bound; only RTB_TRACE_LINEAR_SCAN can run");
     REQUIRE(ubo->numTriangles == c->bT && ubo->numSpheres == c->bS, "rtb_raytrace: UBO primitive counts differ from the bound set");
     REQUIRE(a->imageWidth && a->imageHeight && a->bandRows && a->bandStep, "rtb_raytrace: bad image / band description");
     REQUIRE(!(a->flags & RTB_TRACE_COUNT) || a->counters, "rtb_raytrace: RTB_TRACE_COUNT needs a counters buffer");
@@ -390,8 +391,9 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     { const char* e = getenv("RTB_WAVE_TMIN"); p.tMin = e ? (uint32_t)atoi(e) : 0u; }   // tuning knob, results unaffected
     const bool count = (a->flags & RTB_TRACE_COUNT) != 0, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;
     int launches = 1;
-    if (a->flags & RTB_TRACE_SIMPLE_KERNEL) {
-        launch_trace(c->stream, p, count, ext, c->smCount);
+    const bool linear = (a->flags & RTB_TRACE_LINEAR_SCAN) != 0;
+    if (linear || (a->flags & RTB_TRACE_SIMPLE_KERNEL)) {
+        launch_trace(c->stream, p, count, ext, linear, c->smCount);
     } else {
         // per-(sample, pixel) colour slots: as many samples per pass as fit the scratch budget (default 4 GiB)
         const size_t pixels = (size_t)a->imageWidth * a->localRows;

@@ -124,6 +124,7 @@ struct TraceParams {
     float4* sampleBuf;                 // [samplesPerPass][slotCapacity]: (colour.xyz, incoming alpha) per (sample, active pixel)
     uint32_t slotCapacity;
     uint32_t firstPass, lastPass;
+    f3 background;                     // _BACKGROUND_COLOR (0 for the BVH program, (0.1,0.1,0.3) for the non-BVH program)
 };
 
 }  // namespace rtb

@@ -16,9 +16,21 @@
 
 namespace rtb {
 
+// sceneHit of the NON-BVH program (raytrace.comp:167-190, the Config::Programs::Raytracer host): every triangle in index
+// order, then every sphere, with the running closest-so-far.  O(N) per ray -- only meaningful for small scenes, and an
+// independent check of the BVH walk's closest hits.
+template <bool COUNT>
+__device__ __forceinline__ bool hit_linear(const TraceScene& sc, const f3 o, const f3 d, const float tMin, const float tMax, Hit& rec, Tally& tl) {
+    bool hit = false;
+    float closest = tMax;
+    if (COUNT) tl.rays++;
+    for (uint32_t g = 0; g < sc.N; g++) leaf_test<COUNT>(sc, g, o, d, tMin, closest, hit, rec, tl);
+    return hit;
+}
+
 constexpr int TRACE_THREADS = 128;
 
-template <bool COUNT, bool EXT>
+template <bool COUNT, bool EXT, bool LINEAR>
 __device__ __forceinline__ f3 ray_color(const TraceParams& p, const f3 origin, const f3 dirIn, uint32_t& rng, Tally& tl, unsigned& err,
                                         uint32_t* firstPrim, float* firstT) {
     const TraceScene& sc = p.sc;
@@ -28,10 +40,11 @@ __device__ __forceinline__ f3 ray_color(const TraceParams& p, const f3 origin, c
     f3 d = normalize(dirIn);                                     // rayColor: unitDir = normalize(r.direction) (:280)
     for (uint32_t depth = 0; depth < p.maxDepth; depth++) {
         Hit rec;
-        const bool hit = hit_bvh<COUNT>(sc, o, d, 0.001f, 10000000.0f, rec, tl, err);     // sceneHit :267-274
+        const bool hit = LINEAR ? hit_linear<COUNT>(sc, o, d, 0.001f, 10000000.0f, rec, tl)
+                                : hit_bvh<COUNT>(sc, o, d, 0.001f, 10000000.0f, rec, tl, err);     // sceneHit :267-274
         if (depth == 0 && firstPrim) { *firstPrim = hit ? rec.prim : 0xFFFFFFFFu; *firstT = hit ? rec.t : 0.0f; }
         if (!hit) {
-            color = color + F3(0.f, 0.f, 0.f) * att;             // _BACKGROUND_COLOR * globalAttenuation (:284)
+            color = color + p.background * att;                  // _BACKGROUND_COLOR * globalAttenuation (:284)
             break;
         }
         const float4 m = __ldg(sc.mats + rec.mat);
@@ -58,7 +71,7 @@ __device__ __forceinline__ f3 ray_color(const TraceParams& p, const f3 origin, c
     return color;
 }
 
-template <bool COUNT, bool EXT>
+template <bool COUNT, bool EXT, bool LINEAR>
 __global__ void __launch_bounds__(TRACE_THREADS) trace_kernel(const TraceParams p) {
     const unsigned lane = threadIdx.x & 31;
     Tally tl = { 0, 0, 0, 0, 0 };
@@ -94,7 +107,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) trace_kernel(const TraceParams 
             const float nextRandom = pcg_float(rng);                                        // :352
             uint32_t fp = 0xFFFFFFFFu; float ft = 0.f;
             const bool wantFirst = (k == 0) && (p.hitPrim != nullptr);
-            const f3 color = ray_color<COUNT, EXT>(p, p.cam.origin, rayDir, rng, tl, err, wantFirst ? &fp : nullptr, &ft);
+            const f3 color = ray_color<COUNT, EXT, LINEAR>(p, p.cam.origin, rayDir, rng, tl, err, wantFirst ? &fp : nullptr, &ft);
             rgb = color + rgb;                                                              // pixelColor + currentColor.xyz :372
             alpha = nextRandom;
             if (wantFirst) { p.hitPrim[px] = fp; if (p.hitT) p.hitT[px] = ft; }
@@ -134,34 +147,33 @@ __global__ void __launch_bounds__(256) resolve_kernel(const float4* __restrict__
     }
 }
 
-int trace_blocks_per_sm(bool count, bool ext) {
+template <bool COUNT, bool EXT, bool LINEAR>
+static void launch_trace_variant(cudaStream_t st, const TraceParams& p, int smCount, uint64_t need) {
     int nb = 0;
-    if (count) {
-        if (ext) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, true>, TRACE_THREADS, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, false>, TRACE_THREADS, 0);
-    } else {
-        if (ext) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, true>, TRACE_THREADS, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, false>, TRACE_THREADS, 0);
-    }
-    return nb > 0 ? nb : 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<COUNT, EXT, LINEAR>, TRACE_THREADS, 0);
+    uint64_t grid = (uint64_t)smCount * (nb > 0 ? nb : 1);   // persistent grid: resident CTAs per SM x SM count
+    if (grid > need) grid = need;
+    trace_kernel<COUNT, EXT, LINEAR><<<(unsigned)grid, TRACE_THREADS, 0, st>>>(p);
 }
 
-void launch_trace(cudaStream_t st, TraceParams p, bool count, bool ext, int smCount) {
+void launch_trace(cudaStream_t st, TraceParams p, bool count, bool ext, bool linear, int smCount) {
     p.tilesX = (p.W + TILE_W - 1) / TILE_W;
     p.tilesY = (p.localRows + TILE_H - 1) / TILE_H;
     const uint64_t numWarps = (uint64_t)p.tilesX * p.tilesY;
-    // persistent grid: resident CTAs per SM x SM count (never more warps than tiles)
-    uint64_t grid = (uint64_t)smCount * trace_blocks_per_sm(count, ext);
     const uint64_t need = (numWarps + TRACE_THREADS / 32 - 1) / (TRACE_THREADS / 32);
-    if (grid > need) grid = need;
-    if (grid == 0) return;
+    if (need == 0) return;
+    p.background = linear ? F3(0.1f, 0.1f, 0.3f) : F3(0.f, 0.f, 0.f);   // raytrace.comp:43 / raytraceBVH.comp:52
     cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), st);
-    if (count) {
-        if (ext) trace_kernel<true, true><<<(unsigned)grid, TRACE_THREADS, 0, st>>>(p);
-        else trace_kernel<true, false><<<(unsigned)grid, TRACE_THREADS, 0, st>>>(p);
-    } else {
-        if (ext) trace_kernel<false, true><<<(unsigned)grid, TRACE_THREADS, 0, st>>>(p);
-        else trace_kernel<false, false><<<(unsigned)grid, TRACE_THREADS, 0, st>>>(p);
+    const int v = (count ? 4 : 0) | (ext ? 2 : 0) | (linear ? 1 : 0);
+    switch (v) {
+    case 0: launch_trace_variant<false, false, false>(st, p, smCount, need); break;
+    case 1: launch_trace_variant<false, false, true>(st, p, smCount, need); break;
+    case 2: launch_trace_variant<false, true, false>(st, p, smCount, need); break;
+    case 3: launch_trace_variant<false, true, true>(st, p, smCount, need); break;
+    case 4: launch_trace_variant<true, false, false>(st, p, smCount, need); break;
+    case 5: launch_trace_variant<true, false, true>(st, p, smCount, need); break;
+    case 6: launch_trace_variant<true, true, false>(st, p, smCount, need); break;
+    default: launch_trace_variant<true, true, true>(st, p, smCount, need); break;
     }
 }
 

@@ -1,15 +1,23 @@
 // Entry point, same shape as the reference's main.cpp:8-21: pick the program at compile time, construct, mainLoop().
-// Only the BVH program is on this build's path; the other two Config::Programs values are out of scope.
+// The BVH program is the hot path; the non-BVH program (Config::Programs::Raytracer) is the "next" row N2; the
+// LogisticMap demo is out of scope.
 #include "Config.hpp"
+#include "Raytracer.hpp"
 #include "RaytracerBVH.hpp"
 
 #include <cstdlib>
 #include <iostream>
+#include <string>
 
 int main(int argc, char** argv) {
 	try {
 		if constexpr (Config::CurrentProgram == Config::Programs::RaytracerBVH) {
-			if (argc > 1) {   // additive: rtb200_main <scene spec> [width height]
+			if (argc > 1 && std::string(argv[1]) == "--non-bvh") {   // additive: run the Config::Programs::Raytracer host instead
+				const u32 w = argc > 4 ? u32(std::atoi(argv[3])) : Config::Headless::Width;
+				const u32 h = argc > 4 ? u32(std::atoi(argv[4])) : Config::Headless::Height;
+				RaytracerRenderer::Raytracer comp{ w, h, argc > 2 ? argv[2] : "complexScene" };
+				comp.mainLoop();
+			} else if (argc > 1) {   // additive: rtb200_main <scene spec> [width height]
 				const u32 w = argc > 3 ? u32(std::atoi(argv[2])) : Config::Headless::Width;
 				const u32 h = argc > 3 ? u32(std::atoi(argv[3])) : Config::Headless::Height;
 				RaytracerBVHRenderer::Raytracer comp{ w, h, argv[1] };
@@ -18,8 +26,11 @@ int main(int argc, char** argv) {
 				RaytracerBVHRenderer::Raytracer comp{};
 				comp.mainLoop();
 			}
+		} else if constexpr (Config::CurrentProgram == Config::Programs::Raytracer) {
+			RaytracerRenderer::Raytracer comp{};
+			comp.mainLoop();
 		} else {
-			std::cerr << "this build only contains Config::Programs::RaytracerBVH\n";
+			std::cerr << "Config::Programs::LogisticMap (the bifurcation-plot demo) is not part of this build\n";
 			return 2;
 		}
 	} catch (const std::exception& e) {

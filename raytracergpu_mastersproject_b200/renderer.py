@@ -184,6 +184,14 @@ class Raytracer:
                                       self._p(self.enclosing), self._p(self.morton1), self._p(self.morton2),
                                       self._p(self.nodes), self._p(self.cinfo), flags))
 
+    # -- the non-BVH program's frame preparation (Raytracer.cpp:394-538): K1 only, then bind without nodes
+    def prepare_linear(self, ubo):
+        u = np.ascontiguousarray(ubo)
+        up = u.ctypes.data_as(C.c_void_p)
+        check(self._lib.rtb_model_to_world(self.device.handle, up, self._p(self.models), self._p(self.triangles), self._p(self.spheres)))
+        check(self._lib.rtb_bind_trace_buffers(self.device.handle, up, self._p(self.triangles), self._p(self.spheres),
+                                               self._p(self.materials), None))
+
     def ensure_image(self, rows: int | None = None):
         rows = self.height if rows is None else rows
         if self.image is None or self.image.instance_count != rows * self.width:

@@ -39,6 +39,23 @@ def test_cpp_host_frame_matches_oracle(tmp_path, spec, w, h):
     assert np.array_equal(got, ref)
 
 
+def test_cpp_non_bvh_host_frame_matches_oracle(tmp_path):
+    """Config::Programs::Raytracer host (K1 + raytrace.comp) on the small simpleScene."""
+    from raytracergpu_mastersproject_b200 import make_ubo, scenes
+    scenes.build()
+    w, h = 64, 64
+    r = subprocess.run([MAIN, "--non-bvh", "simpleScene", str(w), str(h)], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = _read_ppm(tmp_path / "frame.ppm")
+    random_state = int.from_bytes(np.random.RandomState(12345).bytes(4), "little")
+    sc = scenes.load_scene("simpleScene")
+    ubo = make_ubo(len(sc["triangles"]), len(sc["spheres"]), len(sc["materials"]), sc["max_depth"], random_state, sc["vfov"])
+    tw, sw = O.model_to_world(sc["models"], sc["triangles"], sc["spheres"])
+    img = O.raytrace(ubo, w, h, tw, sw, sc["materials"], None, sc["rays_per_pixel"], opt=O.make_options(linear_scan=True),
+                     want_hits=False, want_rng=False)["image"]
+    assert np.array_equal(got, O.resolve_rgba8(img, sc["rays_per_pixel"])[..., :3])
+
+
 def test_cpp_host_reports_errors(tmp_path):
     r = subprocess.run([MAIN, "noSuchScene"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "unknown scene" in r.stderr

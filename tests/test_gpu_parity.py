@@ -234,6 +234,32 @@ def test_extension_materials_bit_exact(device):
     assert nbad == 0, f"{nbad} pixels differ"
 
 
+@pytest.mark.parametrize("cfg", [SCENES[0], SCENES[2], SCENES[4]], ids=lambda c: f"seed{c['seed']}")
+def test_non_bvh_program_bit_exact(device, cfg):
+    """N2: Config::Programs::Raytracer = K1 + raytrace.comp (linear scan over all primitives, background (0.1,0.1,0.3))."""
+    from raytracergpu_mastersproject_b200 import Buffer, capi
+    W, H, spp = 64, 48, 3
+    sc = SU.random_scene(**cfg)
+    ubo = SU.make_ubo(sc, random_state=31 + cfg["seed"])
+    tw, sw = O.model_to_world(sc["models"], sc["triangles"], sc["spheres"])
+    rr = O.raytrace(ubo, W, H, tw, sw, sc["materials"], None, spp, opt=O.make_options(linear_scan=True))
+    rt = _rt(device, W, H)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.prepare_linear(ubo)
+    hp = Buffer(device, 4, W * H); rg = Buffer(device, 4, W * H)
+    rt.clear_image(); rt.counters.zero()
+    rt.raytrace(ubo, spp, flags=capi.TRACE_LINEAR_SCAN | capi.TRACE_COUNT, hit_prim=hp, rng_out=rg)
+    device.wait_idle()
+    img = rt.read_image()
+    assert np.array_equal(_bits(img), _bits(rr["image"]))
+    assert np.array_equal(hp.read(np.uint32).reshape(H, W), rr["hit_prim"])
+    assert np.array_equal(rg.read(np.uint32).reshape(H, W), rr["rng"])
+    assert rt.read_counters() == rr["counters"]
+    # without BVH nodes bound only the linear scan may run
+    with pytest.raises(capi.RtbError):
+        rt.raytrace(ubo, 1)
+
+
 def test_error_behaviour(device):
     """The reference throws std::runtime_error on failed submissions; the C-ABI returns non-zero + message."""
     from raytracergpu_mastersproject_b200 import RtbError, capi

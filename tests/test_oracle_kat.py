@@ -185,6 +185,20 @@ def test_bvh_hits_agree_with_bruteforce_up_to_exact_ties():
     assert differ.mean() < 0.02
 
 
+def test_non_bvh_program_agrees_with_bvh_program_on_primary_hits():
+    """raytrace.comp (linear scan) and raytraceBVH.comp find the same closest primary hit t; the image differs only by the
+    background colour (0.1,0.1,0.3) and by exact-t tie-breaks."""
+    sc = SU.random_scene(24, n_tris=150, n_spheres=15)
+    ubo = SU.make_ubo(sc, max_depth=1)
+    b = O.build_bvh(sc["models"], sc["triangles"], sc["spheres"])
+    a = O.raytrace(ubo, 80, 60, b["tris"], b["sphs"], sc["materials"], b["nodes"], 1)
+    l = O.raytrace(ubo, 80, 60, b["tris"], b["sphs"], sc["materials"], None, 1, opt=O.make_options(linear_scan=True))
+    assert np.array_equal(a["hit_t"].view(np.uint32), l["hit_t"].view(np.uint32))
+    miss = l["hit_prim"] == 0xFFFFFFFF
+    assert np.all(l["image"][miss][:, :3] == np.float32([0.1, 0.1, 0.3])) and np.all(a["image"][miss][:, :3] == 0)
+    assert l["counters"]["nodeVisits"] == 0 and l["counters"]["triTests"] == l["counters"]["rays"] * len(sc["triangles"])
+
+
 def test_alpha_chain_and_accumulation_over_dispatches():
     sc = SU.random_scene(22, n_tris=100, n_spheres=10)
     ubo = SU.make_ubo(sc, random_state=777)
