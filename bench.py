@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", default="wave", choices=["wave", "simple"], help="trace kernel (simple = A/B baseline)")
+    ap.add_argument("--mode", default="exact", choices=["exact", "culled"],
+                    help="exact = the reference's traversal (default, the headline); culled = extension RTB_TRACE_CULLED")
     return ap.parse_args()
 
 
@@ -251,7 +253,8 @@ def run_b200(args):
         d_tris.copy_(d_tris0); d_sphs.copy_(d_sphs0)
         capi.check(L.rtb_clear_image(h, vp(image), W, rows))
         capi.check(L.rtb_build_bvh(h, ubo_p, vp(d_models), vp(d_tris), vp(d_sphs), vp(d_mats), None, None, None, None, None, 0))
-        targs.flags = (capi.TRACE_COUNT if count else 0) | (capi.TRACE_SIMPLE_KERNEL if args.kernel == "simple" else 0)
+        targs.flags = ((capi.TRACE_COUNT if count else 0) | (capi.TRACE_SIMPLE_KERNEL if args.kernel == "simple" else 0)
+                       | (capi.TRACE_CULLED if args.mode == "culled" else 0))
         targs.counters = counters.data_ptr() if count else None
         if trace_events:
             trace_events[0].record(stream)
@@ -396,6 +399,8 @@ def run_b200(args):
                              f"lavapipe unavailable in image"}
         desc["parallelism"] = f"tile{world}: 8-row bands interleaved over {world} rank(s), scene replicated, NCCL all-gather" if world > 1 else "single GPU"
         desc["l2"] = "256 MiB buffer written between timed steps (L2 flush)"
+        if args.mode == "culled":
+            desc["mode"] = "EXTENSION RTB_TRACE_CULLED: segment-box culling on top of the reference traversal (not the headline mode)"
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",

@@ -61,9 +61,12 @@ enum {
     RTB_TRACE_ENCLOSING_INF = 1u << 2,  /* build option: enclosing-AABB locals start at +-inf instead of pin U4 (0.0) */
     RTB_TRACE_SIMPLE_KERNEL = 1u << 3,  /* run the straightforward one-lane-one-pixel kernel (trace.cu) instead of the
                                            warp-coherent one (trace_wave.cu); same results, kept for A/B measurements */
-    RTB_TRACE_LINEAR_SCAN = 1u << 4     /* the NON-BVH program (Config::Programs::Raytracer): raytrace.comp's sceneHit loops
+    RTB_TRACE_LINEAR_SCAN = 1u << 4,    /* the NON-BVH program (Config::Programs::Raytracer): raytrace.comp's sceneHit loops
                                            over all triangles then all spheres (raytrace.comp:167-190), background
                                            (0.1,0.1,0.3) (:43).  Needs no BVH: bind with nodes = NULL. */
+    RTB_TRACE_CULLED = 1u << 5          /* extension, default off: also skip subtrees outside the box of the ray segment
+                                           [tMin, closest] (+ margin).  NOT the reference's traversal (it has no t-interval);
+                                           fewer node visits, results empirically identical (see trace_wave.cu) */
 };
 
 /* Device-side work counters (u64 each), see DESIGN.md "roofline": rays = hitBVH calls, nodeVisits = nodes

@@ -409,7 +409,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
         p.activePix = (uint32_t*)c->activePix.p;
         p.sampleBuf = (float4*)c->sampleBuf.p;
         p.slotCapacity = (uint32_t)pixels;
-        launches = launch_trace_wave(c->stream, p, count, ext, c->smCount, (uint32_t)perPass);
+        launches = launch_trace_wave(c->stream, p, count, ext, (a->flags & RTB_TRACE_CULLED) != 0, c->smCount, (uint32_t)perPass);
     }
     return check_launch(c, launches, "trace kernel");
 }

@@ -183,7 +183,14 @@ __global__ void __launch_bounds__(256) wave_accumulate_kernel(const TraceParams 
     p.image[idx] = make_float4(rgb.x, rgb.y, rgb.z, alphaOut);                               // imageStore :374
 }
 
-template <bool COUNT, bool EXT>
+// CULL (RTB_TRACE_CULLED, default OFF, NOT the reference's traversal): additionally skips children whose box lies outside
+// the axis-aligned box of the ray SEGMENT [tMin, closest-so-far] grown by a safety margin.  The reference visits every
+// box the ray's LINE crosses (raytraceBVH.comp:184-193 has no t-interval); a primitive it would accept has its hit point
+// on that segment and (up to rounding) inside its own leaf box, so skipped subtrees cannot contain an accepted hit as long
+// as the margin exceeds the rounding slack of the intersection tests.  That is an argument, not a proof (sliver triangles
+// stretch the slack), hence a flag: tests/test_gpu_parity.py checks images and hit ids stay bit-identical on the test
+// scenes and bench.py --mode culled reports it as a separate, labelled line.
+template <bool COUNT, bool EXT, bool CULL>
 __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kernel(const TraceParams p) {
     __shared__ WaveSmem sm;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -205,6 +212,13 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
     f3 color = F3(0, 0, 0), att = F3(1, 1, 1);
     f3 o = F3(0, 0, 0), d = F3(0, 0, 1), rinv = F3(0, 0, 0);
     float closest = T_MAX_RAY;
+    f3 segLo = F3(0, 0, 0), segHi = F3(0, 0, 0);      // CULL: box of the ray segment [tMin, closest] + margin
+    auto update_segment = [&]() {
+        const f3 a = o + T_MIN_RAY * d, b = o + closest * d;
+        const float m = 0.05f + 1.0e-4f * fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(b.x)), fmaxf(fabsf(a.y), fabsf(b.y))), fmaxf(fabsf(a.z), fabsf(b.z)));
+        segLo = F3(fminf(a.x, b.x) - m, fminf(a.y, b.y) - m, fminf(a.z, b.z) - m);
+        segHi = F3(fmaxf(a.x, b.x) + m, fmaxf(a.y, b.y) + m, fmaxf(a.z, b.z) + m);
+    };
     Hit rec; rec.t = 0.f; rec.normal = F3(0, 0, 0); rec.mat = 0; rec.prim = 0; rec.back = 0;
     uint32_t cur = 0xFFFFFFFFu;           // internal node to expand next, or NONE
     int sp = 0;
@@ -296,6 +310,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
             rinv = F3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
             exactOnly = !(fabsf(rinv.x) < 3.0e38f && fabsf(rinv.y) < 3.0e38f && fabsf(rinv.z) < 3.0e38f);
             if (COUNT) { tl.rays++; tl.visits++; }
+            if (CULL) update_segment();                                                    // closest = tMax: nothing is culled yet
             const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
             if (box_test(o, d, rinv, exactOnly, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) {
                 if (sc.N == 1) enqueue(0u);                                                // the root is the only leaf
@@ -327,7 +342,11 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
                         fL = box_hit(o, d, lLo.x, lLo.y, lLo.z, lHi.x, lHi.y, lHi.z) ? 1 : 0;
                     }
                     // Reference order (:241-244): the right subtree completely, then the left.  Straight-line bookkeeping:
-                    const bool passR = fR != 0, passL = fL != 0;
+                    bool passR = fR != 0, passL = fL != 0;
+                    if (CULL) {
+                        passR = passR && !(rLo.x > segHi.x || rHi.x < segLo.x || rLo.y > segHi.y || rHi.y < segLo.y || rLo.z > segHi.z || rHi.z < segLo.z);
+                        passL = passL && !(lLo.x > segHi.x || lHi.x < segLo.x || lLo.y > segHi.y || lHi.y < segLo.y || lLo.z > segHi.z || lHi.z < segLo.z);
+                    }
                     const bool leafR = ri >= leafOffset, leafL = li >= leafOffset;
                     const bool goR = passR && !leafR;                      // descend right now
                     const bool enqR = passR && leafR;                      // right child is a leaf: test it first
@@ -370,7 +389,9 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
                 const uint32_t g = sm.queue[qHead][tid];
                 qHead = (qHead + 1) & (QCAP - 1);
                 qCount--;
+                const float before = closest;
                 leaf_test<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl);
+                if (CULL && closest != before) update_segment();
             }
         }
     }
@@ -388,24 +409,20 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
     }
 }
 
-static int wave_blocks_per_sm(bool count, bool ext) {
+template <bool COUNT, bool EXT, bool CULL>
+static void launch_wave_variant(cudaStream_t st, const TraceParams& p, int smCount, uint64_t need) {
     int nb = 0;
-    if (count) {
-        if (ext) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_wave_kernel<true, true>, WAVE_THREADS, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_wave_kernel<true, false>, WAVE_THREADS, 0);
-    } else {
-        if (ext) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_wave_kernel<false, true>, WAVE_THREADS, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_wave_kernel<false, false>, WAVE_THREADS, 0);
-    }
-    return nb > 0 ? nb : 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_wave_kernel<COUNT, EXT, CULL>, WAVE_THREADS, 0);
+    uint64_t grid = (uint64_t)smCount * (nb > 0 ? nb : 1);                 // persistent: resident CTAs per SM x SM count
+    if (grid > need) grid = need;
+    trace_wave_kernel<COUNT, EXT, CULL><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
 }
 
 // One S2 submission = ceil(sampleCount / samplesPerPass) passes of { pre-pass, trace, accumulate }.  Returns #launches.
-int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, int smCount, uint32_t samplesPerPass) {
+int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int smCount, uint32_t samplesPerPass) {
     if (p.tMin == 0) p.tMin = T_MIN_DEFAULT;
     const uint32_t pixels = p.W * p.localRows;
     const uint32_t totalSamples = p.sampleCount, skip0 = p.sampleSkip;
-    const int blocksPerSm = wave_blocks_per_sm(count, ext);
     int launches = 0;
     for (uint32_t first = 0; first < totalSamples; first += samplesPerPass) {
         p.sampleCount = (totalSamples - first < samplesPerPass) ? totalSamples - first : samplesPerPass;
@@ -415,16 +432,17 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, int 
         cudaMemsetAsync(p.workCounter64, 0, 16, st);                        // work counter + active-pixel count
         if (count) wave_prepass_kernel<true><<<(pixels + 255) / 256, 256, 0, st>>>(p);
         else wave_prepass_kernel<false><<<(pixels + 255) / 256, 256, 0, st>>>(p);
-        // persistent grid: resident CTAs per SM x SM count, never more lanes than work items in the worst case
-        uint64_t grid = (uint64_t)smCount * blocksPerSm;
-        const uint64_t need = ((uint64_t)pixels * p.sampleCount + WAVE_THREADS - 1) / WAVE_THREADS;
-        if (grid > need) grid = need;
-        if (count) {
-            if (ext) trace_wave_kernel<true, true><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
-            else trace_wave_kernel<true, false><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
-        } else {
-            if (ext) trace_wave_kernel<false, true><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
-            else trace_wave_kernel<false, false><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
+        const uint64_t need = ((uint64_t)pixels * p.sampleCount + WAVE_THREADS - 1) / WAVE_THREADS;   // never more lanes than items
+        const int v = (count ? 4 : 0) | (ext ? 2 : 0) | (cull ? 1 : 0);
+        switch (v) {
+        case 0: launch_wave_variant<false, false, false>(st, p, smCount, need); break;
+        case 1: launch_wave_variant<false, false, true>(st, p, smCount, need); break;
+        case 2: launch_wave_variant<false, true, false>(st, p, smCount, need); break;
+        case 3: launch_wave_variant<false, true, true>(st, p, smCount, need); break;
+        case 4: launch_wave_variant<true, false, false>(st, p, smCount, need); break;
+        case 5: launch_wave_variant<true, false, true>(st, p, smCount, need); break;
+        case 6: launch_wave_variant<true, true, false>(st, p, smCount, need); break;
+        default: launch_wave_variant<true, true, true>(st, p, smCount, need); break;
         }
         wave_accumulate_kernel<<<(pixels + 255) / 256, 256, 0, st>>>(p);
         launches += 3;

@@ -260,6 +260,30 @@ def test_non_bvh_program_bit_exact(device, cfg):
         rt.raytrace(ubo, 1)
 
 
+@pytest.mark.parametrize("cfg", [SCENES[0], SCENES[1], SCENES[2], SCENES[6]], ids=lambda c: f"seed{c['seed']}")
+def test_culled_extension_matches_exact(device, cfg):
+    """RTB_TRACE_CULLED (extension, not the reference's traversal): same image / hit ids / RNG states as the exact mode on
+    the test scenes, with fewer node visits."""
+    from raytracergpu_mastersproject_b200 import Buffer, capi
+    W, H, spp = 96, 72, 4
+    sc = SU.random_scene(**cfg)
+    ubo = SU.make_ubo(sc, random_state=55 + cfg["seed"])
+    rt = _rt(device, W, H)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.build_bvh(ubo)
+    out = {}
+    for name, fl in (("exact", 0), ("culled", capi.TRACE_CULLED)):
+        hp = Buffer(device, 4, W * H); rg = Buffer(device, 4, W * H)
+        rt.clear_image(); rt.counters.zero()
+        rt.raytrace(ubo, spp, flags=capi.TRACE_COUNT | fl, hit_prim=hp, rng_out=rg)
+        device.wait_idle()
+        out[name] = (rt.read_image(), hp.read(np.uint32), rg.read(np.uint32), rt.read_counters())
+    assert np.array_equal(_bits(out["exact"][0]), _bits(out["culled"][0]))
+    assert np.array_equal(out["exact"][1], out["culled"][1]) and np.array_equal(out["exact"][2], out["culled"][2])
+    assert out["culled"][3]["rays"] == out["exact"][3]["rays"] and out["culled"][3]["matReads"] == out["exact"][3]["matReads"]
+    assert out["culled"][3]["nodeVisits"] <= out["exact"][3]["nodeVisits"]
+
+
 def test_error_behaviour(device):
     """The reference throws std::runtime_error on failed submissions; the C-ABI returns non-zero + message."""
     from raytracergpu_mastersproject_b200 import RtbError, capi
