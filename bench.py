@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", default="wave", choices=["wave", "simple"], help="trace kernel (simple = A/B baseline)")
+    ap.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
+                    help="N > 1: tiles = 8-row bands + all-gather (bit-identical, default); samples = sample ranges + sum-reduce (C5)")
     ap.add_argument("--mode", default="exact", choices=["exact", "culled"],
                     help="exact = the reference's traversal (default, the headline); culled = extension RTB_TRACE_CULLED")
     return ap.parse_args()
@@ -222,8 +224,11 @@ def run_b200(args):
 
     # band sharding of the frame (bit-identical to 1 GPU, tests/test_gpu_parity.py::test_tile_sharding_bit_identical)
     from raytracergpu_mastersproject_b200.sharding import BandLayout, assemble_gathered, single_gpu_layout
-    layout = BandLayout(H, world, BAND_ROWS) if world > 1 else single_gpu_layout(H)
+    by_samples = world > 1 and args.shard == "samples"
+    layout = BandLayout(H, world, BAND_ROWS) if (world > 1 and not by_samples) else single_gpu_layout(H)
     rows, band_rows = layout.local_rows, layout.band_rows
+    from raytracergpu_mastersproject_b200.sharding import sample_range
+    my_first, my_count = sample_range(spp, world, rank) if by_samples else (0, spp)
 
     # resident inputs: pristine model-space arrays + working copies (K1 transforms in place, so every frame starts
     # from the model-space data -- the reference re-uploads it, RaytraceScene.cpp:78-113)
@@ -235,7 +240,7 @@ def run_b200(args):
     d_sphs0 = to_dev(sc["spheres"]) if S else torch.zeros(32, dtype=torch.uint8, device=tdev)
     d_tris = torch.empty_like(d_tris0); d_sphs = torch.empty_like(d_sphs0)
     image = torch.empty((rows, W, 4), dtype=torch.float32, device=tdev)
-    gathered = torch.empty((world, rows, W, 4), dtype=torch.float32, device=tdev) if world > 1 else None
+    gathered = torch.empty((world, rows, W, 4), dtype=torch.float32, device=tdev) if (world > 1 and not by_samples) else None
     final = torch.empty((H, W, 4), dtype=torch.float32, device=tdev) if world > 1 else image
     rgba8 = torch.empty((H, W, 4), dtype=torch.uint8, device=tdev)
     counters = torch.zeros(6, dtype=torch.int64, device=tdev)
@@ -243,8 +248,9 @@ def run_b200(args):
 
     targs = capi.TraceArgs()
     targs.imageWidth, targs.imageHeight, targs.localRows = W, H, rows
-    targs.bandRows, targs.bandFirst, targs.bandStep = band_rows, (rank if world > 1 else 0), (world if world > 1 else 1)
-    targs.sampleSkip, targs.sampleCount, targs.flags = 0, spp, 0
+    tiled = world > 1 and not by_samples
+    targs.bandRows, targs.bandFirst, targs.bandStep = band_rows, (rank if tiled else 0), (world if tiled else 1)
+    targs.sampleSkip, targs.sampleCount, targs.flags = my_first, my_count, 0
 
     vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -261,7 +267,12 @@ def run_b200(args):
         capi.check(L.rtb_raytrace(h, ubo_p, vp(image), C.byref(targs)))
         if trace_events:
             trace_events[1].record(stream)
-        if world > 1:
+        if by_samples:
+            # every rank holds a full-frame partial sum of its sample range: sum the rgb planes onto rank 0 (fp32
+            # re-association -> tolerance, not bit-equality); alpha = end of the seed chain = the last rank's
+            final.copy_(image)
+            dist.reduce(final, dst=0, op=dist.ReduceOp.SUM)
+        elif world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), image.view(-1))
             final.copy_(assemble_gathered(gathered, layout))      # rank r, local band b -> global band b*world + r
         capi.check(L.rtb_resolve_rgba8(h, vp(final), W, H, spp, vp(rgba8)))
@@ -366,7 +377,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (trace) ----
     peak, peak_src = peaks()
-    pix_local = len(layout.owned_rows(rank if world > 1 else 0)) * W
+    pix_local = len(layout.owned_rows(rank if tiled else 0)) * W
     # per launch (this rank): counters of this rank's launch; at N = 1 the all-reduced counters are this rank's
     if world > 1:
         lc = torch.zeros(6, dtype=torch.int64, device=tdev)
@@ -397,7 +408,9 @@ def run_b200(args):
                    "sample": f"full {W}x{H} frame, {s['spp']} of {spp} spp ({s['rays']} rays in {s['t_trace']:.1f} s trace; BVH build "
                              f"{s['t_build']:.2f} s not included); CPU oracle = C restatement of the reference shaders, OpenMP over rows; "
                              f"lavapipe unavailable in image"}
-        desc["parallelism"] = f"tile{world}: 8-row bands interleaved over {world} rank(s), scene replicated, NCCL all-gather" if world > 1 else "single GPU"
+        desc["parallelism"] = ("single GPU" if world == 1 else
+                               f"samples{world}: sample ranges of {spp // world} spp per rank, scene replicated, NCCL sum-reduce" if by_samples else
+                               f"tile{world}: 8-row bands interleaved over {world} rank(s), scene replicated, NCCL all-gather")
         desc["l2"] = "256 MiB buffer written between timed steps (L2 flush)"
         if args.mode == "culled":
             desc["mode"] = "EXTENSION RTB_TRACE_CULLED: segment-box culling on top of the reference traversal (not the headline mode)"
