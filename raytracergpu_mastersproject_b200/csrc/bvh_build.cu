@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) hlbvh_kernel(const float4* __restrict__ t
 // children.  The shader relies on `coherent`; here: L2-scoped loads (__ldcg) + __threadfence() before the
 // counter atomic.  fp min/max of fixed operands (left, right) -> deterministic whatever the arrival order.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinfo, uint32_t n) {
+__global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinfo, uint32_t n, float4* pairs, float4* rootBox) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const uint32_t leafOffset = n - 1;
@@ -273,6 +273,17 @@ __global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinf
         __stcg(reinterpret_cast<float2*>(nd), make_float2(gmin(lx.x, rx.x), gmax(lx.y, rx.y)));
         __stcg(reinterpret_cast<float2*>(nd) + 1, make_float2(gmin(ly.x, ry.x), gmax(ly.y, ry.y)));
         __stcg(reinterpret_cast<float2*>(nd) + 2, make_float2(gmin(lz.x, rz.x), gmax(lz.y, rz.y)));
+        if (pairs) {    // the thread that unions a node holds both child boxes: emit the node's 64-byte traversal record here
+            float4* out = pairs + 4ull * nodeId;
+            out[0] = make_float4(lx.x, ly.x, lz.x, __uint_as_float(ch.x));
+            out[1] = make_float4(lx.y, ly.y, lz.y, __uint_as_float(ch.y));
+            out[2] = make_float4(rx.x, ry.x, rz.x, 0.f);
+            out[3] = make_float4(rx.y, ry.y, rz.y, 0.f);
+            if (nodeId == 0) {
+                rootBox[0] = make_float4(gmin(lx.x, rx.x), gmin(ly.x, ry.x), gmin(lz.x, rz.x), 0.f);
+                rootBox[1] = make_float4(gmax(lx.y, rx.y), gmax(ly.y, ry.y), gmax(lz.y, rz.y), 0.f);
+            }
+        }
         if (nodeId == 0) return;
         __threadfence();
         nodeId = __ldcg(&cinfo[nodeId]).x;
@@ -370,8 +381,8 @@ void launch_hlbvh(cudaStream_t st, const void* tris, uint32_t T, const void* sph
     hlbvh_kernel<<<blocks_for((uint64_t)T + S, 256), 256, 0, st>>>((const float4*)tris, T, (const float4*)sphs, S, c,
                                                                    (uint32_t*)nodes, (uint2*)cinfo);
 }
-void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n) {
-    refit_kernel<<<blocks_for(n, 256), 256, 0, st>>>((uint32_t*)nodes, (uint2*)cinfo, n);
+void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox) {
+    refit_kernel<<<blocks_for(n, 256), 256, 0, st>>>((uint32_t*)nodes, (uint2*)cinfo, n, (float4*)pairs, (float4*)rootBox);
 }
 void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pairs, void* rootBox) {
     const uint32_t work = n > 1 ? n - 1 : 1;

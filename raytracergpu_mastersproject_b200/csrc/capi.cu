@@ -102,7 +102,8 @@ Camera make_camera(const rtb_ubo* ubo, uint32_t W, uint32_t H) {
     return cam;
 }
 
-int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tris, const void* sphs, const void* mats, const void* nodes) {
+int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tris, const void* sphs, const void* mats, const void* nodes,
+                  bool pairsDone = false) {
     const uint32_t N = T + S;
     if (ensure(c, c->pairs, sizeof(float4) * 4ull * (N > 1 ? N - 1 : 1))) return 1;
     if (ensure(c, c->ptris, sizeof(float4) * 4ull * T)) return 1;
@@ -112,7 +113,7 @@ int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tr
     if (ensure(c, c->rootBox, sizeof(float4) * 2)) return 1;
     if (ensure(c, c->workCounter, 16)) return 1;
     if (ensure(c, c->errFlag, 16)) return 1;
-    if (nodes) launch_pack_pairs(c->stream, nodes, N, c->pairs.p, c->rootBox.p);
+    if (nodes && !pairsDone) launch_pack_pairs(c->stream, nodes, N, c->pairs.p, c->rootBox.p);
     launch_pack_prims(c->stream, tris, T, sphs, S, mats, M, c->ptris.p, c->psphs.p, c->psphMat.p, c->pmats.p);
     if (check_launch(c, 2, "pack traversal records")) return 1;
     c->bound = true; c->boundNodes = nodes != nullptr; c->bT = T; c->bS = S; c->bM = M; c->bN = N;
@@ -313,7 +314,7 @@ int rtb_build_hlbvh(rtb_ctx* c, const rtb_ubo* ubo, const void* triangles, const
 int rtb_refit_aabbs(rtb_ctx* c, const rtb_ubo* ubo, void* nodes, void* cinfo) {
     REQUIRE(c && ubo && nodes && cinfo, "rtb_refit_aabbs: bad argument");
     Activate act(c);
-    launch_refit(c->stream, nodes, cinfo, ubo->numTriangles + ubo->numSpheres);
+    launch_refit(c->stream, nodes, cinfo, ubo->numTriangles + ubo->numSpheres, nullptr, nullptr);
     return check_launch(c, 1, "refit_kernel");
 }
 
@@ -340,9 +341,11 @@ int rtb_build_bvh(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void* tria
     launches += launch_radix_sort(c->stream, k0, v0, k1, v1, N, (uint32_t*)c->sortCounts.p);                      // K4
     if (morton1) { launch_morton_repack(c->stream, k0, v0, N, T, morton1); launches++; }
     launch_hlbvh(c->stream, triangles, T, spheres, S, k0, 1, nodes, cinfo); launches++;                           // K5
-    launch_refit(c->stream, nodes, cinfo, N); launches++;                                                         // K6
+    if (ensure(c, c->pairs, sizeof(float4) * 4ull * (N > 1 ? N - 1 : 1))) return 1;
+    if (ensure(c, c->rootBox, sizeof(float4) * 2)) return 1;
+    launch_refit(c->stream, nodes, cinfo, N, N > 1 ? c->pairs.p : nullptr, c->rootBox.p); launches++;            // K6 (+ pair records)
     if (check_launch(c, launches, "BVH build kernels")) return 1;
-    return bind_internal(c, T, S, ubo->numMaterials, triangles, spheres, materials, nodes);
+    return bind_internal(c, T, S, ubo->numMaterials, triangles, spheres, materials, nodes, /*pairsDone=*/N > 1);
 }
 
 // ---- S2 --------------------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ void launch_morton_unpack(cudaStream_t st, const void* morton, uint32_t n, uint3
 void launch_morton_repack(cudaStream_t st, const uint32_t* keys, const uint32_t* vals, uint32_t n, uint32_t T, void* morton);
 void launch_hlbvh(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const uint32_t* codes,
                   uint32_t codeStrideWords, void* nodes, void* cinfo);
-void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n);
+void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox);   // pairs != NULL: also emit traversal records
 void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pairs, void* rootBox);
 void launch_pack_prims(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* mats, uint32_t M,
                        void* ptris, void* psphs, void* sphMat, void* pmats);

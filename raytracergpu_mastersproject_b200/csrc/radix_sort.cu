@@ -3,7 +3,7 @@
 // The reference sorts the MortonPrimitive array by `code` with a stable LSD radix sort, 4 passes x 8 bits, inside ONE
 // 256-thread workgroup (RaytracerBVH.cpp:916), i.e. serially on one SM.  Same algorithm, same pass structure, same
 // (stable) result -- but every pass is spread over the grid:
-//     digit histogram per 4096-element tile  ->  exclusive scan of the [digit][tile] table  ->  stable scatter.
+//     digit histogram per 4096-element tile  ->  per-digit exclusive scan over tiles (one block per digit)  ->  stable scatter.
 // Keys travel as SoA (code, global primitive id); the 12-byte records are (un)packed by bvh_build.cu.
 #include "common.cuh"
 #include "kernels.h"
@@ -29,44 +29,58 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const uint32_t*
     counts[threadIdx.x * numTiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of `total` counters in place, one block (total = 256 * numTiles, a few MB at most)
-__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* counts, uint32_t total) {
-    __shared__ uint32_t warpSums[32];
-    const uint32_t chunk = (total + 1023u) / 1024u;
-    const uint32_t begin = min(threadIdx.x * chunk, total), end = min(begin + chunk, total);
-    uint32_t sum = 0;
-    for (uint32_t i = begin; i < end; i++) sum += counts[i];
-    // block exclusive scan of the 1024 partial sums
+// Exclusive scan of the [digit][tile] table, one block per digit row (rows are contiguous): row d becomes the exclusive
+// prefix over tiles and its total goes to totals[d].  The scatter kernel adds the exclusive prefix over digits itself.
+__global__ void __launch_bounds__(256) sort_scan_kernel(uint32_t* counts, uint32_t numTiles, uint32_t* totals) {
+    __shared__ uint32_t warpSums[8];
+    __shared__ uint32_t carry;
+    uint32_t* row = counts + (size_t)blockIdx.x * numTiles;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= (uint32_t)o) incl += v;
-    }
-    if (lane == 31) warpSums[warp] = incl;
+    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warpSums[lane], wi = w;
+    for (uint32_t base = 0; base < numTiles; base += 256) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t c = i < numTiles ? row[i] : 0u;
+        uint32_t incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-            if (lane >= (uint32_t)o) wi += v;
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += v;
         }
-        warpSums[lane] = wi - w;
+        if (lane == 31) warpSums[warp] = incl;
+        __syncthreads();
+        uint32_t before = carry;
+        for (uint32_t w = 0; w < warp; w++) before += warpSums[w];
+        if (i < numTiles) row[i] = before + incl - c;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = before + incl;
+        __syncthreads();
     }
-    __syncthreads();
-    uint32_t run = warpSums[warp] + incl - sum;
-    for (uint32_t i = begin; i < end; i++) { const uint32_t c = counts[i]; counts[i] = run; run += c; }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
                                                                     uint32_t* keysOut, uint32_t* valsOut, uint32_t n, uint32_t shift,
-                                                                    uint32_t numTiles, const uint32_t* __restrict__ offsets) {
+                                                                    uint32_t numTiles, const uint32_t* __restrict__ offsets,
+                                                                    const uint32_t* __restrict__ totals) {
     __shared__ uint32_t warpCnt[SORT_THREADS / 32][256];
     __shared__ uint32_t binBase[256];
+    __shared__ uint32_t wsum[8];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    binBase[threadIdx.x] = offsets[threadIdx.x * numTiles + blockIdx.x];
+    {   // global start of bin d = (exclusive prefix of the digit totals) + (prefix of this digit over the earlier tiles)
+        const uint32_t t = totals[threadIdx.x];
+        uint32_t incl = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < warp; w++) before += wsum[w];
+        binBase[threadIdx.x] = before + incl - t + offsets[threadIdx.x * numTiles + blockIdx.x];
+    }
     const uint32_t base = blockIdx.x * SORT_TILE;
     for (int k = 0; k < SORT_ITEMS; k++) {
 #pragma unroll
@@ -105,8 +119,8 @@ int launch_radix_sort(cudaStream_t st, uint32_t* keys0, uint32_t* vals0, uint32_
     for (uint32_t pass = 0; pass < 4; pass++) {       // ITERATIONS 4 x BITS_PER_ITERATION 8 (RadixSortSimple.comp:11-12)
         const uint32_t shift = 8u * pass;
         sort_hist_kernel<<<numTiles, SORT_THREADS, 0, st>>>(kin, n, shift, numTiles, counts);
-        sort_scan_kernel<<<1, 1024, 0, st>>>(counts, 256u * numTiles);
-        sort_scatter_kernel<<<numTiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, numTiles, counts);
+        sort_scan_kernel<<<256, 256, 0, st>>>(counts, numTiles, counts + 256ull * numTiles);
+        sort_scatter_kernel<<<numTiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, numTiles, counts, counts + 256ull * numTiles);
         uint32_t* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
@@ -114,7 +128,7 @@ int launch_radix_sort(cudaStream_t st, uint32_t* keys0, uint32_t* vals0, uint32_
 }
 size_t radix_sort_counts_bytes(uint32_t n) {
     const uint32_t numTiles = (n + SORT_TILE - 1) / SORT_TILE;
-    return sizeof(uint32_t) * 256ull * (numTiles ? numTiles : 1);
+    return sizeof(uint32_t) * (256ull * (numTiles ? numTiles : 1) + 256ull);   // [digit][tile] table + 256 digit totals
 }
 
 }  // namespace rtb
