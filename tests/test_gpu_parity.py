@@ -298,3 +298,85 @@ def test_error_behaviour(device):
         rt.raytrace(bad, 1)
     with pytest.raises(RtbError):
         capi.check(capi.lib().rtb_raytrace(device.handle, None, None, None))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# edge cases
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("depth", [0, 1, 2])
+@pytest.mark.parametrize("kernel", ["wave", "simple"])
+def test_shallow_depths(device, depth, kernel):
+    """maxRayTraceDepth 0 (the bounce loop never runs: no rays, colour 0, the alpha chain still advances), 1 and 2."""
+    from raytracergpu_mastersproject_b200 import capi
+    W, H, spp = 40, 30, 3
+    sc = SU.random_scene(41, n_tris=120, n_spheres=10)
+    ubo = SU.make_ubo(sc, max_depth=depth, random_state=3)
+    ref = O.build_bvh(sc["models"], sc["triangles"], sc["spheres"])
+    rr = O.raytrace(ubo, W, H, ref["tris"], ref["sphs"], sc["materials"], ref["nodes"], spp)
+    rt = _rt(device, W, H)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.build_bvh(ubo)
+    rt.clear_image(); rt.counters.zero()
+    rt.raytrace(ubo, spp, flags=capi.TRACE_COUNT | (capi.TRACE_SIMPLE_KERNEL if kernel == "simple" else 0))
+    device.wait_idle()
+    assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"]))
+    assert rt.read_counters() == rr["counters"]
+    if depth == 0:
+        assert rr["counters"]["rays"] == 0 and np.all(rr["image"][..., :3] == 0)
+
+
+@pytest.mark.parametrize("size", [(1, 1), (7, 5), (33, 3), (130, 67)])
+def test_ragged_image_sizes(device, size):
+    """image sizes that are not multiples of the 8x4 work tiles, down to a single pixel"""
+    W, H = size
+    sc = SU.random_scene(42, n_tris=150, n_spheres=12)
+    ubo = SU.make_ubo(sc, random_state=8)
+    ref = O.build_bvh(sc["models"], sc["triangles"], sc["spheres"])
+    rr = O.raytrace(ubo, W, H, ref["tris"], ref["sphs"], sc["materials"], ref["nodes"], 2)
+    rt = _rt(device, W, H)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.build_bvh(ubo)
+    rt.clear_image(); rt.raytrace(ubo, 2); device.wait_idle()
+    assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"]))
+
+
+def test_degenerate_and_extreme_geometry_nan_parity(device):
+    """A zero-area triangle makes the shader's normalize() divide 0 by 0: NaN hits that poison closest-so-far.  Whatever the
+    reference arithmetic does with it (as pinned), the kernels must do the same, bit for bit -- NaN payloads included.
+    Also: a far-away huge triangle (large magnitudes) and a needle triangle."""
+    from raytracergpu_mastersproject_b200 import capi
+    W, H, spp = 48, 36, 3
+    sc = SU.random_scene(43, n_tris=60, n_spheres=6)
+    t = sc["triangles"]
+    t["v1"][10] = t["v0"][10]; t["v2"][10] = t["v0"][10]                        # a point
+    t["v2"][11] = t["v1"][11]                                                     # a segment
+    t["v0"][12, :3] = (-1e5, -1e5, 3e5); t["v1"][12, :3] = (1e5, -1e5, 3e5); t["v2"][12, :3] = (0, 2e5, 3e5)
+    t["v0"][13, :3] = (0.1, 0.2, 0.1); t["v1"][13, :3] = (0.1000001, 0.2, 0.1); t["v2"][13, :3] = (0.1, 0.9, 0.4)
+    ubo = SU.make_ubo(sc, random_state=17)
+    ref = O.build_bvh(sc["models"], t, sc["spheres"])
+    rr = O.raytrace(ubo, W, H, ref["tris"], ref["sphs"], sc["materials"], ref["nodes"], spp)
+    for fl in (0, capi.TRACE_SIMPLE_KERNEL):
+        rt = _rt(device, W, H)
+        rt.update_scene(sc["models"], t, sc["spheres"], sc["materials"])
+        rt.build_bvh(ubo)
+        n = len(t) + len(sc["spheres"])
+        assert rt.nodes.read(O.NODE, 2 * n - 1).tobytes() == ref["nodes"].tobytes()
+        rt.clear_image(); rt.counters.zero()
+        rt.raytrace(ubo, spp, flags=capi.TRACE_COUNT | fl); device.wait_idle()
+        assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"]))
+        assert rt.read_counters() == rr["counters"]
+
+
+def test_empty_and_zero_sample_submissions(device):
+    from raytracergpu_mastersproject_b200 import RtbError, capi
+    sc = SU.random_scene(44, n_tris=20, n_spheres=2)
+    ubo = SU.make_ubo(sc)
+    rt = _rt(device, 16, 16)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    empty = ubo.copy(); empty["numTriangles"] = 0; empty["numSpheres"] = 0
+    with pytest.raises(RtbError, match="empty scene"):
+        rt.build_bvh(empty)
+    rt.build_bvh(ubo)
+    rt.clear_image(); rt.raytrace(ubo, 0); device.wait_idle()          # zero dispatches: the cleared image is untouched
+    img = rt.read_image()
+    assert np.all(img[..., :3] == 0) and np.all(img[..., 3] == 1)
