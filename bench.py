@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (parity / debugging only)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel", default="wave", choices=["wave", "simple"], help="trace kernel (simple = A/B baseline)")
+    ap.add_argument("--kernel", default="wave", choices=["wave", "simple", "stream"], help="trace kernel (A/B switch)")
     ap.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
                     help="N > 1: tiles = 8-row bands + all-gather (bit-identical, default); samples = sample ranges + sum-reduce (C5)")
     ap.add_argument("--mode", default="exact", choices=["exact", "culled"],
@@ -259,7 +259,7 @@ def run_b200(args):
         d_tris.copy_(d_tris0); d_sphs.copy_(d_sphs0)
         capi.check(L.rtb_clear_image(h, vp(image), W, rows))
         capi.check(L.rtb_build_bvh(h, ubo_p, vp(d_models), vp(d_tris), vp(d_sphs), vp(d_mats), None, None, None, None, None, 0))
-        targs.flags = ((capi.TRACE_COUNT if count else 0) | (capi.TRACE_SIMPLE_KERNEL if args.kernel == "simple" else 0)
+        targs.flags = ((capi.TRACE_COUNT if count else 0) | {"simple": capi.TRACE_SIMPLE_KERNEL, "stream": capi.TRACE_STREAM_KERNEL}.get(args.kernel, 0)
                        | (capi.TRACE_CULLED if args.mode == "culled" else 0))
         targs.counters = counters.data_ptr() if count else None
         if trace_events:
@@ -394,7 +394,7 @@ def run_b200(args):
         except Exception:  # noqa: BLE001
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "rtb::trace_wave_kernel" if args.kernel == "wave" else "rtb::trace_kernel", "kernel_ms": trace_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": {"wave": "rtb::trace_wave_kernel", "stream": "rtb::trace_stream_kernel"}.get(args.kernel, "rtb::trace_kernel"), "kernel_ms": trace_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": peak_src,
                 "per_ray": {"node_visits": local_cnt["nodeVisits"] / max(local_cnt["rays"], 1),
                             "tri_tests": local_cnt["triTests"] / max(local_cnt["rays"], 1),

@@ -64,6 +64,8 @@ enum {
     RTB_TRACE_LINEAR_SCAN = 1u << 4,    /* the NON-BVH program (Config::Programs::Raytracer): raytrace.comp's sceneHit loops
                                            over all triangles then all spheres (raytrace.comp:167-190), background
                                            (0.1,0.1,0.3) (:43).  Needs no BVH: bind with nodes = NULL. */
+    RTB_TRACE_STREAM_KERNEL = 1u << 6,  /* run the streaming (wavefront) kernel trace_stream.cu instead of trace_wave.cu; same
+                                           results (A/B switch while both exist) */
     RTB_TRACE_CULLED = 1u << 5          /* extension, default off: also skip subtrees outside the box of the ray segment
                                            [tMin, closest] (+ margin).  NOT the reference's traversal (it has no t-interval);
                                            fewer node visits, results empirically identical (see trace_wave.cu) */

@@ -45,6 +45,7 @@ struct rtb_ctx {
     // the bound raytrace set: traversal records derived from the reference-layout arrays
     Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag;
     Scratch activePix, sampleBuf;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
+    Scratch poolSlot, poolColor, poolAtt, poolOrg, poolDir, poolNrm, poolList, poolCnt;   // streaming kernel: path pool
     bool bound = false, boundNodes = false;
     uint32_t bT = 0, bS = 0, bM = 0, bN = 0;
 };
@@ -166,7 +167,8 @@ int rtb_ctx_destroy(rtb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (Scratch* s : { &c->sortKeys[0], &c->sortKeys[1], &c->sortVals[0], &c->sortVals[1], &c->sortCounts, &c->encRed, &c->enclosing,
                         &c->cinfo, &c->nodes, &c->pairs, &c->ptris, &c->psphs, &c->psphMat, &c->pmats, &c->rootBox, &c->workCounter,
-                        &c->errFlag, &c->activePix, &c->sampleBuf })
+                        &c->errFlag, &c->activePix, &c->sampleBuf, &c->poolSlot, &c->poolColor,
+                        &c->poolAtt, &c->poolOrg, &c->poolDir, &c->poolNrm, &c->poolList, &c->poolCnt })
         release(*s);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -412,7 +414,23 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
         p.activePix = (uint32_t*)c->activePix.p;
         p.sampleBuf = (float4*)c->sampleBuf.p;
         p.slotCapacity = (uint32_t)pixels;
-        launches = launch_trace_wave(c->stream, p, count, ext, (a->flags & RTB_TRACE_CULLED) != 0, c->smCount, (uint32_t)perPass);
+        const bool cull = (a->flags & RTB_TRACE_CULLED) != 0;
+        if ((a->flags & RTB_TRACE_STREAM_KERNEL) && !cull) {
+            // pool of in-flight paths: ~18 paths per resident lane keeps the per-iteration tails short
+            size_t cap = (size_t)c->smCount * 128 * 7 * 18;
+            if (const char* e = getenv("RTB_STREAM_POOL")) cap = (size_t)atoll(e);
+            if (cap > pixels * perPass) cap = pixels * perPass;
+            if (cap < 1024) cap = 1024;
+            if (ensure(c, c->poolSlot, cap * 4) || ensure(c, c->poolColor, cap * 16) || ensure(c, c->poolAtt, cap * 16) ||
+                ensure(c, c->poolOrg, cap * 16) || ensure(c, c->poolDir, cap * 16) || ensure(c, c->poolNrm, cap * 16) ||
+                ensure(c, c->poolList, cap * 4) || ensure(c, c->poolCnt, 16)) return 1;
+            p.pool.slot = (uint32_t*)c->poolSlot.p; p.pool.colorRng = (float4*)c->poolColor.p; p.pool.attDepth = (float4*)c->poolAtt.p;
+            p.pool.org = (float4*)c->poolOrg.p; p.pool.dir = (float4*)c->poolDir.p; p.pool.nrm = (float4*)c->poolNrm.p;
+            p.pool.rayList = (uint32_t*)c->poolList.p; p.pool.cnt = (unsigned int*)c->poolCnt.p; p.pool.capacity = (uint32_t)cap;
+            launches = launch_trace_stream(c->stream, p, count, ext, c->smCount, (uint32_t)perPass);
+        } else {
+            launches = launch_trace_wave(c->stream, p, count, ext, cull, c->smCount, (uint32_t)perPass);
+        }
     }
     return check_launch(c, launches, "trace kernel");
 }

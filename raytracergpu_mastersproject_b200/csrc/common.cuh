@@ -105,6 +105,19 @@ struct Camera {            // raytraceBVH.comp:50-81, hoisted to the host (compu
     f3 origin, pixel00, deltaU, deltaV;
 };
 
+// streaming kernel: pool of in-flight paths (SoA) + the list of rays to trace in the current iteration
+struct StreamPool {
+    uint32_t* slot;        // [P] (sample, active pixel) slot index of the path, 0xFFFFFFFF = empty
+    float4* colorRng;      // [P] (colour.xyz, bits(rng))
+    float4* attDepth;      // [P] (attenuation.xyz, bits(depth))
+    float4* org;           // [P] (ray origin.xyz, hit t)
+    float4* dir;           // [P] (ray direction.xyz, bits(hit primitive) or 0xFFFFFFFF)
+    float4* nrm;           // [P] (hit normal.xyz, bits(material | back << 31))
+    uint32_t* rayList;     // [P] pool indices of the rays of this iteration
+    unsigned int* cnt;     // [4] ray count (parity 0/1), fetch cursor (parity 0/1)
+    uint32_t capacity;
+};
+
 struct TraceParams {
     TraceScene sc;
     Camera cam;
@@ -124,6 +137,7 @@ struct TraceParams {
     float4* sampleBuf;                 // [samplesPerPass][slotCapacity]: (colour.xyz, incoming alpha) per (sample, active pixel)
     uint32_t slotCapacity;
     uint32_t firstPass, lastPass;
+    StreamPool pool;
     f3 background;                     // _BACKGROUND_COLOR (0 for the BVH program, (0.1,0.1,0.3) for the non-BVH program)
 };
 

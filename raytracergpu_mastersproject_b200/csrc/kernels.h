@@ -31,6 +31,7 @@ size_t radix_sort_counts_bytes(uint32_t n);
 // trace.cu
 void launch_trace(cudaStream_t st, TraceParams p, bool count, bool ext, bool linear, int smCount);
 int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int smCount, uint32_t samplesPerPass);   // trace_wave.cu
+int launch_trace_stream(cudaStream_t st, TraceParams p, bool count, bool ext, int smCount, uint32_t samplesPerPass);   // trace_stream.cu
 void launch_clear_image(cudaStream_t st, void* img, size_t pixels, int smCount);
 void launch_resolve(cudaStream_t st, const void* img, size_t pixels, uint32_t rpp, void* out, int smCount);
 

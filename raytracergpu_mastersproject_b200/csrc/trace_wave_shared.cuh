@@ -1,0 +1,215 @@
+// trace_wave_shared.cuh -- pieces shared by the warp-coherent trace kernels (trace_wave.cu, trace_stream.cu): the filtered
+// box test, the per-lane traversal step, and the pre-pass / accumulate kernels of the (pixel, sample) work-item scheme.
+#pragma once
+
+#include "trace_common.cuh"
+
+namespace rtb {
+
+constexpr int SSTACK = 32;                // stack entries kept in shared memory; deeper levels spill to local memory
+constexpr int QCAP = 8;                   // pending-leaf FIFO entries per lane
+constexpr int T_MIN_DEFAULT = 20;         // leave the traverse phase when fewer lanes than this can step
+
+template <int THREADS>
+struct __align__(16) WaveSmem {
+    uint32_t stack[SSTACK][THREADS];   // [level][thread]: conflict-free
+    uint32_t queue[QCAP][THREADS];     // pending-leaf FIFO
+};
+
+// two-sided filter on the reciprocal-multiply slab test; returns 1 = pass, 0 = fail, -1 = undecided
+__device__ __forceinline__ int box_filter(const f3 o, const f3 rinv, const float lox, const float loy, const float loz, const float hix,
+                                          const float hiy, const float hiz) {
+    const float ax = (lox - o.x) * rinv.x, ay = (loy - o.y) * rinv.y, az = (loz - o.z) * rinv.z;
+    const float bx = (hix - o.x) * rinv.x, by = (hiy - o.y) * rinv.y, bz = (hiz - o.z) * rinv.z;
+    const float tNear = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tFar = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    // max / min are monotone, so tNear and tFar inherit the 3-ulp relative error of the products with respect to
+    // THEMSELVES; with the rounding of the subtraction: |diff - (tFar - tNear)_reference| <= 4 ulp * (|tNear| + |tFar|)
+    // = 2.4e-7 * (...).  The filter uses 5e-7 (2x margin) plus an absolute term for the subnormal range.
+    const float e = fmaf(fabsf(tNear) + fabsf(tFar), 5.0e-7f, 1.0e-36f);
+    const float diff = tFar - tNear;
+    if (diff > e) return 1;
+    if (diff < -e) return 0;
+    return -1;                            // too close to call (or inf / NaN): ask the exact test
+}
+
+__device__ __forceinline__ bool box_test(const f3 o, const f3 d, const f3 rinv, const bool exactOnly, const float lox, const float loy,
+                                         const float loz, const float hix, const float hiy, const float hiz) {
+    if (!exactOnly) {
+        const int r = box_filter(o, rinv, lox, loy, loz, hix, hiy, hiz);
+        if (r >= 0) return r != 0;
+    }
+    return box_hit(o, d, lox, loy, loz, hix, hiy, hiz);
+}
+
+// global image row of local row j (rtb_trace_args: interleaved bands)
+__device__ __forceinline__ uint32_t global_row(const TraceParams& p, uint32_t j) {
+    return ((j / p.bandRows) * p.bandStep + p.bandFirst) * p.bandRows + (j % p.bandRows);
+}
+// getRay :329-342 (no jitter: the same for every sample of a pixel) + rayColor's own normalize :280
+__device__ __forceinline__ f3 primary_direction(const TraceParams& p, uint32_t x, uint32_t y) {
+    const f3 pixelSample = (p.cam.pixel00 + (float)x * p.cam.deltaU) + (float)y * p.cam.deltaV;
+    return normalize(normalize(pixelSample - p.cam.origin));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pre-pass, one thread per local pixel: walk the alpha seed chain for the `passCount` samples of this pass.
+//  * primary ray misses the root box (or maxDepth == 0): every sample is "seed, one random(), colour 0" -> finish the pixel here
+//  * otherwise: append the pixel to the active list and park sample s's incoming alpha in slot (s, pixel).w
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(256) wave_prepass_kernel(const TraceParams p) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t x = idx % p.W, j = idx / p.W;
+    unsigned long long nRays = 0, nSamples = 0;
+    bool activePixel = false;
+    uint32_t y = 0, base = 0;
+    float alpha = 0.f;
+    if (j < p.localRows) {
+        y = global_row(p, j);
+        if (y < p.H) {
+            const float4 c = p.image[idx];                                                  // imageLoad :349
+            base = (600u * x + y) * (p.randomState + 1u);                                   // random.glsl:10
+            alpha = c.w;
+            for (uint32_t s = 0; s < p.sampleSkip; s++) { uint32_t t = base + alpha_to_u32(alpha); alpha = pcg_float(t); }
+            bool rootPass = false;
+            if (p.maxDepth != 0) {
+                const f3 dir = primary_direction(p, x, y);
+                const f3 ri = F3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+                const bool ex = !(fabsf(ri.x) < 3.0e38f && fabsf(ri.y) < 3.0e38f && fabsf(ri.z) < 3.0e38f);
+                const float4 lo = __ldg(p.sc.rootBox), hi = __ldg(p.sc.rootBox + 1);
+                rootPass = box_test(p.cam.origin, dir, ri, ex, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+            }
+            nSamples = p.sampleCount;
+            if (!rootPass) {
+                f3 rgb = F3(c.x, c.y, c.z);
+                uint32_t rng = 0;
+                for (uint32_t s = 0; s < p.sampleCount; s++) {
+                    rng = base + alpha_to_u32(alpha);                                       // :350
+                    alpha = pcg_float(rng);                                                 // nextRandom :352 -> alpha :372
+                    const f3 col = F3(0.f, 0.f, 0.f) + F3(0.f, 0.f, 0.f) * F3(1.f, 1.f, 1.f);   // :278-279,284
+                    rgb = col + rgb;
+                }
+                if (p.maxDepth != 0) nRays = p.sampleCount;
+                p.image[idx] = make_float4(rgb.x, rgb.y, rgb.z, alpha);                     // imageStore :374
+                if (p.rngOut && p.lastPass) p.rngOut[idx] = rng;
+                if (p.hitPrim && p.firstPass) { p.hitPrim[idx] = 0xFFFFFFFFu; if (p.hitT) p.hitT[idx] = 0.0f; }
+            } else {
+                activePixel = true;
+            }
+        }
+    }
+    // warp-aggregated append to the active list
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, activePixel);
+    if (bal) {
+        const unsigned lane = threadIdx.x & 31;
+        uint32_t slot = 0;
+        if (lane == (unsigned)(__ffs(bal) - 1)) slot = atomicAdd(p.activeCount, (unsigned)__popc(bal));
+        slot = __shfl_sync(0xFFFFFFFFu, slot, __ffs(bal) - 1) + __popc(bal & ((1u << lane) - 1u));
+        if (activePixel) {
+            p.activePix[slot] = idx;
+            for (uint32_t s = 0; s < p.sampleCount; s++) {
+                p.sampleBuf[(size_t)s * p.slotCapacity + slot] = make_float4(0.f, 0.f, 0.f, alpha);
+                uint32_t t = base + alpha_to_u32(alpha);
+                alpha = pcg_float(t);
+            }
+        }
+    }
+    if (COUNT) {
+        unsigned long long v[2] = { nRays, nSamples };
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            unsigned long long t = v[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, off);
+            v[i] = t;
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (v[0]) { atomicAdd(p.counters + 0, v[0]); atomicAdd(p.counters + 1, v[0]); }   // rays, node visits (root only)
+            if (v[1]) atomicAdd(p.counters + 5, v[1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Accumulate, one thread per active pixel: rgb = colour_s + rgb for s in order (main() :372), alpha = end of the chain.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int UNUSED = 0>
+__global__ void __launch_bounds__(256) wave_accumulate_kernel(const TraceParams p) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= *p.activeCount) return;
+    const uint32_t idx = p.activePix[slot];
+    const uint32_t x = idx % p.W, y = global_row(p, idx / p.W);
+    const float4 c = p.image[idx];
+    f3 rgb = F3(c.x, c.y, c.z);
+    float alphaIn = 0.f;
+    for (uint32_t s = 0; s < p.sampleCount; s++) {
+        const float4 e = p.sampleBuf[(size_t)s * p.slotCapacity + slot];
+        rgb = F3(e.x, e.y, e.z) + rgb;                                                       // pixelColor + currentColor.xyz
+        alphaIn = e.w;
+    }
+    uint32_t t = (600u * x + y) * (p.randomState + 1u) + alpha_to_u32(alphaIn);
+    const float alphaOut = pcg_float(t);                                                     // nextRandom of the last sample
+    p.image[idx] = make_float4(rgb.x, rgb.y, rgb.z, alphaOut);                               // imageStore :374
+}
+
+
+// One traverse-phase turn of one lane: expand the child-pair record of `cur` (two 256-bit loads, two filtered box tests,
+// straight-line queue / stack bookkeeping in the reference's order: right subtree completely, then left,
+// raytraceBVH.comp:241-244), then resume from the stack with at most one predicated pop.
+template <bool COUNT, bool CULL, int THREADS>
+__device__ __forceinline__ void wave_step(const TraceScene& sc, WaveSmem<THREADS>& sm, const unsigned tid, const uint32_t leafOffset,
+                                          const f3 o, const f3 d, const f3 rinv, const bool exactOnly, uint32_t& cur, int& sp,
+                                          const uint32_t qHead, uint32_t& qCount, bool& travDone, uint32_t* lstack, Tally& tl, unsigned& err,
+                                          const f3 segLo, const f3 segHi) {
+    if (cur != 0xFFFFFFFFu) {
+        const float4* pr = sc.pairs + 4ull * cur;
+        const f8 nl = ldg256(pr), nr = ldg256(pr + 2);          // 64-byte record = two 256-bit loads
+        const float4 lLo = nl.lo, lHi = nl.hi, rLo = nr.lo, rHi = nr.hi;
+        if (COUNT) tl.visits += 2;
+        const uint32_t li = __float_as_uint(lLo.w), ri = __float_as_uint(lHi.w);
+        int fR = box_filter(o, rinv, rLo.x, rLo.y, rLo.z, rHi.x, rHi.y, rHi.z);
+        int fL = box_filter(o, rinv, lLo.x, lLo.y, lLo.z, lHi.x, lHi.y, lHi.z);
+        if (exactOnly || (fR | fL) < 0) {                      // rare: some comparison is too close to call
+            fR = box_hit(o, d, rLo.x, rLo.y, rLo.z, rHi.x, rHi.y, rHi.z) ? 1 : 0;
+            fL = box_hit(o, d, lLo.x, lLo.y, lLo.z, lHi.x, lHi.y, lHi.z) ? 1 : 0;
+        }
+        bool passR = fR != 0, passL = fL != 0;
+        if (CULL) {
+            passR = passR && !(rLo.x > segHi.x || rHi.x < segLo.x || rLo.y > segHi.y || rHi.y < segLo.y || rLo.z > segHi.z || rHi.z < segLo.z);
+            passL = passL && !(lLo.x > segHi.x || lHi.x < segLo.x || lLo.y > segHi.y || lHi.y < segLo.y || lLo.z > segHi.z || lHi.z < segLo.z);
+        }
+        const bool leafR = ri >= leafOffset, leafL = li >= leafOffset;
+        const bool goR = passR && !leafR;                      // descend right now
+        const bool enqR = passR && leafR;                      // right child is a leaf: test it first
+        const bool pushL = passL && goR;                       // left waits on the stack until right is done
+        const bool enqL = passL && !goR && leafL;
+        const bool goL = passL && !goR && !leafL;
+        uint32_t tail = (qHead + qCount) & (QCAP - 1);
+        if (enqR) sm.queue[tail][tid] = ri - leafOffset;
+        tail = (tail + (enqR ? 1u : 0u)) & (QCAP - 1);
+        if (enqL) sm.queue[tail][tid] = li - leafOffset;
+        qCount += (enqR ? 1u : 0u) + (enqL ? 1u : 0u);
+        // push: predicated shared-memory store; the local-memory levels (sp >= SSTACK) are a cold branch
+        if (pushL && sp < SSTACK) sm.stack[sp][tid] = li;
+        if (pushL && sp >= SSTACK) {
+            if (sp < STACK_DEPTH) lstack[sp - SSTACK] = li; else err |= 1u;
+        }
+        sp += (pushL && sp < STACK_DEPTH) ? 1 : 0;
+        cur = goR ? ri : (goL ? li : 0xFFFFFFFFu);
+    }
+    // resume from the stack: one predicated pop per turn (a popped leaf is queued and the lane pops again next turn)
+    const bool needPop = cur == 0xFFFFFFFFu && qCount < QCAP;
+    if (needPop && sp == 0) travDone = true;
+    const bool doPop = needPop && sp > 0;
+    uint32_t e = 0;
+    if (doPop && sp <= SSTACK) e = sm.stack[sp - 1][tid];
+    if (doPop && sp > SSTACK) e = lstack[sp - 1 - SSTACK];
+    sp -= doPop ? 1 : 0;
+    const bool popLeaf = doPop && e >= leafOffset;
+    if (popLeaf) sm.queue[(qHead + qCount) & (QCAP - 1)][tid] = e - leafOffset;
+    qCount += popLeaf ? 1u : 0u;
+    if (doPop && !popLeaf) cur = e;
+}
+
+}  // namespace rtb

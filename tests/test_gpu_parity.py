@@ -95,12 +95,12 @@ def test_s1_stage_by_stage(device, cfg):
 
 @pytest.mark.parametrize("cfg", SCENES, ids=lambda c: f"seed{c['seed']}")
 @pytest.mark.parametrize("spp", [1, 5])
-@pytest.mark.parametrize("kernel", ["wave", "simple"])
+@pytest.mark.parametrize("kernel", ["wave", "simple", "stream"])
 def test_frame_bit_exact(device, cfg, spp, kernel):
     """Whole frame (S1 fused + S2): node array, hit ids, RNG states, counters and the fp32 image, all bit-exact.
     Both trace kernels: the production warp-coherent one and the straightforward one kept for A/B measurements."""
     from raytracergpu_mastersproject_b200 import Buffer, capi
-    kflag = capi.TRACE_SIMPLE_KERNEL if kernel == "simple" else 0
+    kflag = {"simple": capi.TRACE_SIMPLE_KERNEL, "stream": capi.TRACE_STREAM_KERNEL}.get(kernel, 0)
     W, H = 96, 72
     sc = SU.random_scene(**cfg)
     ubo = SU.make_ubo(sc, max_depth=8, random_state=12345 + cfg["seed"])
@@ -304,7 +304,7 @@ def test_error_behaviour(device):
 # edge cases
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("depth", [0, 1, 2])
-@pytest.mark.parametrize("kernel", ["wave", "simple"])
+@pytest.mark.parametrize("kernel", ["wave", "simple", "stream"])
 def test_shallow_depths(device, depth, kernel):
     """maxRayTraceDepth 0 (the bounce loop never runs: no rays, colour 0, the alpha chain still advances), 1 and 2."""
     from raytracergpu_mastersproject_b200 import capi
@@ -317,7 +317,7 @@ def test_shallow_depths(device, depth, kernel):
     rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
     rt.build_bvh(ubo)
     rt.clear_image(); rt.counters.zero()
-    rt.raytrace(ubo, spp, flags=capi.TRACE_COUNT | (capi.TRACE_SIMPLE_KERNEL if kernel == "simple" else 0))
+    rt.raytrace(ubo, spp, flags=capi.TRACE_COUNT | {"simple": capi.TRACE_SIMPLE_KERNEL, "stream": capi.TRACE_STREAM_KERNEL}.get(kernel, 0))
     device.wait_idle()
     assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"]))
     assert rt.read_counters() == rr["counters"]
@@ -355,7 +355,7 @@ def test_degenerate_and_extreme_geometry_nan_parity(device):
     ubo = SU.make_ubo(sc, random_state=17)
     ref = O.build_bvh(sc["models"], t, sc["spheres"])
     rr = O.raytrace(ubo, W, H, ref["tris"], ref["sphs"], sc["materials"], ref["nodes"], spp)
-    for fl in (0, capi.TRACE_SIMPLE_KERNEL):
+    for fl in (0, capi.TRACE_SIMPLE_KERNEL, capi.TRACE_STREAM_KERNEL):
         rt = _rt(device, W, H)
         rt.update_scene(sc["models"], t, sc["spheres"], sc["materials"])
         rt.build_bvh(ubo)
