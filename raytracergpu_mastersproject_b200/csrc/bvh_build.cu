@@ -312,6 +312,62 @@ __global__ void __launch_bounds__(256) pack_pairs_kernel(const uint32_t* __restr
     out[3] = make_float4(R[1], R[3], R[5], 0.f);
 }
 
+
+// Compressed traversal records (common.cuh): one thread per internal node.  Quantisation is done with directed rounding so
+// that, as REAL numbers, origin + qlo * scale <= lo and origin + qhi * scale >= hi for every plane of both children.
+__global__ void __launch_bounds__(256) pack_cnodes_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* cnodes, float4* leafBox) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {                                               // exact box of leaf i (input order)
+        const float* b = reinterpret_cast<const float*>(nodes + 10ull * (n - 1 + i));
+        leafBox[2ull * i] = make_float4(b[0], b[2], b[4], 0.f);
+        leafBox[2ull * i + 1] = make_float4(b[1], b[3], b[5], 0.f);
+    }
+    if (n < 2 || i >= n - 1) return;
+    const uint32_t* nd = nodes + 10ull * i;
+    const uint32_t li = nd[6], ri = nd[7];
+    const float* L = reinterpret_cast<const float*>(nodes + 10ull * li);
+    const float* R = reinterpret_cast<const float*>(nodes + 10ull * ri);
+    const uint32_t leafOffset = n - 1;
+    const bool leafL = li >= leafOffset, leafR = ri >= leafOffset;
+    const uint32_t split = leafL ? li - leafOffset : li;       // ConstructHLBVH.comp:180-196: left = split or leafOffset + split
+    float org[3], inv[3];
+    uint32_t E[3], q[12];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float llo = L[2 * k], lhi = L[2 * k + 1], rlo = R[2 * k], rhi = R[2 * k + 1];
+        const float lo = fminf(llo, rlo), hi = fmaxf(lhi, rhi);
+        org[k] = lo;
+        const float ext = __fsub_ru(hi, lo);                   // >= the real extent
+        uint32_t e = 1;                                        // scale = 2^(e - 127); need 255 * scale >= ext
+        if (ext > 0.f) {
+            const uint32_t bits = __float_as_uint(__fdiv_ru(ext, 255.0f));
+            e = (bits >> 23) + ((bits & 0x7FFFFFu) ? 1u : 0u);
+            if (e < 1) e = 1;
+            if (e > 253) e = 253;                              // (only reachable with non-finite boxes)
+        }
+        E[k] = e;
+        inv[k] = __uint_as_float((254u - e) << 23);            // 1 / scale, exact
+        const float dl[2] = { __fsub_rd(llo, lo), __fsub_rd(rlo, lo) };   // <= real (lo_child - origin)
+        const float dh[2] = { __fsub_ru(lhi, lo), __fsub_ru(rhi, lo) };   // >= real (hi_child - origin)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            float ql = floorf(dl[c] * inv[k]); ql = fminf(fmaxf(ql, 0.f), 255.f);
+            float qh = ceilf(dh[c] * inv[k]); qh = fminf(fmaxf(qh, 0.f), 255.f);
+            q[c * 6 + k] = (uint32_t)ql;                       // child c: planes lo.x lo.y lo.z hi.x hi.y hi.z
+            q[c * 6 + 3 + k] = (uint32_t)qh;
+        }
+    }
+    uint4 a, bq;
+    a.x = __float_as_uint(org[0]); a.y = __float_as_uint(org[1]); a.z = __float_as_uint(org[2]);
+    a.w = E[0] | (E[1] << 8) | (E[2] << 16) | ((leafL ? 1u : 0u) << 24) | ((leafR ? 1u : 0u) << 25);
+    bq.x = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+    bq.y = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
+    bq.z = q[8] | (q[9] << 8) | (q[10] << 16) | (q[11] << 24);
+    bq.w = split;
+    cnodes[2ull * i] = a;
+    cnodes[2ull * i + 1] = bq;
+}
+
 __global__ void __launch_bounds__(256) pack_prims_kernel(const float4* __restrict__ tris, uint32_t T, const float4* __restrict__ sphs,
                                                          uint32_t S, const float4* __restrict__ mats, uint32_t M, float4* ptris,
                                                          float4* psphs, uint32_t* sphMat, float4* pmats) {
@@ -387,6 +443,9 @@ void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* p
 void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pairs, void* rootBox) {
     const uint32_t work = n > 1 ? n - 1 : 1;
     pack_pairs_kernel<<<blocks_for(work, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (float4*)pairs, (float4*)rootBox);
+}
+void launch_pack_cnodes(cudaStream_t st, const void* nodes, uint32_t n, void* cnodes, void* leafBox) {
+    pack_cnodes_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)cnodes, (float4*)leafBox);
 }
 void launch_pack_prims(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* mats, uint32_t M,
                        void* ptris, void* psphs, void* sphMat, void* pmats) {

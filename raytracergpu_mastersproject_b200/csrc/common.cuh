@@ -86,6 +86,10 @@ struct __align__(16) PairNode {
     float4 rLo;   // right child box min.xyz , w unused
     float4 rHi;   // right child box max.xyz , w unused
 };
+// Compressed child-pair record, 32 B = ONE 256-bit load (trace_wave_shared.cuh::wave_step_c): origin.xyz (the node's own min
+// corner), one power-of-two scale per axis, both child boxes as 8-bit offsets rounded OUTWARD (conservative), Karras split
+// position + two leaf flags instead of two child indices.  Exactness is restored at the leaves (exact leaf box + exact
+// primitive test): a leaf is tested iff its own exact box passes -- see DESIGN.md "compressed nodes".
 // packed triangle: 4 x float4 = 64 B : (v0.xyz, bits(materialIndex)) (n.xyz, u.x) (u.yz, v.xy) (v.z, w.xyz) with u = v1-v0,
 //                  v = v2-v0, n = normalize(cross(u,v)), w = cross(u,v)/dot(cross,cross): triangleHit's ray-independent prologue
 // packed sphere  : 1 x float4        : (center.xyz, radius) + u32 materialIndex in a side array
@@ -98,6 +102,8 @@ struct TraceScene {
     const uint32_t* __restrict__ sphMat; // [S]
     const float4* __restrict__ mats;     // [M]
     const float4* __restrict__ rootBox;  // [2]: (min.xyz,0) (max.xyz,0) of node 0
+    const uint4* __restrict__ cnodes;    // [N-1][2] 32-byte compressed child-pair records (conservative 8-bit boxes), or null
+    const float4* __restrict__ leafBox;  // [N][2]   exact leaf boxes (min.xyz,0) (max.xyz,0), used with cnodes
     uint32_t T, S, N;
 };
 

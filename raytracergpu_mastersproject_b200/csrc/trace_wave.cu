@@ -46,7 +46,7 @@ constexpr int WAVE_MIN_BLOCKS = 6;
 // as the margin exceeds the rounding slack of the intersection tests.  That is an argument, not a proof (sliver triangles
 // stretch the slack), hence a flag: tests/test_gpu_parity.py checks images and hit ids stay bit-identical on the test
 // scenes and bench.py --mode culled reports it as a separate, labelled line.
-template <bool COUNT, bool EXT, bool CULL>
+template <bool COUNT, bool EXT, bool CULL, bool CN>
 __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kernel(const TraceParams p) {
     __shared__ WaveSmem<WAVE_THREADS> sm;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -184,7 +184,12 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
                 const bool waiting = !dead && !can;                       // lanes that L or S could put back to work
                 if (__any_sync(FULL, waiting)) break;
             }
-            if (can) wave_step<COUNT, CULL>(sc, sm, tid, leafOffset, o, d, rinv, exactOnly, cur, sp, qHead, qCount, travDone, lstack, tl, err, segLo, segHi);
+            if (can) {
+                // CN: 32-byte compressed records; rays with a zero / denormal direction component (reference yields inf / NaN)
+                // keep to the exact 64-byte records
+                if (CN && !exactOnly) wave_step_c<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
+                else wave_step<COUNT, CULL>(sc, sm, tid, leafOffset, o, d, rinv, exactOnly, cur, sp, qHead, qCount, travDone, lstack, tl, err, segLo, segHi);
+            }
         }
 
         // =========================================== L: leaf tests ==============================================
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
                 qHead = (qHead + 1) & (QCAP - 1);
                 qCount--;
                 const float before = closest;
-                leaf_test<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl);
+                if (!CN || exactOnly || leaf_box_passes(sc, g, o, d, rinv, exactOnly)) leaf_test<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl);
                 if (CULL && closest != before) update_segment();
             }
         }
@@ -215,17 +220,18 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
     }
 }
 
-template <bool COUNT, bool EXT, bool CULL>
+template <bool COUNT, bool EXT, bool CULL, bool CN>
 static void launch_wave_variant(cudaStream_t st, const TraceParams& p, int smCount, uint64_t need) {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_wave_kernel<COUNT, EXT, CULL>, WAVE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_wave_kernel<COUNT, EXT, CULL, CN>, WAVE_THREADS, 0);
     uint64_t grid = (uint64_t)smCount * (nb > 0 ? nb : 1);                 // persistent: resident CTAs per SM x SM count
     if (grid > need) grid = need;
-    trace_wave_kernel<COUNT, EXT, CULL><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
+    trace_wave_kernel<COUNT, EXT, CULL, CN><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
 }
 
 // One S2 submission = ceil(sampleCount / samplesPerPass) passes of { pre-pass, trace, accumulate }.  Returns #launches.
-int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int smCount, uint32_t samplesPerPass) {
+int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, bool cn, int smCount, uint32_t samplesPerPass) {
+    if (count || !p.sc.cnodes || p.sc.N < 2) cn = false;   // the instrumented variant counts the reference's visits: exact records
     if (p.tMin == 0) p.tMin = T_MIN_DEFAULT;
     const uint32_t pixels = p.W * p.localRows;
     const uint32_t totalSamples = p.sampleCount, skip0 = p.sampleSkip;
@@ -240,15 +246,24 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool
         else wave_prepass_kernel<false><<<(pixels + 255) / 256, 256, 0, st>>>(p);
         const uint64_t need = ((uint64_t)pixels * p.sampleCount + WAVE_THREADS - 1) / WAVE_THREADS;   // never more lanes than items
         const int v = (count ? 4 : 0) | (ext ? 2 : 0) | (cull ? 1 : 0);
-        switch (v) {
-        case 0: launch_wave_variant<false, false, false>(st, p, smCount, need); break;
-        case 1: launch_wave_variant<false, false, true>(st, p, smCount, need); break;
-        case 2: launch_wave_variant<false, true, false>(st, p, smCount, need); break;
-        case 3: launch_wave_variant<false, true, true>(st, p, smCount, need); break;
-        case 4: launch_wave_variant<true, false, false>(st, p, smCount, need); break;
-        case 5: launch_wave_variant<true, false, true>(st, p, smCount, need); break;
-        case 6: launch_wave_variant<true, true, false>(st, p, smCount, need); break;
-        default: launch_wave_variant<true, true, true>(st, p, smCount, need); break;
+        if (cn) {
+            switch (v) {
+            case 0: launch_wave_variant<false, false, false, true>(st, p, smCount, need); break;
+            case 1: launch_wave_variant<false, false, true, true>(st, p, smCount, need); break;
+            case 2: launch_wave_variant<false, true, false, true>(st, p, smCount, need); break;
+            default: launch_wave_variant<false, true, true, true>(st, p, smCount, need); break;
+            }
+        } else {
+            switch (v) {
+            case 0: launch_wave_variant<false, false, false, false>(st, p, smCount, need); break;
+            case 1: launch_wave_variant<false, false, true, false>(st, p, smCount, need); break;
+            case 2: launch_wave_variant<false, true, false, false>(st, p, smCount, need); break;
+            case 3: launch_wave_variant<false, true, true, false>(st, p, smCount, need); break;
+            case 4: launch_wave_variant<true, false, false, false>(st, p, smCount, need); break;
+            case 5: launch_wave_variant<true, false, true, false>(st, p, smCount, need); break;
+            case 6: launch_wave_variant<true, true, false, false>(st, p, smCount, need); break;
+            default: launch_wave_variant<true, true, true, false>(st, p, smCount, need); break;
+            }
         }
         wave_accumulate_kernel<0><<<(pixels + 255) / 256, 256, 0, st>>>(p);
         launches += 3;

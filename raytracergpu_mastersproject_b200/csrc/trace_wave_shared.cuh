@@ -212,4 +212,85 @@ __device__ __forceinline__ void wave_step(const TraceScene& sc, WaveSmem<THREADS
     if (doPop && !popLeaf) cur = e;
 }
 
+// Traverse-phase turn over the 32-byte COMPRESSED record (one 256-bit load).  Child planes are conservative (outward
+// rounded) 8-bit offsets from the node origin; slab parameters are evaluated as t = q * (scale / dir) + (origin - o) / dir
+// with one FFMA per plane.  A child is skipped only when it is a definite miss even after granting every rounding error
+// (|error| <= 4 ulp * (255 |scale/dir| + |(origin - o)/dir|) per value); everything else is visited.  Leaves
+// that survive are queued as CANDIDATES: the L phase first runs the reference's exact box test on the exact leaf box.
+// Because the reference's box test is monotone under box inclusion, a leaf's exact box passing implies all its ancestors'
+// exact (hence conservative) boxes pass, so the set and order of primitive tests is unchanged.
+template <bool CULL, int THREADS>
+__device__ __forceinline__ void wave_step_c(const TraceScene& sc, WaveSmem<THREADS>& sm, const unsigned tid, const uint32_t leafOffset,
+                                            const f3 o, const f3 rinv, uint32_t& cur, int& sp, const uint32_t qHead, uint32_t& qCount,
+                                            bool& travDone, uint32_t* lstack, unsigned& err, const f3 segLo, const f3 segHi) {
+    if (cur != 0xFFFFFFFFu) {
+        const f8 rec = ldg256(sc.cnodes + 2ull * cur);
+        const uint32_t w3 = __float_as_uint(rec.lo.w), q0 = __float_as_uint(rec.hi.x), q1 = __float_as_uint(rec.hi.y),
+                       q2 = __float_as_uint(rec.hi.z), split = __float_as_uint(rec.hi.w);
+        const float sx = __uint_as_float((w3 & 0xFFu) << 23), sy = __uint_as_float(((w3 >> 8) & 0xFFu) << 23),
+                    sz = __uint_as_float(((w3 >> 16) & 0xFFu) << 23);
+        const float ax = sx * rinv.x, ay = sy * rinv.y, az = sz * rinv.z;                       // exact (power-of-two scaling)
+        const float bx = (rec.lo.x - o.x) * rinv.x, by = (rec.lo.y - o.y) * rinv.y, bz = (rec.lo.z - o.z) * rinv.z;
+        const float m = fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(bx)), fmaf(255.0f, fabsf(ay), fabsf(by))), fmaf(255.0f, fabsf(az), fabsf(bz)));
+        const float tol = -2.0e-6f * m;                                                         // NaN / inf -> nothing is skipped
+#define RTB_Q(w, j) __uint2float_rn(((w) >> (8 * (j))) & 0xFFu)
+        // left child: q0 = lo.x lo.y lo.z hi.x ; q1 = hi.y hi.z | right child: q1 = lo.x lo.y ; q2 = lo.z hi.x hi.y hi.z
+        const float lLx = fmaf(RTB_Q(q0, 0), ax, bx), lLy = fmaf(RTB_Q(q0, 1), ay, by), lLz = fmaf(RTB_Q(q0, 2), az, bz);
+        const float lHx = fmaf(RTB_Q(q0, 3), ax, bx), lHy = fmaf(RTB_Q(q1, 0), ay, by), lHz = fmaf(RTB_Q(q1, 1), az, bz);
+        const float rLx = fmaf(RTB_Q(q1, 2), ax, bx), rLy = fmaf(RTB_Q(q1, 3), ay, by), rLz = fmaf(RTB_Q(q2, 0), az, bz);
+        const float rHx = fmaf(RTB_Q(q2, 1), ax, bx), rHy = fmaf(RTB_Q(q2, 2), ay, by), rHz = fmaf(RTB_Q(q2, 3), az, bz);
+#undef RTB_Q
+        const float lNear = fmaxf(fmaxf(fminf(lLx, lHx), fminf(lLy, lHy)), fminf(lLz, lHz));
+        const float lFar = fminf(fminf(fmaxf(lLx, lHx), fmaxf(lLy, lHy)), fmaxf(lLz, lHz));
+        const float rNear = fmaxf(fmaxf(fminf(rLx, rHx), fminf(rLy, rHy)), fminf(rLz, rHz));
+        const float rFar = fminf(fminf(fmaxf(rLx, rHx), fmaxf(rLy, rHy)), fmaxf(rLz, rHz));
+        bool passL = !((lFar - lNear) < tol), passR = !((rFar - rNear) < tol);
+        if (CULL) {   // conservative planes in world space (a few ulp of slack is covered by the segment margin)
+            const float Lx0 = fmaf(__uint2float_rn(q0 & 0xFFu), sx, rec.lo.x), Lx1 = fmaf(__uint2float_rn(q0 >> 24), sx, rec.lo.x);
+            const float Ly0 = fmaf(__uint2float_rn((q0 >> 8) & 0xFFu), sy, rec.lo.y), Ly1 = fmaf(__uint2float_rn(q1 & 0xFFu), sy, rec.lo.y);
+            const float Lz0 = fmaf(__uint2float_rn((q0 >> 16) & 0xFFu), sz, rec.lo.z), Lz1 = fmaf(__uint2float_rn((q1 >> 8) & 0xFFu), sz, rec.lo.z);
+            const float Rx0 = fmaf(__uint2float_rn((q1 >> 16) & 0xFFu), sx, rec.lo.x), Rx1 = fmaf(__uint2float_rn((q2 >> 8) & 0xFFu), sx, rec.lo.x);
+            const float Ry0 = fmaf(__uint2float_rn(q1 >> 24), sy, rec.lo.y), Ry1 = fmaf(__uint2float_rn((q2 >> 16) & 0xFFu), sy, rec.lo.y);
+            const float Rz0 = fmaf(__uint2float_rn(q2 & 0xFFu), sz, rec.lo.z), Rz1 = fmaf(__uint2float_rn(q2 >> 24), sz, rec.lo.z);
+            passL = passL && !(Lx0 > segHi.x || Lx1 < segLo.x || Ly0 > segHi.y || Ly1 < segLo.y || Lz0 > segHi.z || Lz1 < segLo.z);
+            passR = passR && !(Rx0 > segHi.x || Rx1 < segLo.x || Ry0 > segHi.y || Ry1 < segLo.y || Rz0 > segHi.z || Rz1 < segLo.z);
+        }
+        const bool leafL = (w3 >> 24) & 1u, leafR = (w3 >> 25) & 1u;
+        const uint32_t li = leafL ? leafOffset + split : split, ri = leafR ? leafOffset + split + 1u : split + 1u;
+        const bool goR = passR && !leafR;
+        const bool enqR = passR && leafR;
+        const bool pushL = passL && goR;
+        const bool enqL = passL && !goR && leafL;
+        const bool goL = passL && !goR && !leafL;
+        uint32_t tail = (qHead + qCount) & (QCAP - 1);
+        if (enqR) sm.queue[tail][tid] = split + 1u;                       // primitive id of a leaf = its index - leafOffset
+        tail = (tail + (enqR ? 1u : 0u)) & (QCAP - 1);
+        if (enqL) sm.queue[tail][tid] = split;
+        qCount += (enqR ? 1u : 0u) + (enqL ? 1u : 0u);
+        if (pushL && sp < SSTACK) sm.stack[sp][tid] = li;
+        if (pushL && sp >= SSTACK) {
+            if (sp < STACK_DEPTH) lstack[sp - SSTACK] = li; else err |= 1u;
+        }
+        sp += (pushL && sp < STACK_DEPTH) ? 1 : 0;
+        cur = goR ? ri : (goL ? li : 0xFFFFFFFFu);
+    }
+    const bool needPop = cur == 0xFFFFFFFFu && qCount < QCAP;
+    if (needPop && sp == 0) travDone = true;
+    const bool doPop = needPop && sp > 0;
+    uint32_t e = 0;
+    if (doPop && sp <= SSTACK) e = sm.stack[sp - 1][tid];
+    if (doPop && sp > SSTACK) e = lstack[sp - 1 - SSTACK];
+    sp -= doPop ? 1 : 0;
+    const bool popLeaf = doPop && e >= leafOffset;
+    if (popLeaf) sm.queue[(qHead + qCount) & (QCAP - 1)][tid] = e - leafOffset;
+    qCount += popLeaf ? 1u : 0u;
+    if (doPop && !popLeaf) cur = e;
+}
+
+// the reference's box test on the EXACT box of leaf candidate g (compressed traversal only)
+__device__ __forceinline__ bool leaf_box_passes(const TraceScene& sc, const uint32_t g, const f3 o, const f3 d, const f3 rinv, const bool exactOnly) {
+    const f8 b = ldg256(sc.leafBox + 2ull * g);
+    return box_test(o, d, rinv, exactOnly, b.lo.x, b.lo.y, b.lo.z, b.hi.x, b.hi.y, b.hi.z);
+}
+
 }  // namespace rtb
