@@ -27,7 +27,7 @@
 //
 // Box test: t = (bound - origin) * (1/dir) with the per-ray reciprocal, plus an error filter.  Each product is within
 // 3 ulp of the reference's correctly rounded quotient (bound - origin) / dir, so when |tFar - tNear| exceeds
-// 5e-7 * (|tNear| + |tFar|) the comparison tNear < tFar provably has the reference's outcome; otherwise (and for rays
+// 3e-7 * (|tNear| + |tFar|) the comparison tNear < tFar provably has the reference's outcome; otherwise (and for rays
 // with a zero / denormal direction component, where the reference produces inf / NaN) the exact division path of
 // trace_common.cuh runs.
 // Results are bit-identical either way (tests/test_gpu_parity.py compares images, hit ids, RNG states and visit counters).

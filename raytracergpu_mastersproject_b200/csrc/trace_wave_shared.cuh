@@ -25,8 +25,8 @@ __device__ __forceinline__ int box_filter(const f3 o, const f3 rinv, const float
     const float tFar = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
     // max / min are monotone, so tNear and tFar inherit the 3-ulp relative error of the products with respect to
     // THEMSELVES; with the rounding of the subtraction: |diff - (tFar - tNear)_reference| <= 4 ulp * (|tNear| + |tFar|)
-    // = 2.4e-7 * (...).  The filter uses 5e-7 (2x margin) plus an absolute term for the subnormal range.
-    const float e = fmaf(fabsf(tNear) + fabsf(tFar), 5.0e-7f, 1.0e-36f);
+    // = 2.384e-7 * (...) (second-order terms ~1e-14).  The filter uses 3e-7 plus an absolute term for the subnormal range.
+    const float e = fmaf(fabsf(tNear) + fabsf(tFar), 3.0e-7f, 1.0e-36f);
     const float diff = tFar - tNear;
     if (diff > e) return 1;
     if (diff < -e) return 0;
@@ -170,9 +170,9 @@ __device__ __forceinline__ void wave_step(const TraceScene& sc, WaveSmem<THREADS
         const uint32_t li = __float_as_uint(lLo.w), ri = __float_as_uint(lHi.w);
         int fR = box_filter(o, rinv, rLo.x, rLo.y, rLo.z, rHi.x, rHi.y, rHi.z);
         int fL = box_filter(o, rinv, lLo.x, lLo.y, lLo.z, lHi.x, lHi.y, lHi.z);
-        if (exactOnly || (fR | fL) < 0) {                      // rare: some comparison is too close to call
-            fR = box_hit(o, d, rLo.x, rLo.y, rLo.z, rHi.x, rHi.y, rHi.z) ? 1 : 0;
-            fL = box_hit(o, d, lLo.x, lLo.y, lLo.z, lHi.x, lHi.y, lHi.z) ? 1 : 0;
+        if (exactOnly || (fR | fL) < 0) {                      // rare: some comparison is too close to call -> the reference's divisions
+            if (exactOnly || fR < 0) fR = box_hit(o, d, rLo.x, rLo.y, rLo.z, rHi.x, rHi.y, rHi.z) ? 1 : 0;
+            if (exactOnly || fL < 0) fL = box_hit(o, d, lLo.x, lLo.y, lLo.z, lHi.x, lHi.y, lHi.z) ? 1 : 0;
         }
         bool passR = fR != 0, passL = fL != 0;
         if (CULL) {

@@ -14,7 +14,11 @@ namespace Config {
 	constexpr const bool ShowBufferDebug = 0;
 	constexpr const bool Fake1SecondDelay = 0;
 
+#ifdef RTB_CONFIG_RPP_DEMO                       // build flag of the `rtb200_rppdemo` target (the reference edits this line by hand)
+	constexpr const bool RunRayPerPixelIncreasingDemo = 1;
+#else
 	constexpr const bool RunRayPerPixelIncreasingDemo = 0;
+#endif
 	namespace RayPerPixelIncreasingDemoConfig {
 		constexpr const u32 runsBeforeIncrease = 4;
 		constexpr const u32 startRaysPerPixel = 100;
