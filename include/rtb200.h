@@ -161,6 +161,12 @@ int rtb_bind_trace_buffers(rtb_ctx* ctx, const rtb_ubo* ubo, const void* triangl
 int rtb_raytrace(rtb_ctx* ctx, const rtb_ubo* ubo, void* image, const rtb_trace_args* args);
 /* SingleTriangleFullScreen.frag:13-21 (+ FragmentUniformBufferObject RaytracerBVH.hpp:47-49) -> RGBA8 */
 int rtb_resolve_rgba8(rtb_ctx* ctx, const void* image, uint32_t width, uint32_t rows, uint32_t raysPerPixel, void* outRgba8);
+/* ---- the LogisticMap demo program (Config::Programs::LogisticMap; not part of the render path) ------------------- */
+/* One dispatch of logistic.comp (LogisticMap.cpp:384, bindings: UBO {pixelColor, iteration, width, height}, the (x, r)
+ * point SSBO, an rgba8 storage image that is never cleared): x' = x * r * (1 - x) per point, in place, then
+ * imageStore(int(r / 4 * width), int((1 - x') * height)) = pixelColor. */
+int rtb_logistic_step(rtb_ctx* ctx, void* points /* float2[count] */, uint32_t count, void* imageRgba8, uint32_t width,
+                      uint32_t height, const float* pixelColor /* [4] */);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int rtb_launch_count(rtb_ctx* ctx, uint64_t* count);
 

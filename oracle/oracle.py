@@ -87,6 +87,7 @@ def lib():
         L.orc_primary_hits_bruteforce.argtypes = [vp, u32, u32, vp, vp, vp, vp]
         L.orc_resolve_rgba8.restype = None; L.orc_resolve_rgba8.argtypes = [vp, u32, u32, u32, vp]
         L.orc_max_threads.restype = C.c_int; L.orc_max_threads.argtypes = []
+        L.orc_logistic_step.restype = None; L.orc_logistic_step.argtypes = [vp, u32, vp, u32, u32, vp]
         _lib = L
     return _lib
 
@@ -226,3 +227,10 @@ def resolve_rgba8(image, rays_per_pixel):
     out = np.zeros((H, W, 4), np.uint8)
     lib().orc_resolve_rgba8(_p(np.ascontiguousarray(image, np.float32)), W, H, rays_per_pixel, _p(out))
     return out
+
+
+def logistic_step(points, image_rgba8, pixel_color=(1.0, 1.0, 1.0, 1.0)):
+    """one dispatch of logistic.comp, in place: points float32 [n, 2] = (x, r); image uint8 [H, W, 4]"""
+    H, W, _ = image_rgba8.shape
+    col = np.asarray(pixel_color, np.float32)
+    lib().orc_logistic_step(_p(points), len(points), _p(image_rgba8), W, H, _p(col))

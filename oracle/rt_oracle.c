@@ -669,3 +669,31 @@ void orc_resolve_rgba8(const float* rgba, uint32_t W, uint32_t H, uint32_t raysP
         out[4 * i + 3] = 255;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* K9  logistic.comp:23-35 -- the LogisticMap demo program (Config::Programs::LogisticMap): one step of     */
+/* x' = x * r * (1 - x) per point, then plot the point into an rgba8 image (never cleared between steps).   */
+/* ------------------------------------------------------------------------------------------------ */
+static int f2i_trunc_sat(float f) {            /* GLSL int(float): truncation; out of range / NaN pinned like CUDA F2I */
+    if (f != f) return 0;
+    if (f >= 2147483648.0f) return 2147483647;
+    if (f <= -2147483648.0f) return (int)(-2147483647 - 1);
+    return (int)f;
+}
+void orc_logistic_step(float* points /* (x, r) pairs */, uint32_t count, uint8_t* rgba8, uint32_t W, uint32_t H, const float* pixelColor) {
+    uint8_t c[4];
+    for (int k = 0; k < 4; k++) {              /* rgba8 unorm store of ubo.pixelColor */
+        float v = pixelColor[k];
+        v = (v > 0.0f) ? v : 0.0f; v = (v < 1.0f) ? v : 1.0f;
+        c[k] = (uint8_t)(v * 255.0f + 0.5f);
+    }
+    for (uint32_t i = 0; i < count; i++) {
+        const float x = points[2 * i], r = points[2 * i + 1];
+        const float nx = x * r * (1.0f - x);   /* :29, left to right */
+        points[2 * i] = nx;
+        const int xc = f2i_trunc_sat((r / 4.0f) * (float)W);            /* :31 */
+        const int yc = f2i_trunc_sat(((1 - nx) / 1.0f) * (float)H);     /* :32 */
+        if (xc >= 0 && yc >= 0 && (uint32_t)xc < W && (uint32_t)yc < H)  /* imageStore outside the image is discarded */
+            memcpy(rgba8 + 4 * ((size_t)yc * W + (size_t)xc), c, 4);
+    }
+}

@@ -104,6 +104,8 @@ void orc_primary_hits_bruteforce(const OrcUBO* ubo, uint32_t W, uint32_t H,
 /* fragment resolve: SingleTriangleFullScreen.frag:13-21 -> RGBA8 */
 void orc_resolve_rgba8(const float* rgba, uint32_t W, uint32_t H, uint32_t raysPerPixel, uint8_t* out);
 int  orc_max_threads(void);
+/* LogisticMap demo program, one dispatch of logistic.comp (LogisticMap.cpp:384): points = (x, r) float pairs */
+void orc_logistic_step(float* points, uint32_t count, uint8_t* rgba8, uint32_t W, uint32_t H, const float* pixelColor);
 
 #ifdef __cplusplus
 }

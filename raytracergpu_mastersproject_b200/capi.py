@@ -53,7 +53,7 @@ EXPORTS = [
     "rtb_host_alloc", "rtb_host_free", "rtb_timer_start", "rtb_timer_stop_ms", "rtb_model_to_world",
     "rtb_enclosing_aabb", "rtb_morton_codes", "rtb_sort_morton", "rtb_build_hlbvh", "rtb_refit_aabbs",
     "rtb_build_bvh", "rtb_clear_image", "rtb_bind_trace_buffers", "rtb_raytrace", "rtb_resolve_rgba8",
-    "rtb_launch_count",
+    "rtb_launch_count", "rtb_logistic_step",
 ]
 
 
@@ -119,6 +119,7 @@ def lib():
         "rtb_raytrace": [vp, vp, vp, C.POINTER(TraceArgs)],
         "rtb_resolve_rgba8": [vp, vp, u32, u32, u32, vp],
         "rtb_launch_count": [vp, C.POINTER(C.c_uint64)],
+        "rtb_logistic_step": [vp, vp, u32, vp, u32, u32, vp],
     }
     for name, args in sigs.items():
         fn = getattr(L, name)

@@ -450,6 +450,13 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     return check_launch(c, launches, "trace kernel");
 }
 
+int rtb_logistic_step(rtb_ctx* c, void* points, uint32_t count, void* imageRgba8, uint32_t width, uint32_t height, const float* pixelColor) {
+    REQUIRE(c && points && imageRgba8 && pixelColor && width && height, "rtb_logistic_step: bad argument");
+    Activate act(c);
+    launch_logistic(c->stream, points, count, imageRgba8, width, height, pixelColor);
+    return check_launch(c, count ? 1 : 0, "logistic_kernel");
+}
+
 int rtb_resolve_rgba8(rtb_ctx* c, const void* image, uint32_t width, uint32_t rows, uint32_t raysPerPixel, void* out) {
     REQUIRE(c && image && out && raysPerPixel, "rtb_resolve_rgba8: bad argument");
     Activate act(c);

@@ -33,6 +33,7 @@ size_t radix_sort_counts_bytes(uint32_t n);
 void launch_trace(cudaStream_t st, TraceParams p, bool count, bool ext, bool linear, int smCount);
 int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, bool cnodes, int smCount, uint32_t samplesPerPass);   // trace_wave.cu
 int launch_trace_stream(cudaStream_t st, TraceParams p, bool count, bool ext, int smCount, uint32_t samplesPerPass);   // trace_stream.cu
+void launch_logistic(cudaStream_t st, void* points, uint32_t count, void* image, uint32_t W, uint32_t H, const float* pixelColor);
 void launch_clear_image(cudaStream_t st, void* img, size_t pixels, int smCount);
 void launch_resolve(cudaStream_t st, const void* img, size_t pixels, uint32_t rpp, void* out, int smCount);
 

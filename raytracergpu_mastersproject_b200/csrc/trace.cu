@@ -147,6 +147,28 @@ __global__ void __launch_bounds__(256) resolve_kernel(const float4* __restrict__
     }
 }
 
+// logistic.comp:23-35 -- the LogisticMap demo program: x' = x * r * (1 - x), then plot (r / 4 * W, (1 - x') * H)
+__global__ void __launch_bounds__(256) logistic_kernel(float2* points, uint32_t count, uchar4* image, uint32_t W, uint32_t H, uchar4 color) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float2 c = points[i];
+    const float nx = c.x * c.y * (1.0f - c.x);
+    points[i] = make_float2(nx, c.y);
+    const int xc = __float2int_rz((c.y / 4.0f) * (float)W);          // int(float): truncation, F2I saturates, NaN -> 0
+    const int yc = __float2int_rz(((1 - nx) / 1.0f) * (float)H);
+    if (xc >= 0 && yc >= 0 && (uint32_t)xc < W && (uint32_t)yc < H) image[(size_t)yc * W + xc] = color;
+}
+void launch_logistic(cudaStream_t st, void* points, uint32_t count, void* image, uint32_t W, uint32_t H, const float* pixelColor) {
+    if (!count) return;
+    unsigned char c[4];
+    for (int k = 0; k < 4; k++) {
+        float v = pixelColor[k];
+        v = (v > 0.0f) ? v : 0.0f; v = (v < 1.0f) ? v : 1.0f;
+        c[k] = (unsigned char)(v * 255.0f + 0.5f);
+    }
+    logistic_kernel<<<(count + 255) / 256, 256, 0, st>>>((float2*)points, count, (uchar4*)image, W, H, make_uchar4(c[0], c[1], c[2], c[3]));
+}
+
 template <bool COUNT, bool EXT, bool LINEAR>
 static void launch_trace_variant(cudaStream_t st, const TraceParams& p, int smCount, uint64_t need) {
     int nb = 0;

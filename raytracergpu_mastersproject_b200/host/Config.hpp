@@ -30,6 +30,7 @@ namespace Config {
 		constexpr const u32 Width = 800;        // window{800, 800}
 		constexpr const u32 Height = 800;
 		constexpr const u32 Frames = 1;         // mainLoop() iterations before the "window closes"
+		constexpr const u32 LogisticFrames = 200; // same, for the LogisticMap program (one map step per frame)
 		constexpr const u32 RandomState = 12345; // deterministic stand-in for the clock-seeded mt19937 (D9); 0 = clock
 		constexpr const int DeviceIndex = 0;
 		constexpr const char* OutputImage = "frame.ppm";

@@ -1,7 +1,8 @@
 // Entry point, same shape as the reference's main.cpp:8-21: pick the program at compile time, construct, mainLoop().
-// The BVH program is the hot path; the non-BVH program (Config::Programs::Raytracer) is the "next" row N2; the
-// LogisticMap demo is out of scope.
+// The BVH program is the hot path; the non-BVH program (Config::Programs::Raytracer) and the LogisticMap demo are the
+// "next" rows N2 / N4.
 #include "Config.hpp"
+#include "LogisticMap.hpp"
 #include "Raytracer.hpp"
 #include "RaytracerBVH.hpp"
 
@@ -12,7 +13,12 @@
 int main(int argc, char** argv) {
 	try {
 		if constexpr (Config::CurrentProgram == Config::Programs::RaytracerBVH) {
-			if (argc > 1 && std::string(argv[1]) == "--non-bvh") {   // additive: run the Config::Programs::Raytracer host instead
+			if (argc > 1 && std::string(argv[1]) == "--logistic") {   // additive: run the Config::Programs::LogisticMap host
+				const u32 w = argc > 4 ? u32(std::atoi(argv[2])) : 1920, h = argc > 4 ? u32(std::atoi(argv[3])) : 1080;
+				const u32 frames = argc > 4 ? u32(std::atoi(argv[4])) : Config::Headless::LogisticFrames;
+				LogisticMapRenderer::LogisticMap comp{ w, h, frames };
+				comp.mainLoop();
+			} else if (argc > 1 && std::string(argv[1]) == "--non-bvh") {   // additive: run the Config::Programs::Raytracer host instead
 				const u32 w = argc > 4 ? u32(std::atoi(argv[3])) : Config::Headless::Width;
 				const u32 h = argc > 4 ? u32(std::atoi(argv[4])) : Config::Headless::Height;
 				RaytracerRenderer::Raytracer comp{ w, h, argc > 2 ? argv[2] : "complexScene" };
@@ -30,8 +36,8 @@ int main(int argc, char** argv) {
 			RaytracerRenderer::Raytracer comp{};
 			comp.mainLoop();
 		} else {
-			std::cerr << "Config::Programs::LogisticMap (the bifurcation-plot demo) is not part of this build\n";
-			return 2;
+			LogisticMapRenderer::LogisticMap comp{};
+			comp.mainLoop();
 		}
 	} catch (const std::exception& e) {
 		std::cerr << "error: " << e.what() << "\n";

@@ -239,3 +239,15 @@ def test_resolve_formula():
     out = O.resolve_rgba8(img, 4)
     assert out[0, :, 0].tolist() == [0, 255, 128, 255]           # clamp(sqrt(x / 4), 0, 1) * 255 rounded
     assert np.all(out[..., 3] == 255)
+
+
+def test_logistic_map_step():
+    """logistic.comp:26-34: x' = x r (1 - x); plot at (int(r/4 W), int((1 - x') H)); out-of-image stores are discarded"""
+    pts = np.float32([[0.5, 4.0], [0.5, 2.0], [0.25, 3.0], [0.0, 1.0]])
+    img = np.zeros((10, 8, 4), np.uint8)
+    O.logistic_step(pts, img)
+    assert pts[:, 0].tolist() == [1.0, 0.5, 0.5625, 0.0]
+    # (0.5, 4.0): x = int(1.0 * 8) = 8 -> outside; (0.5, 2.0): (4, 5); (0.25, 3.0): (6, int(0.4375 * 10) = 4); (0, 1): y = 10 -> outside
+    lit = {(int(y), int(x)) for y, x in zip(*np.nonzero(img[..., 0]))}
+    assert lit == {(5, 4), (4, 6)}
+    assert img[5, 4].tolist() == [255, 255, 255, 255]
