@@ -83,16 +83,6 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
     unsigned err = 0;
     Tally tl = { 0, 0, 0, 0, 0 };
 
-    auto push = [&](uint32_t v) {
-        if (sp < SSTACK) sm.stack[sp][tid] = v;
-        else if (sp < STACK_DEPTH) lstack[sp - SSTACK] = v;
-        else { err |= 1u; return; }
-        sp++;
-    };
-    auto pop = [&]() -> uint32_t {
-        sp--;
-        return sp < SSTACK ? sm.stack[sp][tid] : lstack[sp - SSTACK];
-    };
     auto enqueue = [&](uint32_t g) {
         sm.queue[(qHead + qCount) & (QCAP - 1)][tid] = g;
         qCount++;
