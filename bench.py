@@ -47,8 +47,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", default="wave", choices=["wave", "simple", "stream"], help="trace kernel (A/B switch)")
-    ap.add_argument("--nodes", default="exact", choices=["exact", "compressed"],
-                    help="traversal records: exact 64-byte child pairs (default) or 32-byte compressed (A/B switch, same results)")
+    ap.add_argument("--nodes", default="auto", choices=["auto", "exact", "compressed", "wide"],
+                    help="traversal records: auto (library default: 4-ary for >= 8192 primitives), exact 64-byte child pairs, "
+                         "32-byte compressed, 64-byte 4-ary (A/B switch, same results)")
     ap.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
                     help="N > 1: tiles = 8-row bands + all-gather (bit-identical, default); samples = sample ranges + sum-reduce (C5)")
     ap.add_argument("--mode", default="exact", choices=["exact", "culled"],
@@ -262,7 +263,7 @@ def run_b200(args):
         capi.check(L.rtb_clear_image(h, vp(image), W, rows))
         capi.check(L.rtb_build_bvh(h, ubo_p, vp(d_models), vp(d_tris), vp(d_sphs), vp(d_mats), None, None, None, None, None, 0))
         targs.flags = ((capi.TRACE_COUNT if count else 0) | {"simple": capi.TRACE_SIMPLE_KERNEL, "stream": capi.TRACE_STREAM_KERNEL}.get(args.kernel, 0)
-                       | (capi.TRACE_CULLED if args.mode == "culled" else 0) | (capi.TRACE_COMPRESSED_NODES if args.nodes == "compressed" else 0))
+                       | (capi.TRACE_CULLED if args.mode == "culled" else 0) | {"compressed": capi.TRACE_COMPRESSED_NODES, "wide": capi.TRACE_WIDE_NODES, "exact": capi.TRACE_EXACT_NODES}.get(args.nodes, 0))
         targs.counters = counters.data_ptr() if count else None
         if trace_events:
             trace_events[0].record(stream)

@@ -66,9 +66,14 @@ enum {
                                            (0.1,0.1,0.3) (:43).  Needs no BVH: bind with nodes = NULL. */
     RTB_TRACE_STREAM_KERNEL = 1u << 6,  /* run the streaming (wavefront) kernel trace_stream.cu instead of trace_wave.cu; same
                                            results (A/B switch while both exist) */
-    RTB_TRACE_COMPRESSED_NODES = 1u << 7, /* traverse 32-byte compressed (conservative, 8-bit) child-pair records instead of the
-                                           exact 64-byte ones; exactness is restored at the leaves, results are identical
-                                           (measured: +6 % on C3, -2..4 % on C2 / C4, hence opt-in) */
+    /* Traversal records.  Default (no flag): 64-byte 4-ary records with conservative 8-bit boxes for scenes of >= 8192
+     * primitives (two binary levels per step; exactness is restored at the leaves), the exact 64-byte child
+     * pairs below that (the derivation of the 4-ary records costs more than it saves on tiny scenes).  The flags force
+     * one representation (A/B measurements); results are identical in all cases.  The instrumented variant
+     * (RTB_TRACE_COUNT) always walks the exact child pairs because it counts the reference's node visits. */
+    RTB_TRACE_COMPRESSED_NODES = 1u << 7, /* 32-byte compressed child pairs (+6 % on C3, -2..4 % on C2 / C4) */
+    RTB_TRACE_WIDE_NODES = 1u << 8,     /* 64-byte 4-ary records (+6..21 % on C2..C5) */
+    RTB_TRACE_EXACT_NODES = 1u << 9,    /* exact 64-byte child pairs */
     RTB_TRACE_CULLED = 1u << 5          /* extension, default off: also skip subtrees outside the box of the ray segment
                                            [tMin, closest] (+ margin).  NOT the reference's traversal (it has no t-interval);
                                            fewer node visits, results empirically identical (see trace_wave.cu) */

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256) pack_cnodes_kernel(const uint32_t* __rest
         leafBox[2ull * i] = make_float4(b[0], b[2], b[4], 0.f);
         leafBox[2ull * i + 1] = make_float4(b[1], b[3], b[5], 0.f);
     }
-    if (n < 2 || i >= n - 1) return;
+    if (!cnodes || n < 2 || i >= n - 1) return;
     const uint32_t* nd = nodes + 10ull * i;
     const uint32_t li = nd[6], ri = nd[7];
     const float* L = reinterpret_cast<const float*>(nodes + 10ull * li);
@@ -366,6 +366,68 @@ __global__ void __launch_bounds__(256) pack_cnodes_kernel(const uint32_t* __rest
     bq.w = split;
     cnodes[2ull * i] = a;
     cnodes[2ull * i + 1] = bq;
+}
+
+// Wide (4-ary) traversal records, 64 B, one per binary internal node X: the up-to-four GRANDCHILD entries of X in the
+// reference's visiting order [right.right, right.left, left.right, left.left] (a leaf child stands for itself), each with its
+// exact box quantised OUTWARD to 8 bits per plane relative to the record's origin / power-of-two scales.  Layout (16 words):
+//   0-2 origin.xyz | 3: Ex, Ey, Ez, meta (bits 0-3 leaf flags, bits 4-7 present flags) | 4-9: 4 x 6 plane bytes
+//   (lo.x lo.y lo.z hi.x hi.y hi.z) | 10-13: entry ids (internal: node index, leaf: primitive id) | 14-15 unused
+__global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* wide) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < 2 || i >= n - 1) return;
+    const uint32_t leafOffset = n - 1;
+    uint32_t entry[4]; int cnt = 0;
+    const uint32_t kids[2] = { nodes[10ull * i + 7], nodes[10ull * i + 6] };           // right first (raytraceBVH.comp:241-244)
+    for (int c = 0; c < 2; c++) {
+        const uint32_t k = kids[c];
+        if (k >= leafOffset) entry[cnt++] = k;
+        else { entry[cnt++] = nodes[10ull * k + 7]; entry[cnt++] = nodes[10ull * k + 6]; }
+    }
+    float lo[4][3], hi[4][3], org[3], top[3];
+    for (int k = 0; k < 3; k++) { org[k] = __int_as_float(0x7f800000); top[k] = __int_as_float(0xff800000); }
+    for (int e = 0; e < cnt; e++) {
+        const float* b = reinterpret_cast<const float*>(nodes + 10ull * entry[e]);
+        for (int k = 0; k < 3; k++) {
+            lo[e][k] = b[2 * k]; hi[e][k] = b[2 * k + 1];
+            org[k] = fminf(org[k], lo[e][k]); top[k] = fmaxf(top[k], hi[e][k]);
+        }
+    }
+    uint32_t E[3], q[24];
+    for (int j = 0; j < 24; j++) q[j] = 0;
+    for (int k = 0; k < 3; k++) {
+        const float ext = __fsub_ru(top[k], org[k]);
+        uint32_t ex = 1;
+        if (ext > 0.f) {
+            const uint32_t bits = __float_as_uint(__fdiv_ru(ext, 255.0f));
+            ex = (bits >> 23) + ((bits & 0x7FFFFFu) ? 1u : 0u);
+            if (ex < 1) ex = 1;
+            if (ex > 253) ex = 253;
+        }
+        E[k] = ex;
+        const float inv = __uint_as_float((254u - ex) << 23);
+        for (int e = 0; e < cnt; e++) {
+            float ql = floorf(__fsub_rd(lo[e][k], org[k]) * inv); ql = fminf(fmaxf(ql, 0.f), 255.f);
+            float qh = ceilf(__fsub_ru(hi[e][k], org[k]) * inv); qh = fminf(fmaxf(qh, 0.f), 255.f);
+            q[6 * e + k] = (uint32_t)ql;
+            q[6 * e + 3 + k] = (uint32_t)qh;
+        }
+    }
+    uint32_t meta = 0, ids[4] = { 0, 0, 0, 0 };
+    for (int e = 0; e < cnt; e++) {
+        const bool leaf = entry[e] >= leafOffset;
+        meta |= (leaf ? 1u : 0u) << e;
+        meta |= 1u << (4 + e);
+        ids[e] = leaf ? entry[e] - leafOffset : entry[e];
+    }
+    uint32_t w[16];
+    w[0] = __float_as_uint(org[0]); w[1] = __float_as_uint(org[1]); w[2] = __float_as_uint(org[2]);
+    w[3] = E[0] | (E[1] << 8) | (E[2] << 16) | (meta << 24);
+    for (int j = 0; j < 6; j++) w[4 + j] = q[4 * j] | (q[4 * j + 1] << 8) | (q[4 * j + 2] << 16) | (q[4 * j + 3] << 24);
+    for (int e = 0; e < 4; e++) w[10 + e] = ids[e];
+    w[14] = 0; w[15] = 0;
+    uint4* out = wide + 4ull * i;
+    for (int j = 0; j < 4; j++) out[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
 }
 
 __global__ void __launch_bounds__(256) pack_prims_kernel(const float4* __restrict__ tris, uint32_t T, const float4* __restrict__ sphs,
@@ -446,6 +508,10 @@ void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pai
 }
 void launch_pack_cnodes(cudaStream_t st, const void* nodes, uint32_t n, void* cnodes, void* leafBox) {
     pack_cnodes_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)cnodes, (float4*)leafBox);
+}
+void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide) {
+    if (n < 2) return;
+    pack_wide_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)wide);
 }
 void launch_pack_prims(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* mats, uint32_t M,
                        void* ptris, void* psphs, void* sphMat, void* pmats) {

@@ -44,10 +44,10 @@ struct rtb_ctx {
     Scratch sortKeys[2], sortVals[2], sortCounts, encRed, enclosing, cinfo, nodes;
     // the bound raytrace set: traversal records derived from the reference-layout arrays
     Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag;
-    Scratch cnodes, leafBox;          // compressed 32-byte traversal records + exact leaf boxes
+    Scratch cnodes, leafBox, wide;    // compressed 32-byte / wide 64-byte traversal records + exact leaf boxes
     Scratch activePix, sampleBuf;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
     Scratch poolSlot, poolColor, poolAtt, poolOrg, poolDir, poolNrm, poolList, poolCnt;   // streaming kernel: path pool
-    bool bound = false, boundNodes = false, cnodesReady = false;
+    bool bound = false, boundNodes = false, cnodesReady = false, wideReady = false, leafBoxReady = false;
     const void* boundNodesPtr = nullptr;
     uint32_t bT = 0, bS = 0, bM = 0, bN = 0;
 };
@@ -119,7 +119,9 @@ int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tr
     if (nodes && !pairsDone) launch_pack_pairs(c->stream, nodes, N, c->pairs.p, c->rootBox.p);
     launch_pack_prims(c->stream, tris, T, sphs, S, mats, M, c->ptris.p, c->psphs.p, c->psphMat.p, c->pmats.p);
     c->boundNodesPtr = nodes;
-    c->cnodesReady = false;                 // the 32-byte compressed records are derived on first use
+    c->cnodesReady = false;                 // the compressed / wide records are derived on first use
+    c->wideReady = false;
+    c->leafBoxReady = false;
     if (check_launch(c, 2, "pack traversal records")) return 1;
     c->bound = true; c->boundNodes = nodes != nullptr; c->bT = T; c->bS = S; c->bM = M; c->bN = N;
     return 0;
@@ -171,7 +173,7 @@ int rtb_ctx_destroy(rtb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (Scratch* s : { &c->sortKeys[0], &c->sortKeys[1], &c->sortVals[0], &c->sortVals[1], &c->sortCounts, &c->encRed, &c->enclosing,
                         &c->cinfo, &c->nodes, &c->pairs, &c->ptris, &c->psphs, &c->psphMat, &c->pmats, &c->rootBox, &c->workCounter,
-                        &c->errFlag, &c->cnodes, &c->leafBox, &c->activePix, &c->sampleBuf, &c->poolSlot, &c->poolColor,
+                        &c->errFlag, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->sampleBuf, &c->poolSlot, &c->poolColor,
                         &c->poolAtt, &c->poolOrg, &c->poolDir, &c->poolNrm, &c->poolList, &c->poolCnt })
         release(*s);
     cudaEventDestroy(c->ev0);
@@ -388,6 +390,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     p.sc.rootBox = (const float4*)c->rootBox.p;
     p.sc.cnodes = nullptr;
     p.sc.leafBox = nullptr;
+    p.sc.wide = nullptr;
     p.sc.T = c->bT; p.sc.S = c->bS; p.sc.N = c->bN;
     p.cam = make_camera(ubo, a->imageWidth, a->imageHeight);
     p.image = (float4*)image;
@@ -435,16 +438,25 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
             p.pool.rayList = (uint32_t*)c->poolList.p; p.pool.cnt = (unsigned int*)c->poolCnt.p; p.pool.capacity = (uint32_t)cap;
             launches = launch_trace_stream(c->stream, p, count, ext, c->smCount, (uint32_t)perPass);
         } else {
-            bool cn = (a->flags & RTB_TRACE_COMPRESSED_NODES) != 0 && c->boundNodes && c->bN > 1 && !count;
+            const bool derived = c->boundNodes && c->bN > 1 && !count;
+            const int nodesMode = !derived ? 0 : (a->flags & RTB_TRACE_EXACT_NODES) ? 0 : (a->flags & RTB_TRACE_WIDE_NODES) ? 2
+                                : (a->flags & RTB_TRACE_COMPRESSED_NODES) ? 1 : (c->bN >= 8192 ? 2 : 0);
             int extra = 0;
-            if (cn && !c->cnodesReady) {
-                if (ensure(c, c->cnodes, 32ull * (c->bN - 1))) return 1;
+            if (nodesMode && (!c->leafBoxReady || (nodesMode == 1 && !c->cnodesReady))) {   // exact leaf boxes (+ the 32-byte records)
+                if (nodesMode == 1 && ensure(c, c->cnodes, 32ull * (c->bN - 1))) return 1;
                 if (ensure(c, c->leafBox, 32ull * c->bN)) return 1;
-                launch_pack_cnodes(c->stream, c->boundNodesPtr, c->bN, c->cnodes.p, c->leafBox.p);
-                c->cnodesReady = true; extra = 1;
+                launch_pack_cnodes(c->stream, c->boundNodesPtr, c->bN, nodesMode == 1 ? c->cnodes.p : nullptr, c->leafBox.p);
+                c->leafBoxReady = true; if (nodesMode == 1) c->cnodesReady = true;
+                extra++;
             }
-            if (cn) { p.sc.cnodes = (const uint4*)c->cnodes.p; p.sc.leafBox = (const float4*)c->leafBox.p; }
-            launches = extra + launch_trace_wave(c->stream, p, count, ext, cull, cn, c->smCount, (uint32_t)perPass);
+            if (nodesMode == 2 && !c->wideReady) {
+                if (ensure(c, c->wide, 64ull * (c->bN - 1))) return 1;
+                launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wide.p);
+                c->wideReady = true; extra++;
+            }
+            if (nodesMode) { p.sc.cnodes = nodesMode == 1 ? (const uint4*)c->cnodes.p : nullptr; p.sc.leafBox = (const float4*)c->leafBox.p; }
+            if (nodesMode == 2) p.sc.wide = (const uint4*)c->wide.p;
+            launches = extra + launch_trace_wave(c->stream, p, count, ext, cull, nodesMode, c->smCount, (uint32_t)perPass);
         }
     }
     return check_launch(c, launches, "trace kernel");

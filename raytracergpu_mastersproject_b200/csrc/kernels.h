@@ -22,6 +22,7 @@ void launch_hlbvh(cudaStream_t st, const void* tris, uint32_t T, const void* sph
 void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox);   // pairs != NULL: also emit traversal records
 void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pairs, void* rootBox);
 void launch_pack_cnodes(cudaStream_t st, const void* nodes, uint32_t n, void* cnodes, void* leafBox);
+void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide);
 void launch_pack_prims(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* mats, uint32_t M,
                        void* ptris, void* psphs, void* sphMat, void* pmats);
 
@@ -31,7 +32,7 @@ size_t radix_sort_counts_bytes(uint32_t n);
 
 // trace.cu
 void launch_trace(cudaStream_t st, TraceParams p, bool count, bool ext, bool linear, int smCount);
-int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, bool cnodes, int smCount, uint32_t samplesPerPass);   // trace_wave.cu
+int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint32_t samplesPerPass);   // trace_wave.cu
 int launch_trace_stream(cudaStream_t st, TraceParams p, bool count, bool ext, int smCount, uint32_t samplesPerPass);   // trace_stream.cu
 void launch_logistic(cudaStream_t st, void* points, uint32_t count, void* image, uint32_t W, uint32_t H, const float* pixelColor);
 void launch_clear_image(cudaStream_t st, void* img, size_t pixels, int smCount);

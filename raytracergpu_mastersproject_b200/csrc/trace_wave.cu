@@ -46,7 +46,7 @@ constexpr int WAVE_MIN_BLOCKS = 6;
 // as the margin exceeds the rounding slack of the intersection tests.  That is an argument, not a proof (sliver triangles
 // stretch the slack), hence a flag: tests/test_gpu_parity.py checks images and hit ids stay bit-identical on the test
 // scenes and bench.py --mode culled reports it as a separate, labelled line.
-template <bool COUNT, bool EXT, bool CULL, bool CN>
+template <bool COUNT, bool EXT, bool CULL, int NODES>   // NODES: 0 exact 64-B pairs, 1 compressed 32-B pairs, 2 wide 64-B (4-ary)
 __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kernel(const TraceParams p) {
     __shared__ WaveSmem<WAVE_THREADS> sm;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
     const uint32_t groupItems = 32u * p.sampleCount;
     const uint64_t totalWork = (uint64_t)((activeCount + 31u) / 32u) * groupItems;
     const float T_MIN_RAY = 0.001f, T_MAX_RAY = 10000000.0f;                    // sceneHit :268-269
+    constexpr bool CN = NODES != 0;                       // conservative internal boxes: leaves are re-checked exactly
+    constexpr uint32_t Q_ROOM = NODES == 2 ? 4u : 2u;     // free FIFO entries a turn may need
 
     // ---- per-lane state -------------------------------------------------------------------------------------------
     bool dead = false, rayActive = false, travDone = true, exactOnly = false, hit = false;
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
 
         // =========================================== T: traverse ================================================
         while (true) {
-            const bool can = rayActive && !travDone && qCount <= QCAP - 2;
+            const bool can = rayActive && !travDone && qCount <= QCAP - Q_ROOM;
             const unsigned bal = __ballot_sync(FULL, can);
             if (bal == 0) break;
             if (__popc(bal) < (int)p.tMin) {
@@ -177,7 +179,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
             if (can) {
                 // CN: 32-byte compressed records; rays with a zero / denormal direction component (reference yields inf / NaN)
                 // keep to the exact 64-byte records
-                if (CN && !exactOnly) wave_step_c<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
+                if (NODES == 2 && !exactOnly) wave_step_w<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
+                else if (NODES == 1 && !exactOnly) wave_step_c<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
                 else wave_step<COUNT, CULL>(sc, sm, tid, leafOffset, o, d, rinv, exactOnly, cur, sp, qHead, qCount, travDone, lstack, tl, err, segLo, segHi);
             }
         }
@@ -210,19 +213,21 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
     }
 }
 
-template <bool COUNT, bool EXT, bool CULL, bool CN>
+template <bool COUNT, bool EXT, bool CULL, int NODES>
 static void launch_wave_variant(cudaStream_t st, const TraceParams& p, int smCount, uint64_t need) {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_wave_kernel<COUNT, EXT, CULL, CN>, WAVE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_wave_kernel<COUNT, EXT, CULL, NODES>, WAVE_THREADS, 0);
     uint64_t grid = (uint64_t)smCount * (nb > 0 ? nb : 1);                 // persistent: resident CTAs per SM x SM count
     if (grid > need) grid = need;
-    trace_wave_kernel<COUNT, EXT, CULL, CN><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
+    trace_wave_kernel<COUNT, EXT, CULL, NODES><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
 }
 
 // One S2 submission = ceil(sampleCount / samplesPerPass) passes of { pre-pass, trace, accumulate }.  Returns #launches.
-int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, bool cn, int smCount, uint32_t samplesPerPass) {
-    if (count || !p.sc.cnodes || p.sc.N < 2) cn = false;   // the instrumented variant counts the reference's visits: exact records
-    if (p.tMin == 0) p.tMin = T_MIN_DEFAULT;
+int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint32_t samplesPerPass) {
+    if (count || p.sc.N < 2) nodesMode = 0;                // the instrumented variant counts the reference's visits: exact records
+    if (nodesMode == 1 && !p.sc.cnodes) nodesMode = 0;
+    if (nodesMode == 2 && !p.sc.wide) nodesMode = 0;
+    if (p.tMin == 0) p.tMin = nodesMode == 2 ? 24 : T_MIN_DEFAULT;   // swept on C2 (RTB_WAVE_TMIN)
     const uint32_t pixels = p.W * p.localRows;
     const uint32_t totalSamples = p.sampleCount, skip0 = p.sampleSkip;
     int launches = 0;
@@ -236,23 +241,30 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool
         else wave_prepass_kernel<false><<<(pixels + 255) / 256, 256, 0, st>>>(p);
         const uint64_t need = ((uint64_t)pixels * p.sampleCount + WAVE_THREADS - 1) / WAVE_THREADS;   // never more lanes than items
         const int v = (count ? 4 : 0) | (ext ? 2 : 0) | (cull ? 1 : 0);
-        if (cn) {
+        if (nodesMode == 2) {
             switch (v) {
-            case 0: launch_wave_variant<false, false, false, true>(st, p, smCount, need); break;
-            case 1: launch_wave_variant<false, false, true, true>(st, p, smCount, need); break;
-            case 2: launch_wave_variant<false, true, false, true>(st, p, smCount, need); break;
-            default: launch_wave_variant<false, true, true, true>(st, p, smCount, need); break;
+            case 0: launch_wave_variant<false, false, false, 2>(st, p, smCount, need); break;
+            case 1: launch_wave_variant<false, false, true, 2>(st, p, smCount, need); break;
+            case 2: launch_wave_variant<false, true, false, 2>(st, p, smCount, need); break;
+            default: launch_wave_variant<false, true, true, 2>(st, p, smCount, need); break;
+            }
+        } else if (nodesMode == 1) {
+            switch (v) {
+            case 0: launch_wave_variant<false, false, false, 1>(st, p, smCount, need); break;
+            case 1: launch_wave_variant<false, false, true, 1>(st, p, smCount, need); break;
+            case 2: launch_wave_variant<false, true, false, 1>(st, p, smCount, need); break;
+            default: launch_wave_variant<false, true, true, 1>(st, p, smCount, need); break;
             }
         } else {
             switch (v) {
-            case 0: launch_wave_variant<false, false, false, false>(st, p, smCount, need); break;
-            case 1: launch_wave_variant<false, false, true, false>(st, p, smCount, need); break;
-            case 2: launch_wave_variant<false, true, false, false>(st, p, smCount, need); break;
-            case 3: launch_wave_variant<false, true, true, false>(st, p, smCount, need); break;
-            case 4: launch_wave_variant<true, false, false, false>(st, p, smCount, need); break;
-            case 5: launch_wave_variant<true, false, true, false>(st, p, smCount, need); break;
-            case 6: launch_wave_variant<true, true, false, false>(st, p, smCount, need); break;
-            default: launch_wave_variant<true, true, true, false>(st, p, smCount, need); break;
+            case 0: launch_wave_variant<false, false, false, 0>(st, p, smCount, need); break;
+            case 1: launch_wave_variant<false, false, true, 0>(st, p, smCount, need); break;
+            case 2: launch_wave_variant<false, true, false, 0>(st, p, smCount, need); break;
+            case 3: launch_wave_variant<false, true, true, 0>(st, p, smCount, need); break;
+            case 4: launch_wave_variant<true, false, false, 0>(st, p, smCount, need); break;
+            case 5: launch_wave_variant<true, false, true, 0>(st, p, smCount, need); break;
+            case 6: launch_wave_variant<true, true, false, 0>(st, p, smCount, need); break;
+            default: launch_wave_variant<true, true, true, 0>(st, p, smCount, need); break;
             }
         }
         wave_accumulate_kernel<0><<<(pixels + 255) / 256, 256, 0, st>>>(p);

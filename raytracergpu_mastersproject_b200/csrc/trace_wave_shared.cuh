@@ -287,7 +287,89 @@ __device__ __forceinline__ void wave_step_c(const TraceScene& sc, WaveSmem<THREA
     if (doPop && !popLeaf) cur = e;
 }
 
-// the reference's box test on the EXACT box of leaf candidate g (compressed traversal only)
+
+// Traverse-phase turn over the 64-byte WIDE record (two 256-bit loads): up to four grandchild entries of binary node `cur` in
+// the reference's visiting order, boxes conservative (8-bit, outward rounded) exactly as in wave_step_c, so one turn covers
+// two levels of the binary tree.  The first surviving internal entry is descended into; surviving entries before it are
+// leaves and are queued in order; surviving entries after it wait on the stack (pushed last-first so that they pop in order).
+// Skipping the intermediate child's own box test is legal because its box contains its children's boxes (conservative).
+template <bool CULL, int THREADS>
+__device__ __forceinline__ void wave_step_w(const TraceScene& sc, WaveSmem<THREADS>& sm, const unsigned tid, const uint32_t leafOffset,
+                                            const f3 o, const f3 rinv, uint32_t& cur, int& sp, const uint32_t qHead, uint32_t& qCount,
+                                            bool& travDone, uint32_t* lstack, unsigned& err, const f3 segLo, const f3 segHi) {
+    if (cur != 0xFFFFFFFFu) {
+        const uint4* rp = sc.wide + 4ull * cur;
+        const f8 h0 = ldg256(rp), h1 = ldg256(rp + 2);
+        const uint32_t w3 = __float_as_uint(h0.lo.w);
+        const uint32_t qw[6] = { __float_as_uint(h0.hi.x), __float_as_uint(h0.hi.y), __float_as_uint(h0.hi.z), __float_as_uint(h0.hi.w),
+                                 __float_as_uint(h1.lo.x), __float_as_uint(h1.lo.y) };
+        const uint32_t ids[4] = { __float_as_uint(h1.lo.z), __float_as_uint(h1.lo.w), __float_as_uint(h1.hi.x), __float_as_uint(h1.hi.y) };
+        const float sx = __uint_as_float((w3 & 0xFFu) << 23), sy = __uint_as_float(((w3 >> 8) & 0xFFu) << 23),
+                    sz = __uint_as_float(((w3 >> 16) & 0xFFu) << 23);
+        const float ax = sx * rinv.x, ay = sy * rinv.y, az = sz * rinv.z;
+        const float bx = (h0.lo.x - o.x) * rinv.x, by = (h0.lo.y - o.y) * rinv.y, bz = (h0.lo.z - o.z) * rinv.z;
+        const float m = fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(bx)), fmaf(255.0f, fabsf(ay), fabsf(by))), fmaf(255.0f, fabsf(az), fabsf(bz)));
+        const float tol = -2.0e-6f * m;                                   // NaN / inf -> nothing is skipped
+        const uint32_t meta = w3 >> 24;
+        uint32_t passMask = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            // plane bytes 6e .. 6e+5 of the 24-byte array: lo.x lo.y lo.z hi.x hi.y hi.z
+// (compiles to one I2F.U8 with a byte selector; a PRMT + FADD decode measured 5 % slower)
+#define RTB_B(j) __uint2float_rn((qw[(6 * e + (j)) >> 2] >> (8 * ((6 * e + (j)) & 3))) & 0xFFu)
+            const float lx = fmaf(RTB_B(0), ax, bx), ly = fmaf(RTB_B(1), ay, by), lz = fmaf(RTB_B(2), az, bz);
+            const float hx = fmaf(RTB_B(3), ax, bx), hy = fmaf(RTB_B(4), ay, by), hz = fmaf(RTB_B(5), az, bz);
+            const float tn = fmaxf(fmaxf(fminf(lx, hx), fminf(ly, hy)), fminf(lz, hz));
+            const float tf = fminf(fminf(fmaxf(lx, hx), fmaxf(ly, hy)), fmaxf(lz, hz));
+            bool pass = ((meta >> (4 + e)) & 1u) && !((tf - tn) < tol);
+            if (CULL) {
+                const float X0 = fmaf(RTB_B(0), sx, h0.lo.x), Y0 = fmaf(RTB_B(1), sy, h0.lo.y), Z0 = fmaf(RTB_B(2), sz, h0.lo.z);
+                const float X1 = fmaf(RTB_B(3), sx, h0.lo.x), Y1 = fmaf(RTB_B(4), sy, h0.lo.y), Z1 = fmaf(RTB_B(5), sz, h0.lo.z);
+                pass = pass && !(X0 > segHi.x || X1 < segLo.x || Y0 > segHi.y || Y1 < segLo.y || Z0 > segHi.z || Z1 < segLo.z);
+            }
+#undef RTB_B
+            passMask |= (pass ? 1u : 0u) << e;
+        }
+        const uint32_t leafMask = meta & 0xFu;
+        const uint32_t intMask = passMask & ~leafMask;
+        const int j = intMask ? (__ffs(intMask) - 1) : 4;                 // first surviving internal entry
+        const uint32_t before = (1u << j) - 1u;
+        const uint32_t enqMask = passMask & leafMask & before;            // leaves ahead of it: test them first, in order
+        const uint32_t pushMask = passMask & ~before & ~(1u << j);        // everything behind it waits on the stack
+        uint32_t tail = (qHead + qCount) & (QCAP - 1);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const bool en = (enqMask >> e) & 1u;
+            if (en) sm.queue[tail][tid] = ids[e];
+            tail = (tail + (en ? 1u : 0u)) & (QCAP - 1);
+        }
+        qCount += __popc(enqMask);
+#pragma unroll
+        for (int e = 3; e >= 1; e--) {
+            const bool pu = (pushMask >> e) & 1u;
+            const uint32_t v = ((leafMask >> e) & 1u) ? leafOffset + ids[e] : ids[e];
+            if (pu && sp < SSTACK) sm.stack[sp][tid] = v;
+            if (pu && sp >= SSTACK) {
+                if (sp < STACK_DEPTH) lstack[sp - SSTACK] = v; else err |= 1u;
+            }
+            sp += (pu && sp < STACK_DEPTH) ? 1 : 0;
+        }
+        cur = j == 0 ? ids[0] : (j == 1 ? ids[1] : (j == 2 ? ids[2] : (j == 3 ? ids[3] : 0xFFFFFFFFu)));
+    }
+    const bool needPop = cur == 0xFFFFFFFFu && qCount < QCAP;
+    if (needPop && sp == 0) travDone = true;
+    const bool doPop = needPop && sp > 0;
+    uint32_t e = 0;
+    if (doPop && sp <= SSTACK) e = sm.stack[sp - 1][tid];
+    if (doPop && sp > SSTACK) e = lstack[sp - 1 - SSTACK];
+    sp -= doPop ? 1 : 0;
+    const bool popLeaf = doPop && e >= leafOffset;
+    if (popLeaf) sm.queue[(qHead + qCount) & (QCAP - 1)][tid] = e - leafOffset;
+    qCount += popLeaf ? 1u : 0u;
+    if (doPop && !popLeaf) cur = e;
+}
+
+// the reference's box test on the EXACT box of leaf candidate g (compressed / wide traversal only)
 __device__ __forceinline__ bool leaf_box_passes(const TraceScene& sc, const uint32_t g, const f3 o, const f3 d, const f3 rinv, const bool exactOnly) {
     const f8 b = ldg256(sc.leafBox + 2ull * g);
     return box_test(o, d, rinv, exactOnly, b.lo.x, b.lo.y, b.lo.z, b.hi.x, b.hi.y, b.hi.z);

@@ -95,12 +95,13 @@ def test_s1_stage_by_stage(device, cfg):
 
 @pytest.mark.parametrize("cfg", SCENES, ids=lambda c: f"seed{c['seed']}")
 @pytest.mark.parametrize("spp", [1, 5])
-@pytest.mark.parametrize("kernel", ["wave", "wave-compressed-nodes", "simple", "stream"])
+@pytest.mark.parametrize("kernel", ["wave", "wave-exact-nodes", "wave-compressed-nodes", "wave-wide-nodes", "simple", "stream"])
 def test_frame_bit_exact(device, cfg, spp, kernel):
     """Whole frame (S1 fused + S2): node array, hit ids, RNG states, counters and the fp32 image, all bit-exact.
     Both trace kernels: the production warp-coherent one and the straightforward one kept for A/B measurements."""
     from raytracergpu_mastersproject_b200 import Buffer, capi
-    kflag = {"simple": capi.TRACE_SIMPLE_KERNEL, "stream": capi.TRACE_STREAM_KERNEL, "wave-compressed-nodes": capi.TRACE_COMPRESSED_NODES}.get(kernel, 0)
+    kflag = {"simple": capi.TRACE_SIMPLE_KERNEL, "stream": capi.TRACE_STREAM_KERNEL, "wave-compressed-nodes": capi.TRACE_COMPRESSED_NODES, "wave-wide-nodes": capi.TRACE_WIDE_NODES,
+             "wave-exact-nodes": capi.TRACE_EXACT_NODES}.get(kernel, 0)
     W, H = 96, 72
     sc = SU.random_scene(**cfg)
     ubo = SU.make_ubo(sc, max_depth=8, random_state=12345 + cfg["seed"])
