@@ -371,8 +371,9 @@ __global__ void __launch_bounds__(256) pack_cnodes_kernel(const uint32_t* __rest
 // Wide (4-ary) traversal records, 64 B, one per binary internal node X: the up-to-four GRANDCHILD entries of X in the
 // reference's visiting order [right.right, right.left, left.right, left.left] (a leaf child stands for itself), each with its
 // exact box quantised OUTWARD to 8 bits per plane relative to the record's origin / power-of-two scales.  Layout (16 words):
-//   0-2 origin.xyz | 3: Ex, Ey, Ez, meta (bits 0-3 leaf flags, bits 4-7 present flags) | 4-9: 4 x 6 plane bytes
-//   (lo.x lo.y lo.z hi.x hi.y hi.z) | 10-13: entry ids (internal: node index, leaf: primitive id) | 14-15 unused
+//   0-2 origin.xyz | 3: Ex, Ey, Ez, meta (bits 0-3 leaf flags, bits 4-7 present flags) | 4-9: one word per plane
+//   (lo.x lo.y lo.z hi.x hi.y hi.z), byte e = entry e, so the kernel picks a ray's near / far planes of all four entries
+//   with one select per word | 10-13: entry node indices (a leaf is leafOffset + primitive id) | 14-15 unused
 __global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* wide) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < 2 || i >= n - 1) return;
@@ -409,8 +410,8 @@ __global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restri
         for (int e = 0; e < cnt; e++) {
             float ql = floorf(__fsub_rd(lo[e][k], org[k]) * inv); ql = fminf(fmaxf(ql, 0.f), 255.f);
             float qh = ceilf(__fsub_ru(hi[e][k], org[k]) * inv); qh = fminf(fmaxf(qh, 0.f), 255.f);
-            q[6 * e + k] = (uint32_t)ql;
-            q[6 * e + 3 + k] = (uint32_t)qh;
+            q[4 * k + e] = (uint32_t)ql;
+            q[4 * (3 + k) + e] = (uint32_t)qh;
         }
     }
     uint32_t meta = 0, ids[4] = { 0, 0, 0, 0 };
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restri
         const bool leaf = entry[e] >= leafOffset;
         meta |= (leaf ? 1u : 0u) << e;
         meta |= 1u << (4 + e);
-        ids[e] = leaf ? entry[e] - leafOffset : entry[e];
+        ids[e] = entry[e];
     }
     uint32_t w[16];
     w[0] = __float_as_uint(org[0]); w[1] = __float_as_uint(org[1]); w[2] = __float_as_uint(org[2]);

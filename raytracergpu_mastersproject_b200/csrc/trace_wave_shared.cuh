@@ -293,6 +293,10 @@ __device__ __forceinline__ void wave_step_c(const TraceScene& sc, WaveSmem<THREA
 // two levels of the binary tree.  The first surviving internal entry is descended into; surviving entries before it are
 // leaves and are queued in order; surviving entries after it wait on the stack (pushed last-first so that they pop in order).
 // Skipping the intermediate child's own box test is legal because its box contains its children's boxes (conservative).
+// The plane bytes are stored one word per plane (byte e = entry e): the ray's direction signs pick the near / far word per
+// axis once, so an entry costs six byte conversions, six FFMA and one 3-input max + one 3-input min.  (fma is monotone in the
+// byte value, so near <= far holds exactly as with min / max of both planes; NaN planes -- a zero direction component never
+// gets here, see exactOnly -- would only drop a constraint, which is conservative.)
 template <bool CULL, int THREADS>
 __device__ __forceinline__ void wave_step_w(const TraceScene& sc, WaveSmem<THREADS>& sm, const unsigned tid, const uint32_t leafOffset,
                                             const f3 o, const f3 rinv, uint32_t& cur, int& sp, const uint32_t qHead, uint32_t& qCount,
@@ -301,60 +305,70 @@ __device__ __forceinline__ void wave_step_w(const TraceScene& sc, WaveSmem<THREA
         const uint4* rp = sc.wide + 4ull * cur;
         const f8 h0 = ldg256(rp), h1 = ldg256(rp + 2);
         const uint32_t w3 = __float_as_uint(h0.lo.w);
-        const uint32_t qw[6] = { __float_as_uint(h0.hi.x), __float_as_uint(h0.hi.y), __float_as_uint(h0.hi.z), __float_as_uint(h0.hi.w),
-                                 __float_as_uint(h1.lo.x), __float_as_uint(h1.lo.y) };
-        const uint32_t ids[4] = { __float_as_uint(h1.lo.z), __float_as_uint(h1.lo.w), __float_as_uint(h1.hi.x), __float_as_uint(h1.hi.y) };
+        const uint32_t lox = __float_as_uint(h0.hi.x), loy = __float_as_uint(h0.hi.y), loz = __float_as_uint(h0.hi.z),
+                       hix = __float_as_uint(h0.hi.w), hiy = __float_as_uint(h1.lo.x), hiz = __float_as_uint(h1.lo.y);
+        const uint32_t id0 = __float_as_uint(h1.lo.z), id1 = __float_as_uint(h1.lo.w), id2 = __float_as_uint(h1.hi.x),
+                       id3 = __float_as_uint(h1.hi.y);
         const float sx = __uint_as_float((w3 & 0xFFu) << 23), sy = __uint_as_float(((w3 >> 8) & 0xFFu) << 23),
                     sz = __uint_as_float(((w3 >> 16) & 0xFFu) << 23);
         const float ax = sx * rinv.x, ay = sy * rinv.y, az = sz * rinv.z;
         const float bx = (h0.lo.x - o.x) * rinv.x, by = (h0.lo.y - o.y) * rinv.y, bz = (h0.lo.z - o.z) * rinv.z;
         const float m = fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(bx)), fmaf(255.0f, fabsf(ay), fabsf(by))), fmaf(255.0f, fabsf(az), fabsf(bz)));
         const float tol = -2.0e-6f * m;                                   // NaN / inf -> nothing is skipped
+        const bool ngx = rinv.x < 0.0f, ngy = rinv.y < 0.0f, ngz = rinv.z < 0.0f;
+        const uint32_t nX = ngx ? hix : lox, fX = ngx ? lox : hix;
+        const uint32_t nY = ngy ? hiy : loy, fY = ngy ? loy : hiy;
+        const uint32_t nZ = ngz ? hiz : loz, fZ = ngz ? loz : hiz;
         const uint32_t meta = w3 >> 24;
         uint32_t passMask = 0;
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-            // plane bytes 6e .. 6e+5 of the 24-byte array: lo.x lo.y lo.z hi.x hi.y hi.z
-// (compiles to one I2F.U8 with a byte selector; a PRMT + FADD decode measured 5 % slower)
-#define RTB_B(j) __uint2float_rn((qw[(6 * e + (j)) >> 2] >> (8 * ((6 * e + (j)) & 3))) & 0xFFu)
-            const float lx = fmaf(RTB_B(0), ax, bx), ly = fmaf(RTB_B(1), ay, by), lz = fmaf(RTB_B(2), az, bz);
-            const float hx = fmaf(RTB_B(3), ax, bx), hy = fmaf(RTB_B(4), ay, by), hz = fmaf(RTB_B(5), az, bz);
-            const float tn = fmaxf(fmaxf(fminf(lx, hx), fminf(ly, hy)), fminf(lz, hz));
-            const float tf = fminf(fminf(fmaxf(lx, hx), fmaxf(ly, hy)), fmaxf(lz, hz));
-            bool pass = ((meta >> (4 + e)) & 1u) && !((tf - tn) < tol);
+#define RTB_B(w) __uint2float_rn(((w) >> (8 * e)) & 0xFFu)                 // one I2F.U8 with a byte selector
+            const float tn = fmaxf(fmaxf(fmaf(RTB_B(nX), ax, bx), fmaf(RTB_B(nY), ay, by)), fmaf(RTB_B(nZ), az, bz));
+            const float tf = fminf(fminf(fmaf(RTB_B(fX), ax, bx), fmaf(RTB_B(fY), ay, by)), fmaf(RTB_B(fZ), az, bz));
+            bool pass = !((tf - tn) < tol);
             if (CULL) {
-                const float X0 = fmaf(RTB_B(0), sx, h0.lo.x), Y0 = fmaf(RTB_B(1), sy, h0.lo.y), Z0 = fmaf(RTB_B(2), sz, h0.lo.z);
-                const float X1 = fmaf(RTB_B(3), sx, h0.lo.x), Y1 = fmaf(RTB_B(4), sy, h0.lo.y), Z1 = fmaf(RTB_B(5), sz, h0.lo.z);
+                const float X0 = fmaf(RTB_B(lox), sx, h0.lo.x), Y0 = fmaf(RTB_B(loy), sy, h0.lo.y), Z0 = fmaf(RTB_B(loz), sz, h0.lo.z);
+                const float X1 = fmaf(RTB_B(hix), sx, h0.lo.x), Y1 = fmaf(RTB_B(hiy), sy, h0.lo.y), Z1 = fmaf(RTB_B(hiz), sz, h0.lo.z);
                 pass = pass && !(X0 > segHi.x || X1 < segLo.x || Y0 > segHi.y || Y1 < segLo.y || Z0 > segHi.z || Z1 < segLo.z);
             }
 #undef RTB_B
-            passMask |= (pass ? 1u : 0u) << e;
+            passMask |= pass ? (1u << e) : 0u;
         }
+        passMask &= meta >> 4;                                            // entries that exist
         const uint32_t leafMask = meta & 0xFu;
         const uint32_t intMask = passMask & ~leafMask;
-        const int j = intMask ? (__ffs(intMask) - 1) : 4;                 // first surviving internal entry
-        const uint32_t before = (1u << j) - 1u;
+        const uint32_t first = intMask & (0u - intMask);                  // first surviving internal entry (one-hot, or 0)
+        const uint32_t before = (first - 1u) & 0xFu;                      // entries ahead of it (all four when there is none)
         const uint32_t enqMask = passMask & leafMask & before;            // leaves ahead of it: test them first, in order
-        const uint32_t pushMask = passMask & ~before & ~(1u << j);        // everything behind it waits on the stack
+        const uint32_t pushMask = passMask & ~before & ~first;            // everything behind it waits on the stack
         uint32_t tail = (qHead + qCount) & (QCAP - 1);
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const bool en = (enqMask >> e) & 1u;
-            if (en) sm.queue[tail][tid] = ids[e];
-            tail = (tail + (en ? 1u : 0u)) & (QCAP - 1);
-        }
+        { const bool en = enqMask & 1u; if (en) sm.queue[tail][tid] = id0 - leafOffset; tail = (tail + (en ? 1u : 0u)) & (QCAP - 1); }
+        { const bool en = enqMask & 2u; if (en) sm.queue[tail][tid] = id1 - leafOffset; tail = (tail + (en ? 1u : 0u)) & (QCAP - 1); }
+        { const bool en = enqMask & 4u; if (en) sm.queue[tail][tid] = id2 - leafOffset; tail = (tail + (en ? 1u : 0u)) & (QCAP - 1); }
+        { const bool en = enqMask & 8u; if (en) sm.queue[tail][tid] = id3 - leafOffset; }
         qCount += __popc(enqMask);
-#pragma unroll
-        for (int e = 3; e >= 1; e--) {
-            const bool pu = (pushMask >> e) & 1u;
-            const uint32_t v = ((leafMask >> e) & 1u) ? leafOffset + ids[e] : ids[e];
-            if (pu && sp < SSTACK) sm.stack[sp][tid] = v;
-            if (pu && sp >= SSTACK) {
-                if (sp < STACK_DEPTH) lstack[sp - SSTACK] = v; else err |= 1u;
+        if (sp <= SSTACK - 3) {                                           // the usual case: three predicated shared-memory stores
+            { const bool pu = pushMask & 8u; if (pu) sm.stack[sp][tid] = id3; sp += pu ? 1 : 0; }
+            { const bool pu = pushMask & 4u; if (pu) sm.stack[sp][tid] = id2; sp += pu ? 1 : 0; }
+            { const bool pu = pushMask & 2u; if (pu) sm.stack[sp][tid] = id1; sp += pu ? 1 : 0; }
+        } else {                                                          // deep: the levels beyond SSTACK live in local memory
+            const uint32_t ids[3] = { id3, id2, id1 };
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) {
+                if (!((pushMask >> (3 - k)) & 1u)) continue;
+                if (sp < SSTACK) sm.stack[sp][tid] = ids[k];
+                else if (sp < STACK_DEPTH) lstack[sp - SSTACK] = ids[k];
+                else { err |= 1u; continue; }
+                sp++;
             }
-            sp += (pu && sp < STACK_DEPTH) ? 1 : 0;
         }
-        cur = j == 0 ? ids[0] : (j == 1 ? ids[1] : (j == 2 ? ids[2] : (j == 3 ? ids[3] : 0xFFFFFFFFu)));
+        uint32_t next = 0xFFFFFFFFu;
+        next = (first & 1u) ? id0 : next;
+        next = (first & 2u) ? id1 : next;
+        next = (first & 4u) ? id2 : next;
+        next = (first & 8u) ? id3 : next;
+        cur = next;
     }
     const bool needPop = cur == 0xFFFFFFFFu && qCount < QCAP;
     if (needPop && sp == 0) travDone = true;
