@@ -368,8 +368,8 @@ __global__ void __launch_bounds__(256) pack_cnodes_kernel(const uint32_t* __rest
     cnodes[2ull * i + 1] = bq;
 }
 
-// Wide (4-ary) traversal records, 64 B, one per binary internal node X: the up-to-four GRANDCHILD entries of X in the
-// reference's visiting order [right.right, right.left, left.right, left.left] (a leaf child stands for itself), each with its
+// Wide (4-ary) traversal records, 64 B, one per binary internal node X: up to four DESCENDANT entries of X that together
+// cover X's subtree, in the reference's visiting order (e.g. [right.right, right.left, left.right, left.left]), each with its
 // exact box quantised OUTWARD to 8 bits per plane relative to the record's origin / power-of-two scales.  Layout (16 words):
 //   0-2 origin.xyz | 3: Ex, Ey, Ez, meta (bits 0-3 leaf flags, bits 4-7 present flags) | 4-9: one word per plane
 //   (lo.x lo.y lo.z hi.x hi.y hi.z), byte e = entry e, so the kernel picks a ray's near / far planes of all four entries
@@ -378,12 +378,25 @@ __global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restri
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < 2 || i >= n - 1) return;
     const uint32_t leafOffset = n - 1;
-    uint32_t entry[4]; int cnt = 0;
-    const uint32_t kids[2] = { nodes[10ull * i + 7], nodes[10ull * i + 6] };           // right first (raytraceBVH.comp:241-244)
-    for (int c = 0; c < 2; c++) {
-        const uint32_t k = kids[c];
-        if (k >= leafOffset) entry[cnt++] = k;
-        else { entry[cnt++] = nodes[10ull * k + 7]; entry[cnt++] = nodes[10ull * k + 6]; }
+    // The entries are a cut through X's subtree, kept in visiting order (right before left, raytraceBVH.comp:241-244): start from
+    // X's two children and keep replacing the internal entry with the largest surface area by its own two children while a slot
+    // is free (the entry a ray is most likely to enter is the one worth resolving inside this record).
+    uint32_t entry[4]; int cnt = 2;
+    entry[0] = nodes[10ull * i + 7]; entry[1] = nodes[10ull * i + 6];
+    while (cnt < 4) {
+        int pick = -1; float best = -1.0f;
+        for (int e = 0; e < cnt; e++) {
+            if (entry[e] >= leafOffset) continue;
+            const float* b = reinterpret_cast<const float*>(nodes + 10ull * entry[e]);
+            const float dx = b[1] - b[0], dy = b[3] - b[2], dz = b[5] - b[4];
+            const float area = dx * dy + dy * dz + dz * dx;
+            if (pick < 0 || area > best) { pick = e; best = area; }
+        }
+        if (pick < 0) break;
+        const uint32_t k = entry[pick];
+        for (int e = cnt; e > pick + 1; e--) entry[e] = entry[e - 1];
+        entry[pick] = nodes[10ull * k + 7]; entry[pick + 1] = nodes[10ull * k + 6];
+        cnt++;
     }
     float lo[4][3], hi[4][3], org[3], top[3];
     for (int k = 0; k < 3; k++) { org[k] = __int_as_float(0x7f800000); top[k] = __int_as_float(0xff800000); }

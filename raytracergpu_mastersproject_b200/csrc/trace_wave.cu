@@ -37,7 +37,11 @@
 namespace rtb {
 
 constexpr int WAVE_THREADS = 128;
+#ifndef RTB_WIDE_MINB
+#define RTB_WIDE_MINB 7
+#endif
 constexpr int WAVE_MIN_BLOCKS = 6;
+constexpr int WIDE_MIN_BLOCKS = RTB_WIDE_MINB;   // resident CTAs per SM for the 4-ary variant
 
 // CULL (RTB_TRACE_CULLED, default OFF, NOT the reference's traversal): additionally skips children whose box lies outside
 // the axis-aligned box of the ray SEGMENT [tMin, closest-so-far] grown by a safety margin.  The reference visits every
@@ -47,7 +51,7 @@ constexpr int WAVE_MIN_BLOCKS = 6;
 // stretch the slack), hence a flag: tests/test_gpu_parity.py checks images and hit ids stay bit-identical on the test
 // scenes and bench.py --mode culled reports it as a separate, labelled line.
 template <bool COUNT, bool EXT, bool CULL, int NODES>   // NODES: 0 exact 64-B pairs, 1 compressed 32-B pairs, 2 wide 64-B (4-ary)
-__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kernel(const TraceParams p) {
+__global__ void __launch_bounds__(WAVE_THREADS, NODES == 2 ? WIDE_MIN_BLOCKS : WAVE_MIN_BLOCKS) trace_wave_kernel(const TraceParams p) {
     __shared__ WaveSmem<WAVE_THREADS> sm;
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned tid = threadIdx.x;
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) trace_wave_kern
     uint32_t cur = 0xFFFFFFFFu;           // internal node to expand next, or NONE
     int sp = 0;
     uint32_t qHead = 0, qCount = 0;
-    uint32_t lstack[STACK_DEPTH - SSTACK];
+    uint32_t lstack[(NODES == 2 ? WIDE_STACK_DEPTH : STACK_DEPTH) - SSTACK];
     unsigned err = 0;
     Tally tl = { 0, 0, 0, 0, 0 };
 
@@ -227,7 +231,7 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool
     if (count || p.sc.N < 2) nodesMode = 0;                // the instrumented variant counts the reference's visits: exact records
     if (nodesMode == 1 && !p.sc.cnodes) nodesMode = 0;
     if (nodesMode == 2 && !p.sc.wide) nodesMode = 0;
-    if (p.tMin == 0) p.tMin = nodesMode == 2 ? 24 : T_MIN_DEFAULT;   // swept on C2 (RTB_WAVE_TMIN)
+    if (p.tMin == 0) p.tMin = nodesMode == 2 ? 20 : T_MIN_DEFAULT;   // swept on C2 (RTB_WAVE_TMIN)
     const uint32_t pixels = p.W * p.localRows;
     const uint32_t totalSamples = p.sampleCount, skip0 = p.sampleSkip;
     int launches = 0;

@@ -8,7 +8,8 @@ namespace rtb {
 
 constexpr int SSTACK = 32;                // stack entries kept in shared memory; deeper levels spill to local memory
 constexpr int QCAP = 8;                   // pending-leaf FIFO entries per lane
-constexpr int T_MIN_DEFAULT = 20;         // leave the traverse phase when fewer lanes than this can step
+constexpr int T_MIN_DEFAULT = 20;
+constexpr int WIDE_STACK_DEPTH = 128;      // 4-ary records push up to three entries per level: a deeper spill area than the reference's 64         // leave the traverse phase when fewer lanes than this can step
 
 template <int THREADS>
 struct __align__(16) WaveSmem {
