@@ -34,10 +34,8 @@ __device__ __forceinline__ bool box_hit(const f3 o, const f3 d, const float lox,
 // triangleHit, raytraceBVH.comp:118-149.  The ray-independent part of the shader's function -- u, v, the normalised normal
 // and w = N / dot(N, N) (:120-125) -- is evaluated once per triangle by pack_prims_kernel with the shader's operation
 // order and fetched here as one 64-byte record (two 256-bit loads); the ray-dependent part is the shader's, verbatim.
-__device__ __forceinline__ bool triangle_hit(const TraceScene& sc, const uint32_t idx, const f3 o, const f3 d, const float tMin,
-                                             const float tMax, Hit& rec) {
-    const float4* tp = sc.tris + 4ull * idx;
-    const f8 r0 = ldg256(tp), r1 = ldg256(tp + 2);
+__device__ __forceinline__ bool triangle_hit_rec(const f8 r0, const f8 r1, const f3 o, const f3 d, const float tMin, const float tMax,
+                                                 Hit& rec) {
     const f3 v0 = xyz(r0.lo);
     const f3 n = xyz(r0.hi);
     const f3 u = F3(r0.hi.w, r1.lo.x, r1.lo.y);
@@ -59,6 +57,12 @@ __device__ __forceinline__ bool triangle_hit(const TraceScene& sc, const uint32_
     rec.back = back;
     rec.mat = __float_as_uint(r0.lo.w);
     return true;
+}
+__device__ __forceinline__ bool triangle_hit(const TraceScene& sc, const uint32_t idx, const f3 o, const f3 d, const float tMin,
+                                             const float tMax, Hit& rec) {
+    const float4* tp = sc.tris + 4ull * idx;
+    const f8 r0 = ldg256(tp), r1 = ldg256(tp + 2);
+    return triangle_hit_rec(r0, r1, o, d, tMin, tMax, rec);
 }
 
 // sphereHit, raytraceBVH.comp:152-181 (rec.u / rec.v are dead values)

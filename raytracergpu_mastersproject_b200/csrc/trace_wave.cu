@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES == 2 ? WIDE_MIN_BLOCKS : W
                 if (CULL && closest != before) update_segment();
             }
         }
+        qHead = 0;                                                        // every FIFO is empty: rewind (wave_step_w relies on it)
     }
 
     if (err) atomicOr(p.errFlag, err);

@@ -9,6 +9,9 @@ namespace rtb {
 constexpr int SSTACK = 32;                // stack entries kept in shared memory; deeper levels spill to local memory
 constexpr int QCAP = 8;                   // pending-leaf FIFO entries per lane
 constexpr int T_MIN_DEFAULT = 20;
+#ifndef RTB_WIDE_POPS
+#define RTB_WIDE_POPS 1
+#endif
 constexpr int WIDE_STACK_DEPTH = 128;      // 4-ary records push up to three entries per level: a deeper spill area than the reference's 64         // leave the traverse phase when fewer lanes than this can step
 
 template <int THREADS>
@@ -343,12 +346,12 @@ __device__ __forceinline__ void wave_step_w(const TraceScene& sc, WaveSmem<THREA
         const uint32_t before = (first - 1u) & 0xFu;                      // entries ahead of it (all four when there is none)
         const uint32_t enqMask = passMask & leafMask & before;            // leaves ahead of it: test them first, in order
         const uint32_t pushMask = passMask & ~before & ~first;            // everything behind it waits on the stack
-        uint32_t tail = (qHead + qCount) & (QCAP - 1);
-        { const bool en = enqMask & 1u; if (en) sm.queue[tail][tid] = id0 - leafOffset; tail = (tail + (en ? 1u : 0u)) & (QCAP - 1); }
-        { const bool en = enqMask & 2u; if (en) sm.queue[tail][tid] = id1 - leafOffset; tail = (tail + (en ? 1u : 0u)) & (QCAP - 1); }
-        { const bool en = enqMask & 4u; if (en) sm.queue[tail][tid] = id2 - leafOffset; tail = (tail + (en ? 1u : 0u)) & (QCAP - 1); }
-        { const bool en = enqMask & 8u; if (en) sm.queue[tail][tid] = id3 - leafOffset; }
-        qCount += __popc(enqMask);
+        // FIFO append.  trace_wave.cu drains every lane's FIFO in the L phase and rewinds it, so during T the head is slot 0
+        // and the tail is simply qCount (the turn's precondition qCount <= QCAP - 4 leaves room for four appends).
+        { const bool en = enqMask & 1u; if (en) sm.queue[qCount][tid] = id0 - leafOffset; qCount += en ? 1u : 0u; }
+        { const bool en = enqMask & 2u; if (en) sm.queue[qCount][tid] = id1 - leafOffset; qCount += en ? 1u : 0u; }
+        { const bool en = enqMask & 4u; if (en) sm.queue[qCount][tid] = id2 - leafOffset; qCount += en ? 1u : 0u; }
+        { const bool en = enqMask & 8u; if (en) sm.queue[qCount][tid] = id3 - leafOffset; qCount += en ? 1u : 0u; }
         if (sp <= SSTACK - 3) {                                           // the usual case: three predicated shared-memory stores
             { const bool pu = pushMask & 8u; if (pu) sm.stack[sp][tid] = id3; sp += pu ? 1 : 0; }
             { const bool pu = pushMask & 4u; if (pu) sm.stack[sp][tid] = id2; sp += pu ? 1 : 0; }
@@ -371,17 +374,21 @@ __device__ __forceinline__ void wave_step_w(const TraceScene& sc, WaveSmem<THREA
         next = (first & 8u) ? id3 : next;
         cur = next;
     }
-    const bool needPop = cur == 0xFFFFFFFFu && qCount < QCAP;
-    if (needPop && sp == 0) travDone = true;
-    const bool doPop = needPop && sp > 0;
-    uint32_t e = 0;
-    if (doPop && sp <= SSTACK) e = sm.stack[sp - 1][tid];
-    if (doPop && sp > SSTACK) e = lstack[sp - 1 - SSTACK];
-    sp -= doPop ? 1 : 0;
-    const bool popLeaf = doPop && e >= leafOffset;
-    if (popLeaf) sm.queue[(qHead + qCount) & (QCAP - 1)][tid] = e - leafOffset;
-    qCount += popLeaf ? 1u : 0u;
-    if (doPop && !popLeaf) cur = e;
+    // resume from the stack: a popped leaf only moves to the FIFO, so a lane gets up to RTB_WIDE_POPS predicated pops per turn
+#pragma unroll
+    for (int r = 0; r < RTB_WIDE_POPS; r++) {
+        const bool needPop = cur == 0xFFFFFFFFu && qCount < QCAP;
+        if (needPop && sp == 0) travDone = true;
+        const bool doPop = needPop && sp > 0;
+        uint32_t e = 0;
+        if (doPop && sp <= SSTACK) e = sm.stack[sp - 1][tid];
+        if (doPop && sp > SSTACK) e = lstack[sp - 1 - SSTACK];
+        sp -= doPop ? 1 : 0;
+        const bool popLeaf = doPop && e >= leafOffset;
+        if (popLeaf) sm.queue[qCount][tid] = e - leafOffset;
+        qCount += popLeaf ? 1u : 0u;
+        if (doPop && !popLeaf) cur = e;
+    }
 }
 
 // the reference's box test on the EXACT box of leaf candidate g (compressed / wide traversal only)
