@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", default="wave", choices=["wave", "simple", "stream"], help="trace kernel (A/B switch)")
+    ap.add_argument("--no-primary-sharing", action="store_true",
+                    help="trace every sample's (identical, un-jittered) primary ray separately like the shader does (A/B switch, same results)")
     ap.add_argument("--nodes", default="auto", choices=["auto", "exact", "compressed", "wide"],
                     help="traversal records: auto (library default: 4-ary for >= 8192 primitives), exact 64-byte child pairs, "
                          "32-byte compressed, 64-byte 4-ary (A/B switch, same results)")
@@ -263,7 +265,7 @@ def run_b200(args):
         capi.check(L.rtb_clear_image(h, vp(image), W, rows))
         capi.check(L.rtb_build_bvh(h, ubo_p, vp(d_models), vp(d_tris), vp(d_sphs), vp(d_mats), None, None, None, None, None, 0))
         targs.flags = ((capi.TRACE_COUNT if count else 0) | {"simple": capi.TRACE_SIMPLE_KERNEL, "stream": capi.TRACE_STREAM_KERNEL}.get(args.kernel, 0)
-                       | (capi.TRACE_CULLED if args.mode == "culled" else 0) | {"compressed": capi.TRACE_COMPRESSED_NODES, "wide": capi.TRACE_WIDE_NODES, "exact": capi.TRACE_EXACT_NODES}.get(args.nodes, 0))
+                       | (capi.TRACE_CULLED if args.mode == "culled" else 0) | (capi.TRACE_NO_PRIMARY_SHARING if args.no_primary_sharing else 0) | {"compressed": capi.TRACE_COMPRESSED_NODES, "wide": capi.TRACE_WIDE_NODES, "exact": capi.TRACE_EXACT_NODES}.get(args.nodes, 0))
         targs.counters = counters.data_ptr() if count else None
         if trace_events:
             trace_events[0].record(stream)
@@ -289,6 +291,21 @@ def run_b200(args):
     cnt = dict(zip(capi.COUNTER_FIELDS, [int(x) for x in counters.tolist()]))
     local_cnt = cnt
     rays = cnt["rays"]
+    # Rays the kernel really walks: the reference's camera rays are not jittered, so the wave kernel traces each active pixel's
+    # primary ray once per submission and its samples start from that hit (RTB_TRACE_NO_PRIMARY_SHARING switches it off).
+    # Active pixels = rays of an instrumented 1-sample, depth-1 submission.
+    sharing = args.kernel == "wave" and not args.no_primary_sharing and my_count > 1
+    u1 = ubo.copy(); u1["maxRayTraceDepth"] = 1
+    counters.zero_()
+    targs.sampleSkip, targs.sampleCount, targs.flags, targs.counters = 0, 1, capi.TRACE_COUNT, counters.data_ptr()
+    capi.check(L.rtb_raytrace(h, u1.ctypes.data_as(C.c_void_p), vp(image), C.byref(targs)))
+    torch.cuda.synchronize()
+    active_px = int(counters[0])
+    targs.sampleSkip, targs.sampleCount, targs.flags, targs.counters = my_first, my_count, 0, None
+    saved = torch.tensor([active_px * (my_count - 1) if sharing else 0], dtype=torch.int64, device=tdev)
+    if world > 1:
+        dist.all_reduce(saved)
+    rays_traversed = rays - int(saved[0])
 
     # ---- warm-up ----
     for _ in range(max(args.warmup, 0)):
@@ -415,6 +432,8 @@ def run_b200(args):
                                f"samples{world}: sample ranges of {spp // world} spp per rank, scene replicated, NCCL sum-reduce" if by_samples else
                                f"tile{world}: 8-row bands interleaved over {world} rank(s), scene replicated, NCCL all-gather")
         desc["l2"] = "256 MiB buffer written between timed steps (L2 flush)"
+        desc["primary_sharing"] = ("on: the samples of a pixel share one traversal of their identical (un-jittered) primary ray; value counts "
+                                   "the reference's rays, breakdown.rays_traversed_per_step the rays walked" if sharing else "off")
         if args.mode == "culled":
             desc["mode"] = "EXTENSION RTB_TRACE_CULLED: segment-box culling on top of the reference traversal (not the headline mode)"
         line = {
@@ -426,7 +445,8 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "breakdown": {"rays_per_step": rays, "samples_per_step": cnt["samples"], "msamples_per_s": cnt["samples"] / (ms_per_step * 1e-3) / 1e6,
+            "breakdown": {"rays_per_step": rays, "rays_traversed_per_step": rays_traversed,
+                          "mrays_traversed_per_s": rays_traversed / (ms_per_step * 1e-3) / 1e6, "samples_per_step": cnt["samples"], "msamples_per_s": cnt["samples"] / (ms_per_step * 1e-3) / 1e6,
                           "bvh_build_ms": build_ms, "trace_ms": trace_ms, "counters": cnt},
         }
         print(json.dumps(line), flush=True)

@@ -74,6 +74,10 @@ enum {
     RTB_TRACE_COMPRESSED_NODES = 1u << 7, /* 32-byte compressed child pairs (+6 % on C3, -2..4 % on C2 / C4) */
     RTB_TRACE_WIDE_NODES = 1u << 8,     /* 64-byte 4-ary records (+6..21 % on C2..C5) */
     RTB_TRACE_EXACT_NODES = 1u << 9,    /* exact 64-byte child pairs */
+    /* The reference's camera rays have no jitter (raytraceBVH.comp:329-342): the sampleCount samples of a pixel start with the
+     * same primary ray, whose hitBVH result is therefore traced once per pixel per rtb_raytrace call and shared by the samples
+     * (identical results; nothing is kept between calls).  This flag traces it once per sample like the shader does. */
+    RTB_TRACE_NO_PRIMARY_SHARING = 1u << 10,
     RTB_TRACE_CULLED = 1u << 5          /* extension, default off: also skip subtrees outside the box of the ray segment
                                            [tMin, closest] (+ margin).  NOT the reference's traversal (it has no t-interval);
                                            fewer node visits, results empirically identical (see trace_wave.cu) */

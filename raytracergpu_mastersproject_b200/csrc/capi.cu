@@ -45,7 +45,7 @@ struct rtb_ctx {
     // the bound raytrace set: traversal records derived from the reference-layout arrays
     Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag;
     Scratch cnodes, leafBox, wide;    // compressed 32-byte / wide 64-byte traversal records + exact leaf boxes
-    Scratch activePix, sampleBuf;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
+    Scratch activePix, sampleBuf, primaryHits;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
     Scratch poolSlot, poolColor, poolAtt, poolOrg, poolDir, poolNrm, poolList, poolCnt;   // streaming kernel: path pool
     bool bound = false, boundNodes = false, cnodesReady = false, wideReady = false, leafBoxReady = false;
     const void* boundNodesPtr = nullptr;
@@ -173,7 +173,7 @@ int rtb_ctx_destroy(rtb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (Scratch* s : { &c->sortKeys[0], &c->sortKeys[1], &c->sortVals[0], &c->sortVals[1], &c->sortCounts, &c->encRed, &c->enclosing,
                         &c->cinfo, &c->nodes, &c->pairs, &c->ptris, &c->psphs, &c->psphMat, &c->pmats, &c->rootBox, &c->workCounter,
-                        &c->errFlag, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->sampleBuf, &c->poolSlot, &c->poolColor,
+                        &c->errFlag, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->sampleBuf, &c->primaryHits, &c->poolSlot, &c->poolColor,
                         &c->poolAtt, &c->poolOrg, &c->poolDir, &c->poolNrm, &c->poolList, &c->poolCnt })
         release(*s);
     cudaEventDestroy(c->ev0);
@@ -456,6 +456,11 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
             }
             if (nodesMode) { p.sc.cnodes = nodesMode == 1 ? (const uint4*)c->cnodes.p : nullptr; p.sc.leafBox = (const float4*)c->leafBox.p; }
             if (nodesMode == 2) p.sc.wide = (const uint4*)c->wide.p;
+            p.primaryHits = nullptr; p.primaryMode = 0;
+            if (!count && a->sampleCount > 1 && !(a->flags & RTB_TRACE_NO_PRIMARY_SHARING)) {
+                if (ensure(c, c->primaryHits, pixels * 2 * sizeof(float4))) return 1;
+                p.primaryHits = (float4*)c->primaryHits.p;
+            }
             launches = extra + launch_trace_wave(c->stream, p, count, ext, cull, nodesMode, c->smCount, (uint32_t)perPass);
         }
     }

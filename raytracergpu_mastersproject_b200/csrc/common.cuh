@@ -144,6 +144,10 @@ struct TraceParams {
     float4* sampleBuf;                 // [samplesPerPass][slotCapacity]: (colour.xyz, incoming alpha) per (sample, active pixel)
     uint32_t slotCapacity;
     uint32_t firstPass, lastPass;
+    // primary-hit sharing (trace_wave.cu): 0 off | 1 this launch traces ONE primary ray per active pixel and stores its hit |
+    // 2 every (pixel, sample) item starts from the stored hit
+    uint32_t primaryMode;
+    float4* primaryHits;               // [pixels][2]: (t, normal.xyz), (prim, mat, hit, backFace)
     StreamPool pool;
     f3 background;                     // _BACKGROUND_COLOR (0 for the BVH program, (0.1,0.1,0.3) for the non-BVH program)
 };

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES == 2 ? WIDE_MIN_BLOCKS : W
     const uint32_t activeCount = *p.activeCount;
     // item i -> group of 32 active pixels g = i / (32 * S), sample s = (i % (32 * S)) / 32, pixel slot g * 32 + i % 32:
     // the 32 items a warp pulls together are the same sample of 32 neighbouring pixels (coherent primary rays)
-    const uint32_t groupItems = 32u * p.sampleCount;
+    const uint32_t groupItems = 32u * (p.primaryMode == 1u ? 1u : p.sampleCount);
     const uint64_t totalWork = (uint64_t)((activeCount + 31u) / 32u) * groupItems;
     const float T_MIN_RAY = 0.001f, T_MAX_RAY = 10000000.0f;                    // sceneHit :268-269
     constexpr bool CN = NODES != 0;                       // conservative internal boxes: leaves are re-checked exactly
@@ -98,7 +98,13 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES == 2 ? WIDE_MIN_BLOCKS : W
         // =========================================== S: shade / generate =========================================
         while (!dead && (!rayActive || (travDone && qCount == 0))) {
             bool needItem = !rayActive;
-            if (rayActive) {                                              // the ray is finished: rayColor loop body :283-307
+            if (rayActive && p.primaryMode == 1u) {                       // primary-hit launch: keep the hit record, no shading
+                rayActive = false; needItem = true;
+                float4* h = p.primaryHits + 2ull * pix;
+                h[0] = make_float4(rec.t, rec.normal.x, rec.normal.y, rec.normal.z);
+                h[1] = make_float4(__uint_as_float(rec.prim), __uint_as_float(rec.mat), __uint_as_float(hit ? 1u : 0u),
+                                   __uint_as_float((uint32_t)rec.back));
+            } else if (rayActive) {                                       // the ray is finished: rayColor loop body :283-307
                 rayActive = false;
                 if (depth == 0 && smp == 0 && p.firstPass && p.hitPrim) {
                     p.hitPrim[pix] = hit ? rec.prim : 0xFFFFFFFFu;
@@ -155,6 +161,14 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES == 2 ? WIDE_MIN_BLOCKS : W
                 color = F3(0.f, 0.f, 0.f); att = F3(1.f, 1.f, 1.f);
                 depth = 0;
                 o = p.cam.origin; d = primary_direction(p, x, y);
+                if (p.primaryMode == 2u) {                                // the primary ray's hitBVH result, traced once per pixel
+                    const float4 h0 = __ldg(p.primaryHits + 2ull * pix), h1 = __ldg(p.primaryHits + 2ull * pix + 1);
+                    rec.t = h0.x; rec.normal = F3(h0.y, h0.z, h0.w);
+                    rec.prim = __float_as_uint(h1.x); rec.mat = __float_as_uint(h1.y);
+                    hit = __float_as_uint(h1.z) != 0u; rec.back = (int)__float_as_uint(h1.w);
+                    rayActive = true; travDone = true; qCount = 0; qHead = 0; sp = 0; cur = 0xFFFFFFFFu;
+                    continue;                                             // straight to shading
+                }
             }
             // ---- start the ray (hitBVH prologue :196-201 + the root's own box test) ----
             rayActive = true; hit = false; closest = T_MAX_RAY;
@@ -227,12 +241,46 @@ static void launch_wave_variant(cudaStream_t st, const TraceParams& p, int smCou
     trace_wave_kernel<COUNT, EXT, CULL, NODES><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
 }
 
-// One S2 submission = ceil(sampleCount / samplesPerPass) passes of { pre-pass, trace, accumulate }.  Returns #launches.
+static void dispatch_wave(cudaStream_t st, const TraceParams& p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint64_t need) {
+    const int v = (count ? 4 : 0) | (ext ? 2 : 0) | (cull ? 1 : 0);
+    if (nodesMode == 2) {
+        switch (v) {
+        case 0: launch_wave_variant<false, false, false, 2>(st, p, smCount, need); break;
+        case 1: launch_wave_variant<false, false, true, 2>(st, p, smCount, need); break;
+        case 2: launch_wave_variant<false, true, false, 2>(st, p, smCount, need); break;
+        default: launch_wave_variant<false, true, true, 2>(st, p, smCount, need); break;
+        }
+    } else if (nodesMode == 1) {
+        switch (v) {
+        case 0: launch_wave_variant<false, false, false, 1>(st, p, smCount, need); break;
+        case 1: launch_wave_variant<false, false, true, 1>(st, p, smCount, need); break;
+        case 2: launch_wave_variant<false, true, false, 1>(st, p, smCount, need); break;
+        default: launch_wave_variant<false, true, true, 1>(st, p, smCount, need); break;
+        }
+    } else {
+        switch (v) {
+        case 0: launch_wave_variant<false, false, false, 0>(st, p, smCount, need); break;
+        case 1: launch_wave_variant<false, false, true, 0>(st, p, smCount, need); break;
+        case 2: launch_wave_variant<false, true, false, 0>(st, p, smCount, need); break;
+        case 3: launch_wave_variant<false, true, true, 0>(st, p, smCount, need); break;
+        case 4: launch_wave_variant<true, false, false, 0>(st, p, smCount, need); break;
+        case 5: launch_wave_variant<true, false, true, 0>(st, p, smCount, need); break;
+        case 6: launch_wave_variant<true, true, false, 0>(st, p, smCount, need); break;
+        default: launch_wave_variant<true, true, true, 0>(st, p, smCount, need); break;
+        }
+    }
+}
+
+// One S2 submission = ceil(sampleCount / samplesPerPass) passes of { pre-pass, [primary hits,] trace, accumulate }.  Returns #launches.
 int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint32_t samplesPerPass) {
     if (count || p.sc.N < 2) nodesMode = 0;                // the instrumented variant counts the reference's visits: exact records
     if (nodesMode == 1 && !p.sc.cnodes) nodesMode = 0;
     if (nodesMode == 2 && !p.sc.wide) nodesMode = 0;
     if (p.tMin == 0) p.tMin = nodesMode == 2 ? 20 : T_MIN_DEFAULT;   // swept on C2 (RTB_WAVE_TMIN)
+    // Primary-hit sharing: the reference's getRay has no jitter (raytraceBVH.comp:329-342), so the samples of a pixel all start
+    // with the same primary ray and hitBVH returns the same record for each of them.  It is traced once per pixel per submission
+    // (nothing survives the call); the instrumented variant keeps tracing it per sample because it counts the reference's work.
+    const bool share = !count && p.primaryHits != nullptr && p.sampleCount > 1;
     const uint32_t pixels = p.W * p.localRows;
     const uint32_t totalSamples = p.sampleCount, skip0 = p.sampleSkip;
     int launches = 0;
@@ -244,34 +292,15 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool
         cudaMemsetAsync(p.workCounter64, 0, 16, st);                        // work counter + active-pixel count
         if (count) wave_prepass_kernel<true><<<(pixels + 255) / 256, 256, 0, st>>>(p);
         else wave_prepass_kernel<false><<<(pixels + 255) / 256, 256, 0, st>>>(p);
-        const uint64_t need = ((uint64_t)pixels * p.sampleCount + WAVE_THREADS - 1) / WAVE_THREADS;   // never more lanes than items
-        const int v = (count ? 4 : 0) | (ext ? 2 : 0) | (cull ? 1 : 0);
-        if (nodesMode == 2) {
-            switch (v) {
-            case 0: launch_wave_variant<false, false, false, 2>(st, p, smCount, need); break;
-            case 1: launch_wave_variant<false, false, true, 2>(st, p, smCount, need); break;
-            case 2: launch_wave_variant<false, true, false, 2>(st, p, smCount, need); break;
-            default: launch_wave_variant<false, true, true, 2>(st, p, smCount, need); break;
-            }
-        } else if (nodesMode == 1) {
-            switch (v) {
-            case 0: launch_wave_variant<false, false, false, 1>(st, p, smCount, need); break;
-            case 1: launch_wave_variant<false, false, true, 1>(st, p, smCount, need); break;
-            case 2: launch_wave_variant<false, true, false, 1>(st, p, smCount, need); break;
-            default: launch_wave_variant<false, true, true, 1>(st, p, smCount, need); break;
-            }
-        } else {
-            switch (v) {
-            case 0: launch_wave_variant<false, false, false, 0>(st, p, smCount, need); break;
-            case 1: launch_wave_variant<false, false, true, 0>(st, p, smCount, need); break;
-            case 2: launch_wave_variant<false, true, false, 0>(st, p, smCount, need); break;
-            case 3: launch_wave_variant<false, true, true, 0>(st, p, smCount, need); break;
-            case 4: launch_wave_variant<true, false, false, 0>(st, p, smCount, need); break;
-            case 5: launch_wave_variant<true, false, true, 0>(st, p, smCount, need); break;
-            case 6: launch_wave_variant<true, true, false, 0>(st, p, smCount, need); break;
-            default: launch_wave_variant<true, true, true, 0>(st, p, smCount, need); break;
-            }
+        if (share && first == 0) {                                          // one primary ray per active pixel -> primaryHits
+            p.primaryMode = 1;
+            dispatch_wave(st, p, count, ext, cull, nodesMode, smCount, ((uint64_t)pixels + WAVE_THREADS - 1) / WAVE_THREADS);
+            cudaMemsetAsync(p.workCounter64, 0, 8, st);                     // rewind the work counter, keep the active-pixel count
+            launches++;
         }
+        p.primaryMode = share ? 2u : 0u;
+        const uint64_t need = ((uint64_t)pixels * p.sampleCount + WAVE_THREADS - 1) / WAVE_THREADS;   // never more lanes than items
+        dispatch_wave(st, p, count, ext, cull, nodesMode, smCount, need);
         wave_accumulate_kernel<0><<<(pixels + 255) / 256, 256, 0, st>>>(p);
         launches += 3;
     }

@@ -130,10 +130,39 @@ def test_frame_bit_exact(device, cfg, spp, kernel):
     assert nbad == 0, f"{nbad} pixels differ bitwise; max abs diff {np.nanmax(np.abs(img - rr['image']))}"
     assert rt.read_counters() == rr["counters"]
     # the non-instrumented kernel variant must give the same image
-    rt.clear_image()
-    rt.raytrace(ubo, spp, flags=kflag)
-    device.wait_idle()
-    assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"]))
+    # (for spp > 1 the wave kernels share each pixel's primary hit between its samples; once more with that switched off)
+    for extra in ([0, capi.TRACE_NO_PRIMARY_SHARING] if kernel.startswith("wave") else [0]):
+        rt.clear_image(); hp.zero(); ht.zero(); rg.zero()
+        rt.raytrace(ubo, spp, flags=kflag | extra, hit_prim=hp, hit_t=ht, rng_out=rg)
+        device.wait_idle()
+        assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"]))
+        assert np.array_equal(hp.read(np.uint32).reshape(H, W), rr["hit_prim"])
+        assert np.array_equal(_bits(ht.read(np.float32)).reshape(H, W), _bits(rr["hit_t"]))
+        assert np.array_equal(rg.read(np.uint32).reshape(H, W), rr["rng"])
+
+
+def test_multi_pass_bit_identical(device, monkeypatch):
+    """A submission whose per-sample slots exceed the scratch budget runs in several passes (C4 / C5 do at full size):
+    same image, hit ids and RNG states as one pass; the shared primary hits of pass 1 serve the later passes."""
+    from raytracergpu_mastersproject_b200 import Buffer, capi
+    W, H, spp = 128, 96, 20
+    sc = SU.random_scene(21, n_tris=9000, n_spheres=40)          # >= 8192 primitives: 4-ary records
+    ubo = SU.make_ubo(sc, random_state=77)
+    rt = _rt(device, W, H)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.build_bvh(ubo)
+    hp = Buffer(device, 4, W * H); rg = Buffer(device, 4, W * H)
+    rt.clear_image(); rt.raytrace(ubo, spp, hit_prim=hp, rng_out=rg); device.wait_idle()
+    one = rt.read_image(); hp1 = hp.read(np.uint32); rg1 = rg.read(np.uint32)
+    monkeypatch.setenv("RTB_WAVE_SAMPLE_BUF_MB", "1")            # 128 * 96 * 16 B = 192 KiB per sample -> passes of 5 spp
+    for flags in (0, capi.TRACE_NO_PRIMARY_SHARING, capi.TRACE_EXACT_NODES):
+        hp.zero(); rg.zero()
+        rt.clear_image(); rt.raytrace(ubo, spp, flags=flags, hit_prim=hp, rng_out=rg); device.wait_idle()
+        assert np.array_equal(_bits(rt.read_image()), _bits(one))
+        assert np.array_equal(hp.read(np.uint32), hp1) and np.array_equal(rg.read(np.uint32), rg1)
+    ref = O.build_bvh(sc["models"], sc["triangles"], sc["spheres"])
+    rr = O.raytrace(ubo, W, H, ref["tris"], ref["sphs"], sc["materials"], ref["nodes"], spp)
+    assert np.array_equal(_bits(one), _bits(rr["image"]))
 
 
 def test_progressive_equals_fused(device):
