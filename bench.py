@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", default="wave", choices=["wave", "simple", "stream"], help="trace kernel (A/B switch)")
+    ap.add_argument("--reference-order", action="store_true",
+                    help="walk the tree in the reference's visiting order with no t-interval, like the shader (A/B switch, same results)")
     ap.add_argument("--no-primary-sharing", action="store_true",
                     help="trace every sample's (identical, un-jittered) primary ray separately like the shader does (A/B switch, same results)")
     ap.add_argument("--nodes", default="auto", choices=["auto", "exact", "compressed", "wide"],
@@ -265,7 +267,7 @@ def run_b200(args):
         capi.check(L.rtb_clear_image(h, vp(image), W, rows))
         capi.check(L.rtb_build_bvh(h, ubo_p, vp(d_models), vp(d_tris), vp(d_sphs), vp(d_mats), None, None, None, None, None, 0))
         targs.flags = ((capi.TRACE_COUNT if count else 0) | {"simple": capi.TRACE_SIMPLE_KERNEL, "stream": capi.TRACE_STREAM_KERNEL}.get(args.kernel, 0)
-                       | (capi.TRACE_CULLED if args.mode == "culled" else 0) | (capi.TRACE_NO_PRIMARY_SHARING if args.no_primary_sharing else 0) | {"compressed": capi.TRACE_COMPRESSED_NODES, "wide": capi.TRACE_WIDE_NODES, "exact": capi.TRACE_EXACT_NODES}.get(args.nodes, 0))
+                       | (capi.TRACE_CULLED if args.mode == "culled" else 0) | (capi.TRACE_NO_PRIMARY_SHARING if args.no_primary_sharing else 0) | (capi.TRACE_REFERENCE_ORDER if args.reference_order else 0) | {"compressed": capi.TRACE_COMPRESSED_NODES, "wide": capi.TRACE_WIDE_NODES, "exact": capi.TRACE_EXACT_NODES}.get(args.nodes, 0))
         targs.counters = counters.data_ptr() if count else None
         if trace_events:
             trace_events[0].record(stream)

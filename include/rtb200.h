@@ -78,6 +78,11 @@ enum {
      * same primary ray, whose hitBVH result is therefore traced once per pixel per rtb_raytrace call and shared by the samples
      * (identical results; nothing is kept between calls).  This flag traces it once per sample like the shader does. */
     RTB_TRACE_NO_PRIMARY_SHARING = 1u << 10,
+    /* Default for >= 8192 primitives when the scene's hit-point slack is small (DESIGN.md "nearest-first traversal"): the
+     * 4-ary records are walked nearest-first and entries that cannot change the result (beyond the closest hit so far, or
+     * before tMin) are dropped; equal-t ties are resolved as the reference's visiting order would.  This flag keeps the
+     * reference's visiting order with no t-interval, like the shader. */
+    RTB_TRACE_REFERENCE_ORDER = 1u << 11,
     RTB_TRACE_CULLED = 1u << 5          /* extension, default off: also skip subtrees outside the box of the ray segment
                                            [tMin, closest] (+ margin).  NOT the reference's traversal (it has no t-interval);
                                            fewer node visits, results empirically identical (see trace_wave.cu) */

@@ -37,6 +37,7 @@ SPHERE_PRIMITIVE, TRIANGLE_PRIMITIVE = 0, 1
 TRACE_COUNT, TRACE_EXT_MATERIALS, TRACE_ENCLOSING_INF, TRACE_SIMPLE_KERNEL, TRACE_LINEAR_SCAN, TRACE_CULLED = 1, 2, 4, 8, 16, 32
 TRACE_STREAM_KERNEL, TRACE_COMPRESSED_NODES, TRACE_WIDE_NODES, TRACE_EXACT_NODES = 64, 128, 256, 512
 TRACE_NO_PRIMARY_SHARING = 1024
+TRACE_REFERENCE_ORDER = 2048
 
 COUNTER_FIELDS = ("rays", "nodeVisits", "triTests", "sphTests", "matReads", "samples")
 

@@ -368,13 +368,65 @@ __global__ void __launch_bounds__(256) pack_cnodes_kernel(const uint32_t* __rest
     cnodes[2ull * i + 1] = bq;
 }
 
+// Hit-point slack, for the nearest-first t-culled traversal: a point the shader's primitive tests ACCEPT as a hit
+// lies within eta of the primitive, hence inside the primitive's leaf box grown by eta.
+//  * triangle (raytraceBVH.comp:118-149).  Off-plane: t solves n.(o + t d) = n.v0 up to the rounding of three dot products
+//    and P = o + t d is rounded again: <= 1e-5 R with R the largest coordinate magnitude in play (generous: ~40 eps R).
+//    In-plane: aa >= 0, bb >= 0, aa + bb <= 1 are evaluated with rounding and with the rounded u, v, w: |error| <= c eps |w| |pp|
+//    max(|u|, |v|); as a displacement at most 64 eps |w| max(|u|, |v|) (|u| + |v|)^2.  A zero-area triangle (NaN normal) gets inf.
+//  * sphere (raytraceBVH.comp:152-181).  With U = hb^2 - a c evaluated to within dU <= 12 eps |oc|^2, the returned root puts P
+//    at | |P - c|^2 - r^2 | <= 3 dU whatever the size of U, so | |P - c| - r | <= 18 eps |oc|^2 / r <= 1.1e-6 D^2 / r with D the
+//    largest origin-to-centre distance in play.
+// The per-node value is the maximum over the node's subtree (climbed like the refit: the second arrival at a node continues).
+__global__ void __launch_bounds__(256) eta_leaf_kernel(const float4* __restrict__ ptris, uint32_t T, const float4* __restrict__ psphs,
+                                                       uint32_t S, const float4* __restrict__ rootBox, float camMax, float* etaLeaf) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= T + S) return;
+    const float4 lo = rootBox[0], hi = rootBox[1];
+    const float R = fmaxf(camMax, fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z))));
+    float eta;
+    if (g < T) {
+        const float4 r1 = ptris[4ull * g + 1], r2 = ptris[4ull * g + 2], r3 = ptris[4ull * g + 3];
+        const f3 u = F3(r1.w, r2.x, r2.y), v = F3(r2.z, r2.w, r3.x), w = F3(r3.y, r3.z, r3.w);
+        const float lu = sqrtf(dot(u, u)), lv = sqrtf(dot(v, v)), lw = sqrtf(dot(w, w));
+        eta = 64.0f * 5.9604645e-8f * lw * fmaxf(lu, lv) * (lu + lv) * (lu + lv) + 1.0e-5f * R;
+    } else {
+        const float4 sp = psphs[g - T];
+        const float D = 3.4641016f * R;                                    // 2 sqrt(3) R bounds any distance between two points in play
+        eta = 1.1e-6f * D * D / fabsf(sp.w) + 1.0e-5f * R;
+    }
+    if (!(eta < 3.0e38f)) eta = __int_as_float(0x7f800000);               // NaN / overflow
+    etaLeaf[g] = eta;
+}
+__global__ void __launch_bounds__(256) parent_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint32_t* parent) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < 2 || i >= n - 1) return;
+    parent[nodes[10ull * i + 6]] = i;
+    parent[nodes[10ull * i + 7]] = i;
+}
+__global__ void __launch_bounds__(256) eta_climb_kernel(const uint32_t* __restrict__ nodes, const uint32_t* __restrict__ parent, uint32_t n,
+                                                        float* etaNode, unsigned int* arrivals) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < 2 || g >= n) return;
+    uint32_t node = parent[n - 1 + g];
+    while (true) {
+        __threadfence();
+        if (atomicAdd(&arrivals[node], 1u) == 0u) return;                  // the sibling subtree is not finished yet
+        __threadfence();
+        const float a = __ldcg(&etaNode[nodes[10ull * node + 6]]), b = __ldcg(&etaNode[nodes[10ull * node + 7]]);
+        __stcg(&etaNode[node], fmaxf(a, b));
+        if (node == 0) return;
+        node = parent[node];
+    }
+}
+
 // Wide (4-ary) traversal records, 64 B, one per binary internal node X: up to four DESCENDANT entries of X that together
 // cover X's subtree, in the reference's visiting order (e.g. [right.right, right.left, left.right, left.left]), each with its
 // exact box quantised OUTWARD to 8 bits per plane relative to the record's origin / power-of-two scales.  Layout (16 words):
 //   0-2 origin.xyz | 3: Ex, Ey, Ez, meta (bits 0-3 leaf flags, bits 4-7 present flags) | 4-9: one word per plane
 //   (lo.x lo.y lo.z hi.x hi.y hi.z), byte e = entry e, so the kernel picks a ray's near / far planes of all four entries
 //   with one select per word | 10-13: entry node indices (a leaf is leafOffset + primitive id) | 14-15 unused
-__global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* wide) {
+__global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* wide, const float* __restrict__ etaNode) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < 2 || i >= n - 1) return;
     const uint32_t leafOffset = n - 1;
@@ -402,8 +454,9 @@ __global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restri
     for (int k = 0; k < 3; k++) { org[k] = __int_as_float(0x7f800000); top[k] = __int_as_float(0xff800000); }
     for (int e = 0; e < cnt; e++) {
         const float* b = reinterpret_cast<const float*>(nodes + 10ull * entry[e]);
+        const float eta = etaNode ? etaNode[entry[e]] : 0.0f;                          // largest hit-point slack in the entry's subtree
         for (int k = 0; k < 3; k++) {
-            lo[e][k] = b[2 * k]; hi[e][k] = b[2 * k + 1];
+            lo[e][k] = __fsub_rd(b[2 * k], eta); hi[e][k] = __fadd_ru(b[2 * k + 1], eta);
             org[k] = fminf(org[k], lo[e][k]); top[k] = fmaxf(top[k], hi[e][k]);
         }
     }
@@ -523,9 +576,20 @@ void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pai
 void launch_pack_cnodes(cudaStream_t st, const void* nodes, uint32_t n, void* cnodes, void* leafBox) {
     pack_cnodes_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)cnodes, (float4*)leafBox);
 }
-void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide) {
+void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode) {
     if (n < 2) return;
-    pack_wide_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)wide);
+    pack_wide_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)wide, etaNode);
+}
+// etaNode[2n-1] <- per-node hit-point slack; parent[2n-1], arrivals[n-1] are scratch.  Returns #launches.
+int launch_eta(cudaStream_t st, const void* nodes, uint32_t n, const void* ptris, uint32_t T, const void* psphs, uint32_t S,
+               const void* rootBox, float camMax, float* etaNode, uint32_t* parent, unsigned int* arrivals) {
+    if (n < 2) return 0;
+    cudaMemsetAsync(arrivals, 0, sizeof(unsigned int) * (n - 1), st);
+    eta_leaf_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const float4*)ptris, T, (const float4*)psphs, S, (const float4*)rootBox, camMax,
+                                                        etaNode + (n - 1));
+    parent_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, parent);
+    eta_climb_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t*)nodes, parent, n, etaNode, arrivals);
+    return 3;
 }
 void launch_pack_prims(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* mats, uint32_t M,
                        void* ptris, void* psphs, void* sphMat, void* pmats) {

@@ -44,6 +44,9 @@ struct rtb_ctx {
     Scratch sortKeys[2], sortVals[2], sortCounts, encRed, enclosing, cinfo, nodes;
     // the bound raytrace set: traversal records derived from the reference-layout arrays
     Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag;
+    Scratch etaNode, etaParent, etaArrivals;   // per-node hit-point slack (launch_eta) and its scratch
+    float wideCamMax = 0.f;           // camera magnitude the slack of the current 4-ary records covers
+    bool unorderedOk = false;         // eta small enough for the nearest-first, t-culled traversal
     Scratch cnodes, leafBox, wide;    // compressed 32-byte / wide 64-byte traversal records + exact leaf boxes
     Scratch activePix, sampleBuf, primaryHits;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
     Scratch poolSlot, poolColor, poolAtt, poolOrg, poolDir, poolNrm, poolList, poolCnt;   // streaming kernel: path pool
@@ -173,7 +176,7 @@ int rtb_ctx_destroy(rtb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (Scratch* s : { &c->sortKeys[0], &c->sortKeys[1], &c->sortVals[0], &c->sortVals[1], &c->sortCounts, &c->encRed, &c->enclosing,
                         &c->cinfo, &c->nodes, &c->pairs, &c->ptris, &c->psphs, &c->psphMat, &c->pmats, &c->rootBox, &c->workCounter,
-                        &c->errFlag, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->sampleBuf, &c->primaryHits, &c->poolSlot, &c->poolColor,
+                        &c->errFlag, &c->etaNode, &c->etaParent, &c->etaArrivals, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->sampleBuf, &c->primaryHits, &c->poolSlot, &c->poolColor,
                         &c->poolAtt, &c->poolOrg, &c->poolDir, &c->poolNrm, &c->poolList, &c->poolCnt })
         release(*s);
     cudaEventDestroy(c->ev0);
@@ -402,7 +405,8 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     p.counters = (unsigned long long*)a->counters;
     p.workCounter = (unsigned int*)c->workCounter.p;
     p.errFlag = (unsigned int*)c->errFlag.p;
-    { const char* e = getenv("RTB_WAVE_TMIN"); p.tMin = e ? (uint32_t)atoi(e) : 0u; }   // tuning knob, results unaffected
+    { const char* e = getenv("RTB_WAVE_TMIN"); p.tMin = e ? (uint32_t)atoi(e) : 0u; }
+    { const char* e = getenv("RTB_WAVE_QGATE"); p.qGate = e ? (uint32_t)atoi(e) : 4u; }   // tuning knob, results unaffected
     const bool count = (a->flags & RTB_TRACE_COUNT) != 0, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;
     int launches = 1;
     const bool linear = (a->flags & RTB_TRACE_LINEAR_SCAN) != 0;
@@ -439,7 +443,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
             launches = launch_trace_stream(c->stream, p, count, ext, c->smCount, (uint32_t)perPass);
         } else {
             const bool derived = c->boundNodes && c->bN > 1 && !count;
-            const int nodesMode = !derived ? 0 : (a->flags & RTB_TRACE_EXACT_NODES) ? 0 : (a->flags & RTB_TRACE_WIDE_NODES) ? 2
+            int nodesMode = !derived ? 0 : (a->flags & RTB_TRACE_EXACT_NODES) ? 0 : (a->flags & RTB_TRACE_WIDE_NODES) ? 2
                                 : (a->flags & RTB_TRACE_COMPRESSED_NODES) ? 1 : (c->bN >= 8192 ? 2 : 0);
             int extra = 0;
             if (nodesMode && (!c->leafBoxReady || (nodesMode == 1 && !c->cnodesReady))) {   // exact leaf boxes (+ the 32-byte records)
@@ -449,13 +453,28 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
                 c->leafBoxReady = true; if (nodesMode == 1) c->cnodesReady = true;
                 extra++;
             }
-            if (nodesMode == 2 && !c->wideReady) {
-                if (ensure(c, c->wide, 64ull * (c->bN - 1))) return 1;
-                launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wide.p);
+            const float camMax = fmaxf(fmaxf(fabsf(p.cam.origin.x), fabsf(p.cam.origin.y)), fabsf(p.cam.origin.z));
+            if (nodesMode == 2 && (!c->wideReady || camMax > c->wideCamMax)) {
+                // Hit-point slack (bvh_build.cu eta_leaf_kernel): a point the reference's primitive tests accept lies
+                // within eta of the primitive, so inside every record box grown by the largest eta of its subtree.  If any
+                // primitive's slack is not finite (zero-area triangle) the records stay tight and only the reference-order walk
+                // is used.  One 4-byte readback per build.
+                const size_t nn = 2ull * c->bN - 1;
+                if (ensure(c, c->wide, 64ull * (c->bN - 1)) || ensure(c, c->etaNode, 4 * nn) || ensure(c, c->etaParent, 4 * nn) ||
+                    ensure(c, c->etaArrivals, 4ull * c->bN)) return 1;
+                extra += launch_eta(c->stream, c->boundNodesPtr, c->bN, c->ptris.p, c->bT, c->psphs.p, c->bS, c->rootBox.p, camMax,
+                                    (float*)c->etaNode.p, (uint32_t*)c->etaParent.p, (unsigned int*)c->etaArrivals.p);
+                float etaRoot = 0.f;
+                CK(cudaMemcpyAsync(&etaRoot, c->etaNode.p, 4, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                c->unorderedOk = etaRoot >= 0.f && etaRoot < 3.0e38f;
+                launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wide.p, c->unorderedOk ? (const float*)c->etaNode.p : nullptr);
+                c->wideCamMax = camMax;
                 c->wideReady = true; extra++;
             }
             if (nodesMode) { p.sc.cnodes = nodesMode == 1 ? (const uint4*)c->cnodes.p : nullptr; p.sc.leafBox = (const float4*)c->leafBox.p; }
             if (nodesMode == 2) p.sc.wide = (const uint4*)c->wide.p;
+            if (nodesMode == 2 && c->unorderedOk && !cull && !(a->flags & RTB_TRACE_REFERENCE_ORDER)) nodesMode = 3;
             p.primaryHits = nullptr; p.primaryMode = 0;
             if (!count && a->sampleCount > 1 && !(a->flags & RTB_TRACE_NO_PRIMARY_SHARING)) {
                 if (ensure(c, c->primaryHits, pixels * 2 * sizeof(float4))) return 1;

@@ -104,6 +104,28 @@ __device__ __forceinline__ void leaf_test(const TraceScene& sc, const uint32_t g
     }
 }
 
+// Order-free acceptance for the nearest-first traversal (trace_wave.cu, NODES == 3).  The reference tests a ray's leaves in
+// descending primitive id (right-first DFS, leaves kept in input order: ConstructHLBVH.comp:152-169) and accepts
+// tMin <= t <= closest-so-far, so its result is the smallest t and, among equal t, the SMALLEST id -- provided no accepted t
+// is NaN (a zero-area triangle's NaN normal passes every comparison of triangleHit; from then on the outcome depends on the
+// order).  Tested in any order, the same result follows from "t <= closest, but an equal t only replaces a larger id";
+// a NaN t raises `poison` and the caller re-traces the ray in the reference's order.
+template <bool COUNT>
+__device__ __forceinline__ void leaf_test_unordered(const TraceScene& sc, const uint32_t g, const f3 o, const f3 d, const float tMin,
+                                                    float& closest, bool& hit, Hit& rec, Tally& tl, bool& poison) {
+    Hit tmp;
+    bool ok;
+    if (g < sc.T) { if (COUNT) tl.tri++; ok = triangle_hit(sc, g, o, d, tMin, closest, tmp); }
+    else { if (COUNT) tl.sph++; ok = sphere_hit(sc, g - sc.T, o, d, tMin, closest, tmp); }
+    if (ok) {
+        if (tmp.t != tmp.t) poison = true;
+        else if (!(hit && tmp.t == closest && g > rec.prim)) {
+            rec.t = tmp.t; rec.normal = tmp.normal; rec.mat = tmp.mat; rec.back = tmp.back; rec.prim = g;
+            closest = tmp.t; hit = true;
+        }
+    }
+}
+
 // hitBVH, raytraceBVH.comp:195-265, over child-pair records.  Every stack entry is a node whose own box test has
 // already passed (tested when its parent was expanded); entries >= leafOffset are leaves awaiting their
 // primitive test.  Reference visit count: 1 (root) + 2 per expanded internal node.

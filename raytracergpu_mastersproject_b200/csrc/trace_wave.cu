@@ -50,8 +50,9 @@ constexpr int WIDE_MIN_BLOCKS = RTB_WIDE_MINB;   // resident CTAs per SM for the
 // as the margin exceeds the rounding slack of the intersection tests.  That is an argument, not a proof (sliver triangles
 // stretch the slack), hence a flag: tests/test_gpu_parity.py checks images and hit ids stay bit-identical on the test
 // scenes and bench.py --mode culled reports it as a separate, labelled line.
-template <bool COUNT, bool EXT, bool CULL, int NODES>   // NODES: 0 exact 64-B pairs, 1 compressed 32-B pairs, 2 wide 64-B (4-ary)
-__global__ void __launch_bounds__(WAVE_THREADS, NODES == 2 ? WIDE_MIN_BLOCKS : WAVE_MIN_BLOCKS) trace_wave_kernel(const TraceParams p) {
+// NODES: 0 exact 64-B pairs | 1 compressed 32-B pairs | 2 4-ary 64-B records, reference order | 3 4-ary records, nearest-first + t-culled
+template <bool COUNT, bool EXT, bool CULL, int NODES>
+__global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : WAVE_MIN_BLOCKS) trace_wave_kernel(const TraceParams p) {
     __shared__ WaveSmem<WAVE_THREADS> sm;
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned tid = threadIdx.x;
@@ -65,7 +66,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES == 2 ? WIDE_MIN_BLOCKS : W
     const uint64_t totalWork = (uint64_t)((activeCount + 31u) / 32u) * groupItems;
     const float T_MIN_RAY = 0.001f, T_MAX_RAY = 10000000.0f;                    // sceneHit :268-269
     constexpr bool CN = NODES != 0;                       // conservative internal boxes: leaves are re-checked exactly
-    constexpr uint32_t Q_ROOM = NODES == 2 ? 4u : 2u;     // free FIFO entries a turn may need
+    constexpr uint32_t Q_ROOM = NODES >= 2 ? 4u : 2u;     // free FIFO entries a turn may need
+    const uint32_t qGate = NODES == 3 ? min(p.qGate, QCAP - Q_ROOM) : QCAP - Q_ROOM;   // a lane steps while its FIFO holds <= qGate candidates
 
     // ---- per-lane state -------------------------------------------------------------------------------------------
     bool dead = false, rayActive = false, travDone = true, exactOnly = false, hit = false;
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES == 2 ? WIDE_MIN_BLOCKS : W
     uint32_t cur = 0xFFFFFFFFu;           // internal node to expand next, or NONE
     int sp = 0;
     uint32_t qHead = 0, qCount = 0;
-    uint32_t lstack[(NODES == 2 ? WIDE_STACK_DEPTH : STACK_DEPTH) - SSTACK];
+    uint32_t lstack[(NODES >= 2 ? WIDE_STACK_DEPTH : STACK_DEPTH) - SSTACK];
     unsigned err = 0;
     Tally tl = { 0, 0, 0, 0, 0 };
 
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES == 2 ? WIDE_MIN_BLOCKS : W
 
         // =========================================== T: traverse ================================================
         while (true) {
-            const bool can = rayActive && !travDone && qCount <= QCAP - Q_ROOM;
+            const bool can = rayActive && !travDone && qCount <= qGate;
             const unsigned bal = __ballot_sync(FULL, can);
             if (bal == 0) break;
             if (__popc(bal) < (int)p.tMin) {
@@ -197,7 +199,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES == 2 ? WIDE_MIN_BLOCKS : W
             if (can) {
                 // CN: 32-byte compressed records; rays with a zero / denormal direction component (reference yields inf / NaN)
                 // keep to the exact 64-byte records
-                if (NODES == 2 && !exactOnly) wave_step_w<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
+                if (NODES == 3 && !exactOnly) wave_step_u(sc, sm, tid, o, rinv, closest, T_MIN_RAY, cur, sp, qCount, travDone, lstack, err, leafOffset);
+                else if (NODES == 2 && !exactOnly) wave_step_w<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
                 else if (NODES == 1 && !exactOnly) wave_step_c<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
                 else wave_step<COUNT, CULL>(sc, sm, tid, leafOffset, o, d, rinv, exactOnly, cur, sp, qHead, qCount, travDone, lstack, tl, err, segLo, segHi);
             }
@@ -212,6 +215,14 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES == 2 ? WIDE_MIN_BLOCKS : W
                 qHead = (qHead + 1) & (QCAP - 1);
                 qCount--;
                 const float before = closest;
+                if (NODES == 3 && !exactOnly) {
+                    bool poison = false;
+                    if (leaf_box_passes(sc, g, o, d, rinv, false)) leaf_test_unordered<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl, poison);
+                    if (poison) {                                         // NaN hit: the outcome depends on the reference's order -> re-trace in it
+                        exactOnly = true; hit = false; closest = T_MAX_RAY;
+                        sp = 0; qHead = 0; qCount = 0; cur = 0; travDone = false;
+                    }
+                } else
                 if (!CN || exactOnly || leaf_box_passes(sc, g, o, d, rinv, exactOnly)) leaf_test<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl);
                 if (CULL && closest != before) update_segment();
             }
@@ -243,7 +254,10 @@ static void launch_wave_variant(cudaStream_t st, const TraceParams& p, int smCou
 
 static void dispatch_wave(cudaStream_t st, const TraceParams& p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint64_t need) {
     const int v = (count ? 4 : 0) | (ext ? 2 : 0) | (cull ? 1 : 0);
-    if (nodesMode == 2) {
+    if (nodesMode == 3) {
+        if (ext) launch_wave_variant<false, true, false, 3>(st, p, smCount, need);
+        else launch_wave_variant<false, false, false, 3>(st, p, smCount, need);
+    } else if (nodesMode == 2) {
         switch (v) {
         case 0: launch_wave_variant<false, false, false, 2>(st, p, smCount, need); break;
         case 1: launch_wave_variant<false, false, true, 2>(st, p, smCount, need); break;
@@ -275,8 +289,9 @@ static void dispatch_wave(cudaStream_t st, const TraceParams& p, bool count, boo
 int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint32_t samplesPerPass) {
     if (count || p.sc.N < 2) nodesMode = 0;                // the instrumented variant counts the reference's visits: exact records
     if (nodesMode == 1 && !p.sc.cnodes) nodesMode = 0;
-    if (nodesMode == 2 && !p.sc.wide) nodesMode = 0;
-    if (p.tMin == 0) p.tMin = nodesMode == 2 ? 20 : T_MIN_DEFAULT;   // swept on C2 (RTB_WAVE_TMIN)
+    if (nodesMode >= 2 && !p.sc.wide) nodesMode = 0;
+    if (nodesMode == 3 && cull) nodesMode = 2;             // the segment-box extension belongs to the reference-order walk
+    if (p.tMin == 0) p.tMin = nodesMode >= 2 ? 20 : T_MIN_DEFAULT;   // swept on C2 (RTB_WAVE_TMIN)
     // Primary-hit sharing: the reference's getRay has no jitter (raytraceBVH.comp:329-342), so the samples of a pixel all start
     // with the same primary ray and hitBVH returns the same record for each of them.  It is traced once per pixel per submission
     // (nothing survives the call); the instrumented variant keeps tracing it per sample because it counts the reference's work.

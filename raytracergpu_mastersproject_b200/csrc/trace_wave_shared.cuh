@@ -391,6 +391,100 @@ __device__ __forceinline__ void wave_step_w(const TraceScene& sc, WaveSmem<THREA
     }
 }
 
+// Nearest-first, t-culled turn over the same 64-byte records (NODES == 3).  Which leaves the reference tests does not depend on
+// the order or on hits (no t-interval in its box test), but which of them can still CHANGE the result does: a primitive whose
+// accepted hit would lie beyond the closest hit so far, or before tMin, cannot.  The record boxes are grown by the hit-point
+// slack eta (pack_wide_kernel), so an accepted hit at parameter t lies inside every grown ancestor box and t is inside that
+// box's slab interval; an entry is dropped when its interval, after granting the evaluation error |tol|, lies entirely beyond
+// `closest` or before tMin.  Entries are taken nearest-first (the nearest surviving internal entry is descended, the others
+// wait on the stack, all surviving leaves are queued); the L phase resolves equal-t ties like the reference's order would
+// (leaf_test_unordered).  closest only shrinks, so a dropped entry stays irrelevant.
+template <int THREADS>
+__device__ __forceinline__ void wave_step_u(const TraceScene& sc, WaveSmem<THREADS>& sm, const unsigned tid, const f3 o, const f3 rinv,
+                                            const float closest, const float tMinRay, uint32_t& cur, int& sp, uint32_t& qCount,
+                                            bool& travDone, uint32_t* lstack, unsigned& err, const uint32_t leafOffset) {
+    if (cur != 0xFFFFFFFFu) {
+        const uint4* rp = sc.wide + 4ull * cur;
+        const f8 h0 = ldg256(rp), h1 = ldg256(rp + 2);
+        const uint32_t w3 = __float_as_uint(h0.lo.w);
+        const uint32_t lox = __float_as_uint(h0.hi.x), loy = __float_as_uint(h0.hi.y), loz = __float_as_uint(h0.hi.z),
+                       hix = __float_as_uint(h0.hi.w), hiy = __float_as_uint(h1.lo.x), hiz = __float_as_uint(h1.lo.y);
+        const uint32_t id0 = __float_as_uint(h1.lo.z), id1 = __float_as_uint(h1.lo.w), id2 = __float_as_uint(h1.hi.x),
+                       id3 = __float_as_uint(h1.hi.y);
+        const float sx = __uint_as_float((w3 & 0xFFu) << 23), sy = __uint_as_float(((w3 >> 8) & 0xFFu) << 23),
+                    sz = __uint_as_float(((w3 >> 16) & 0xFFu) << 23);
+        const float ax = sx * rinv.x, ay = sy * rinv.y, az = sz * rinv.z;
+        const float bx = (h0.lo.x - o.x) * rinv.x, by = (h0.lo.y - o.y) * rinv.y, bz = (h0.lo.z - o.z) * rinv.z;
+        const float m = fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(bx)), fmaf(255.0f, fabsf(ay), fabsf(by))), fmaf(255.0f, fabsf(az), fabsf(bz)));
+        const float tol = -2.0e-6f * m;                                   // NaN / inf -> nothing is dropped
+        const float farLimit = closest - tol, nearLimit = tMinRay + tol;  // drop when tn > closest + |tol| or tf < tMin - |tol|
+        const bool ngx = rinv.x < 0.0f, ngy = rinv.y < 0.0f, ngz = rinv.z < 0.0f;
+        const uint32_t nX = ngx ? hix : lox, fX = ngx ? lox : hix;
+        const uint32_t nY = ngy ? hiy : loy, fY = ngy ? loy : hiy;
+        const uint32_t nZ = ngz ? hiz : loz, fZ = ngz ? loz : hiz;
+        const uint32_t meta = w3 >> 24;
+        uint32_t passMask = 0;
+        float tnE[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+#define RTB_B(w) __uint2float_rn(((w) >> (8 * e)) & 0xFFu)
+            const float tn = fmaxf(fmaxf(fmaf(RTB_B(nX), ax, bx), fmaf(RTB_B(nY), ay, by)), fmaf(RTB_B(nZ), az, bz));
+            const float tf = fminf(fminf(fmaf(RTB_B(fX), ax, bx), fmaf(RTB_B(fY), ay, by)), fmaf(RTB_B(fZ), az, bz));
+#undef RTB_B
+            const bool pass = !((tf - tn) < tol) && !(tn > farLimit) && !(tf < nearLimit);
+            passMask |= pass ? (1u << e) : 0u;
+            tnE[e] = tn;
+        }
+        passMask &= meta >> 4;
+        const uint32_t leafMask = meta & 0xFu;
+        const uint32_t intMask = passMask & ~leafMask;
+        // nearest surviving internal entry (one-hot; a NaN tn never compares equal -> falls back to the lowest bit)
+        const float INF = __int_as_float(0x7f800000);
+        const float k0 = (intMask & 1u) ? tnE[0] : INF, k1 = (intMask & 2u) ? tnE[1] : INF, k2 = (intMask & 4u) ? tnE[2] : INF,
+                    k3 = (intMask & 8u) ? tnE[3] : INF;
+        const float kmin = fminf(fminf(k0, k1), fminf(k2, k3));
+        uint32_t first = ((intMask & 1u) && k0 == kmin) ? 1u : ((intMask & 2u) && k1 == kmin) ? 2u : ((intMask & 4u) && k2 == kmin) ? 4u
+                       : ((intMask & 8u) && k3 == kmin) ? 8u : 0u;
+        if (first == 0u) first = intMask & (0u - intMask);
+        const uint32_t enqMask = passMask & leafMask;                     // every surviving leaf is a candidate now
+        const uint32_t pushMask = intMask & ~first;
+        { const bool en = enqMask & 1u; if (en) sm.queue[qCount][tid] = id0 - leafOffset; qCount += en ? 1u : 0u; }
+        { const bool en = enqMask & 2u; if (en) sm.queue[qCount][tid] = id1 - leafOffset; qCount += en ? 1u : 0u; }
+        { const bool en = enqMask & 4u; if (en) sm.queue[qCount][tid] = id2 - leafOffset; qCount += en ? 1u : 0u; }
+        { const bool en = enqMask & 8u; if (en) sm.queue[qCount][tid] = id3 - leafOffset; qCount += en ? 1u : 0u; }
+        if (sp <= SSTACK - 3) {
+            { const bool pu = pushMask & 8u; if (pu) sm.stack[sp][tid] = id3; sp += pu ? 1 : 0; }
+            { const bool pu = pushMask & 4u; if (pu) sm.stack[sp][tid] = id2; sp += pu ? 1 : 0; }
+            { const bool pu = pushMask & 2u; if (pu) sm.stack[sp][tid] = id1; sp += pu ? 1 : 0; }
+            { const bool pu = pushMask & 1u; if (pu) sm.stack[sp][tid] = id0; sp += pu ? 1 : 0; }
+        } else {
+#pragma unroll 1
+            for (int k = 3; k >= 0; k--) {
+                if (!((pushMask >> k) & 1u)) continue;
+                const uint32_t v = k == 3 ? id3 : (k == 2 ? id2 : (k == 1 ? id1 : id0));
+                if (sp < SSTACK) sm.stack[sp][tid] = v;
+                else if (sp < WIDE_STACK_DEPTH) lstack[sp - SSTACK] = v;
+                else { err |= 1u; continue; }
+                sp++;
+            }
+        }
+        uint32_t next = 0xFFFFFFFFu;
+        next = (first & 1u) ? id0 : next;
+        next = (first & 2u) ? id1 : next;
+        next = (first & 4u) ? id2 : next;
+        next = (first & 8u) ? id3 : next;
+        cur = next;
+    }
+    const bool needPop = cur == 0xFFFFFFFFu;
+    if (needPop && sp == 0) travDone = true;
+    const bool doPop = needPop && sp > 0;
+    uint32_t e = 0xFFFFFFFFu;
+    if (doPop && sp <= SSTACK) e = sm.stack[sp - 1][tid];
+    if (doPop && sp > SSTACK) e = lstack[sp - 1 - SSTACK];
+    sp -= doPop ? 1 : 0;
+    if (doPop) cur = e;
+}
+
 // the reference's box test on the EXACT box of leaf candidate g (compressed / wide traversal only)
 __device__ __forceinline__ bool leaf_box_passes(const TraceScene& sc, const uint32_t g, const f3 o, const f3 d, const f3 rinv, const bool exactOnly) {
     const f8 b = ldg256(sc.leafBox + 2ull * g);

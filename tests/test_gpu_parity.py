@@ -95,13 +95,14 @@ def test_s1_stage_by_stage(device, cfg):
 
 @pytest.mark.parametrize("cfg", SCENES, ids=lambda c: f"seed{c['seed']}")
 @pytest.mark.parametrize("spp", [1, 5])
-@pytest.mark.parametrize("kernel", ["wave", "wave-exact-nodes", "wave-compressed-nodes", "wave-wide-nodes", "simple", "stream"])
+@pytest.mark.parametrize("kernel", ["wave", "wave-exact-nodes", "wave-compressed-nodes", "wave-wide-nodes", "wave-wide-reference-order", "simple", "stream"])
 def test_frame_bit_exact(device, cfg, spp, kernel):
     """Whole frame (S1 fused + S2): node array, hit ids, RNG states, counters and the fp32 image, all bit-exact.
     Both trace kernels: the production warp-coherent one and the straightforward one kept for A/B measurements."""
     from raytracergpu_mastersproject_b200 import Buffer, capi
     kflag = {"simple": capi.TRACE_SIMPLE_KERNEL, "stream": capi.TRACE_STREAM_KERNEL, "wave-compressed-nodes": capi.TRACE_COMPRESSED_NODES, "wave-wide-nodes": capi.TRACE_WIDE_NODES,
-             "wave-exact-nodes": capi.TRACE_EXACT_NODES}.get(kernel, 0)
+             "wave-exact-nodes": capi.TRACE_EXACT_NODES,
+             "wave-wide-reference-order": capi.TRACE_WIDE_NODES | capi.TRACE_REFERENCE_ORDER}.get(kernel, 0)
     W, H = 96, 72
     sc = SU.random_scene(**cfg)
     ubo = SU.make_ubo(sc, max_depth=8, random_state=12345 + cfg["seed"])
@@ -155,7 +156,7 @@ def test_multi_pass_bit_identical(device, monkeypatch):
     rt.clear_image(); rt.raytrace(ubo, spp, hit_prim=hp, rng_out=rg); device.wait_idle()
     one = rt.read_image(); hp1 = hp.read(np.uint32); rg1 = rg.read(np.uint32)
     monkeypatch.setenv("RTB_WAVE_SAMPLE_BUF_MB", "1")            # 128 * 96 * 16 B = 192 KiB per sample -> passes of 5 spp
-    for flags in (0, capi.TRACE_NO_PRIMARY_SHARING, capi.TRACE_EXACT_NODES):
+    for flags in (0, capi.TRACE_NO_PRIMARY_SHARING, capi.TRACE_EXACT_NODES, capi.TRACE_REFERENCE_ORDER):
         hp.zero(); rg.zero()
         rt.clear_image(); rt.raytrace(ubo, spp, flags=flags, hit_prim=hp, rng_out=rg); device.wait_idle()
         assert np.array_equal(_bits(rt.read_image()), _bits(one))
@@ -395,6 +396,83 @@ def test_degenerate_and_extreme_geometry_nan_parity(device):
         rt.raytrace(ubo, spp, flags=capi.TRACE_COUNT | fl); device.wait_idle()
         assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"]))
         assert rt.read_counters() == rr["counters"]
+        if fl == 0:   # 4-ary records: the zero-area triangles make the hit-point slack infinite -> reference-order walk
+            for fl2 in (capi.TRACE_WIDE_NODES, capi.TRACE_WIDE_NODES | capi.TRACE_REFERENCE_ORDER):
+                rt.clear_image(); rt.raytrace(ubo, spp, flags=fl2); device.wait_idle()
+                assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"]))
+
+
+def _check_against_oracle(device, sc, ubo, W, H, spp, flag_sets):
+    from raytracergpu_mastersproject_b200 import Buffer
+    ref = O.build_bvh(sc["models"], sc["triangles"], sc["spheres"])
+    rr = O.raytrace(ubo, W, H, ref["tris"], ref["sphs"], sc["materials"], ref["nodes"], spp)
+    rt = _rt(device, W, H)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.build_bvh(ubo)
+    hp = Buffer(device, 4, W * H); ht = Buffer(device, 4, W * H); rg = Buffer(device, 4, W * H)
+    for fl in flag_sets:
+        hp.zero(); ht.zero(); rg.zero()
+        rt.clear_image(); rt.raytrace(ubo, spp, flags=fl, hit_prim=hp, hit_t=ht, rng_out=rg); device.wait_idle()
+        assert np.array_equal(hp.read(np.uint32).reshape(H, W), rr["hit_prim"]), f"flags {fl}: primary hit ids differ"
+        assert np.array_equal(_bits(ht.read(np.float32)).reshape(H, W), _bits(rr["hit_t"])), f"flags {fl}: primary hit t differs"
+        assert np.array_equal(rg.read(np.uint32).reshape(H, W), rr["rng"]), f"flags {fl}: RNG states differ"
+        assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"])), f"flags {fl}: image differs"
+    return rr
+
+
+def test_nearest_first_equal_t_ties(device):
+    """Nearest-first traversal tests leaves in a different order than the reference; equal-t hits must still resolve to the
+    primitive the reference's order ends with (the smallest id).  Every triangle of the scene exists three times (same
+    vertices, different ids and materials), spheres twice, and the room's quads are split along a diagonal that pixels hit."""
+    from raytracergpu_mastersproject_b200 import capi
+    W, H, spp = 96, 72, 4
+    sc = SU.random_scene(51, n_tris=250, n_spheres=12)
+    t = sc["triangles"]; s = sc["spheres"]
+    t2 = t.copy(); t2["materialIndex"] = (t2["materialIndex"] + 1) % len(sc["materials"])
+    t3 = t.copy(); t3["materialIndex"] = (t3["materialIndex"] + 3) % len(sc["materials"])
+    s2 = s.copy(); s2["materialIndex"] = (s2["materialIndex"] + 2) % len(sc["materials"])
+    sc = dict(sc, triangles=np.concatenate([t, t2, t3]), spheres=np.concatenate([s, s2]))
+    ubo = SU.make_ubo(sc, random_state=5)
+    rr = _check_against_oracle(device, sc, ubo, W, H, spp,
+                               [capi.TRACE_WIDE_NODES, capi.TRACE_WIDE_NODES | capi.TRACE_REFERENCE_ORDER, capi.TRACE_EXACT_NODES])
+    hp = rr["hit_prim"]; T0, S0 = len(t), len(s)
+    assert (hp != 0xFFFFFFFF).mean() > 0.2
+    tri = hp[hp < 3 * T0]; sph = hp[(hp >= 3 * T0) & (hp != 0xFFFFFFFF)]
+    assert len(tri) and (tri < T0).all(), "the reference's order ends with the first copy of a triplicated triangle"
+    assert (sph < 3 * T0 + S0).all()
+
+
+@pytest.mark.parametrize("angle", [3e-2, 1e-3, 1e-5, 1e-7])
+def test_nearest_first_sliver_triangles(device, angle):
+    """Thin triangles stretch the slack between an accepted hit point and the triangle (the barycentric tests are evaluated with
+    rounding): moderate slivers widen the culling boxes, extreme ones switch the scene to the reference-order walk.  Either
+    way the frame is the oracle's, bit for bit."""
+    from raytracergpu_mastersproject_b200 import capi
+    W, H, spp = 80, 60, 3
+    sc = SU.random_scene(61, n_tris=400, n_spheres=0)
+    t = sc["triangles"]
+    rng = np.random.default_rng(7)
+    for i in range(20, len(t), 3):                       # every third random triangle becomes a sliver of the given apex angle
+        v0 = t["v0"][i, :3]; e = t["v1"][i, :3] - v0
+        perp = np.cross(e, rng.uniform(-1, 1, 3)); perp /= np.linalg.norm(perp) + 1e-30
+        t["v2"][i, :3] = v0 + e * np.float32(0.9) + perp * np.float32(np.linalg.norm(e) * angle)
+    ubo = SU.make_ubo(sc, random_state=23)
+    _check_against_oracle(device, sc, ubo, W, H, spp, [capi.TRACE_WIDE_NODES, capi.TRACE_WIDE_NODES | capi.TRACE_REFERENCE_ORDER])
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 1e4])
+def test_nearest_first_scene_scales(device, scale):
+    """The slack terms scale with the scene: the same scene at three magnitudes (model matrices and camera scaled)."""
+    from raytracergpu_mastersproject_b200 import capi
+    W, H, spp = 80, 60, 3
+    sc = SU.random_scene(71, n_tris=500, n_spheres=25)
+    m = sc["models"]["m"].reshape(-1, 4, 4).copy()
+    m[:, :, :3] *= np.float32(scale)                     # m[col][row]: scales rotation/scale columns and the translation
+    sc["models"]["m"] = m.reshape(-1, 16)
+    sc["spheres"]["radius"] *= np.float32(scale)
+    ubo = SU.make_ubo(sc, random_state=31)
+    ubo["camPos"][0, :3] *= np.float32(scale); ubo["camLookAt"][0, :3] *= np.float32(scale)
+    _check_against_oracle(device, sc, ubo, W, H, spp, [capi.TRACE_WIDE_NODES, capi.TRACE_WIDE_NODES | capi.TRACE_REFERENCE_ORDER])
 
 
 def test_empty_and_zero_sample_submissions(device):
