@@ -368,32 +368,43 @@ __global__ void __launch_bounds__(256) pack_cnodes_kernel(const uint32_t* __rest
     cnodes[2ull * i + 1] = bq;
 }
 
-// Hit-point slack, for the nearest-first t-culled traversal: a point the shader's primitive tests ACCEPT as a hit
-// lies within eta of the primitive, hence inside the primitive's leaf box grown by eta.
-//  * triangle (raytraceBVH.comp:118-149).  Off-plane: t solves n.(o + t d) = n.v0 up to the rounding of three dot products
-//    and P = o + t d is rounded again: <= 1e-5 R with R the largest coordinate magnitude in play (generous: ~40 eps R).
-//    In-plane: aa >= 0, bb >= 0, aa + bb <= 1 are evaluated with rounding and with the rounded u, v, w: |error| <= c eps |w| |pp|
-//    max(|u|, |v|); as a displacement at most 64 eps |w| max(|u|, |v|) (|u| + |v|)^2.  A zero-area triangle (NaN normal) gets inf.
-//  * sphere (raytraceBVH.comp:152-181).  With U = hb^2 - a c evaluated to within dU <= 12 eps |oc|^2, the returned root puts P
-//    at | |P - c|^2 - r^2 | <= 3 dU whatever the size of U, so | |P - c| - r | <= 18 eps |oc|^2 / r <= 1.1e-6 D^2 / r with D the
-//    largest origin-to-centre distance in play.
+// Hit-point slack, for the nearest-first t-culled traversal: a point P the shader's primitive tests ACCEPT as a hit
+// of a ray whose origin lies inside the (slightly grown) root box is within eta of the primitive, hence inside the primitive's
+// leaf box grown by eta.  eps = 2^-24; R = largest coordinate magnitude of the grown root box.
+//  * triangle (raytraceBVH.comp:118-149).  Off the shader's plane {n.x = n.v0}: the three dot products, the subtraction and
+//    the division leave |n.(o + t d) - n.v0| <= 8 eps (|o| + |v0| + |t d|) <= 3e-6 R; rounding of P, of u = v1 - v0 and
+//    v = v2 - v0: < 1e-6 R.  Together < 1e-5 R.  In the plane: the tests aa >= 0, bb >= 0, aa + bb <= 1 are evaluated with
+//    rounding (|error| <= 7 eps |w| |pp| |v|) and with the rounded w, whose relative error is <= 12 eps / sin(theta) + 5 eps
+//    because cross(u, v) cancels (theta = angle between u and v, 1 / sin(theta) = |u| |v| |w|); the stored normal tilts by the
+//    same 4 eps / sin(theta).  As a displacement: <= 24 eps (1 + 1/sin(theta)) |w| |u| |v| (|u| + |v|); the kernel uses 64 eps.
+//    Needle angles below 1e-4 rad, zero-area triangles (NaN normal) and microscopic ones (|w| > 1e18) get eta = inf.
+//  * sphere (raytraceBVH.comp:152-181).  The returned root t satisfies | |P(t) - c|^2 - r^2 | <= 31 eps (|oc| + r)^2 however
+//    small the discriminant (the perturbed quadratic it solves exactly differs by that much), so | |P - c| - r | <=
+//    31 eps (|oc| + r)^2 / r; |oc| <= distance from the centre to the farthest corner of the grown root box.  The kernel
+//    uses 62 eps = 4e-6 (+ the same 1e-5 R for the rounding of P).
 // The per-node value is the maximum over the node's subtree (climbed like the refit: the second arrival at a node continues).
 __global__ void __launch_bounds__(256) eta_leaf_kernel(const float4* __restrict__ ptris, uint32_t T, const float4* __restrict__ psphs,
-                                                       uint32_t S, const float4* __restrict__ rootBox, float camMax, float* etaLeaf) {
+                                                       uint32_t S, const float4* __restrict__ rootBox, float* etaLeaf) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= T + S) return;
-    const float4 lo = rootBox[0], hi = rootBox[1];
-    const float R = fmaxf(camMax, fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z))));
+    float4 lo = rootBox[0], hi = rootBox[1];
+    const float grow = 1.0e-3f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);   // = the ray-origin test of trace_wave.cu
+    lo.x -= grow; lo.y -= grow; lo.z -= grow; hi.x += grow; hi.y += grow; hi.z += grow;
+    const float R = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
     float eta;
     if (g < T) {
         const float4 r1 = ptris[4ull * g + 1], r2 = ptris[4ull * g + 2], r3 = ptris[4ull * g + 3];
         const f3 u = F3(r1.w, r2.x, r2.y), v = F3(r2.z, r2.w, r3.x), w = F3(r3.y, r3.z, r3.w);
         const float lu = sqrtf(dot(u, u)), lv = sqrtf(dot(v, v)), lw = sqrtf(dot(w, w));
-        eta = 64.0f * 5.9604645e-8f * lw * fmaxf(lu, lv) * (lu + lv) * (lu + lv) + 1.0e-5f * R;
+        const float invSin = lu * lv * lw;
+        eta = 64.0f * 5.9604645e-8f * (1.0f + invSin) * lw * lu * lv * (lu + lv) + 1.0e-5f * R;
+        if (!(invSin < 1.0e4f) || !(lw < 1.0e18f)) eta = __int_as_float(0x7f800000);
     } else {
         const float4 sp = psphs[g - T];
-        const float D = 3.4641016f * R;                                    // 2 sqrt(3) R bounds any distance between two points in play
-        eta = 1.1e-6f * D * D / fabsf(sp.w) + 1.0e-5f * R;
+        const float dx = fmaxf(fabsf(sp.x - lo.x), fabsf(hi.x - sp.x)), dy = fmaxf(fabsf(sp.y - lo.y), fabsf(hi.y - sp.y)),
+                    dz = fmaxf(fabsf(sp.z - lo.z), fabsf(hi.z - sp.z));
+        const float r = fabsf(sp.w), D = sqrtf(dx * dx + dy * dy + dz * dz) + r;
+        eta = 4.0e-6f * D * D / r + 1.0e-5f * R;
     }
     if (!(eta < 3.0e38f)) eta = __int_as_float(0x7f800000);               // NaN / overflow
     etaLeaf[g] = eta;
@@ -582,10 +593,10 @@ void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide
 }
 // etaNode[2n-1] <- per-node hit-point slack; parent[2n-1], arrivals[n-1] are scratch.  Returns #launches.
 int launch_eta(cudaStream_t st, const void* nodes, uint32_t n, const void* ptris, uint32_t T, const void* psphs, uint32_t S,
-               const void* rootBox, float camMax, float* etaNode, uint32_t* parent, unsigned int* arrivals) {
+               const void* rootBox, float* etaNode, uint32_t* parent, unsigned int* arrivals) {
     if (n < 2) return 0;
     cudaMemsetAsync(arrivals, 0, sizeof(unsigned int) * (n - 1), st);
-    eta_leaf_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const float4*)ptris, T, (const float4*)psphs, S, (const float4*)rootBox, camMax,
+    eta_leaf_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const float4*)ptris, T, (const float4*)psphs, S, (const float4*)rootBox,
                                                         etaNode + (n - 1));
     parent_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, parent);
     eta_climb_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t*)nodes, parent, n, etaNode, arrivals);

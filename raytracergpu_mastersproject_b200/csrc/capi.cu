@@ -45,7 +45,6 @@ struct rtb_ctx {
     // the bound raytrace set: traversal records derived from the reference-layout arrays
     Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag;
     Scratch etaNode, etaParent, etaArrivals;   // per-node hit-point slack (launch_eta) and its scratch
-    float wideCamMax = 0.f;           // camera magnitude the slack of the current 4-ary records covers
     bool unorderedOk = false;         // eta small enough for the nearest-first, t-culled traversal
     Scratch cnodes, leafBox, wide;    // compressed 32-byte / wide 64-byte traversal records + exact leaf boxes
     Scratch activePix, sampleBuf, primaryHits;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
@@ -453,23 +452,22 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
                 c->leafBoxReady = true; if (nodesMode == 1) c->cnodesReady = true;
                 extra++;
             }
-            const float camMax = fmaxf(fmaxf(fabsf(p.cam.origin.x), fabsf(p.cam.origin.y)), fabsf(p.cam.origin.z));
-            if (nodesMode == 2 && (!c->wideReady || camMax > c->wideCamMax)) {
-                // Hit-point slack (bvh_build.cu eta_leaf_kernel): a point the reference's primitive tests accept lies
-                // within eta of the primitive, so inside every record box grown by the largest eta of its subtree.  If any
+            if (nodesMode == 2 && !c->wideReady) {
+                // Hit-point slack (bvh_build.cu eta_leaf_kernel): a point the reference's primitive tests accept, for a
+                // ray that starts inside the scene's box, lies within eta of the primitive, so inside every record box grown by
+                // the largest eta of its subtree.  If any
                 // primitive's slack is not finite (zero-area triangle) the records stay tight and only the reference-order walk
                 // is used.  One 4-byte readback per build.
                 const size_t nn = 2ull * c->bN - 1;
                 if (ensure(c, c->wide, 64ull * (c->bN - 1)) || ensure(c, c->etaNode, 4 * nn) || ensure(c, c->etaParent, 4 * nn) ||
                     ensure(c, c->etaArrivals, 4ull * c->bN)) return 1;
-                extra += launch_eta(c->stream, c->boundNodesPtr, c->bN, c->ptris.p, c->bT, c->psphs.p, c->bS, c->rootBox.p, camMax,
+                extra += launch_eta(c->stream, c->boundNodesPtr, c->bN, c->ptris.p, c->bT, c->psphs.p, c->bS, c->rootBox.p,
                                     (float*)c->etaNode.p, (uint32_t*)c->etaParent.p, (unsigned int*)c->etaArrivals.p);
                 float etaRoot = 0.f;
                 CK(cudaMemcpyAsync(&etaRoot, c->etaNode.p, 4, cudaMemcpyDeviceToHost, c->stream));
                 CK(cudaStreamSynchronize(c->stream));
                 c->unorderedOk = etaRoot >= 0.f && etaRoot < 3.0e38f;
                 launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wide.p, c->unorderedOk ? (const float*)c->etaNode.p : nullptr);
-                c->wideCamMax = camMax;
                 c->wideReady = true; extra++;
             }
             if (nodesMode) { p.sc.cnodes = nodesMode == 1 ? (const uint4*)c->cnodes.p : nullptr; p.sc.leafBox = (const float4*)c->leafBox.p; }

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
     const uint32_t qGate = NODES == 3 ? min(p.qGate, QCAP - Q_ROOM) : QCAP - Q_ROOM;   // a lane steps while its FIFO holds <= qGate candidates
 
     // ---- per-lane state -------------------------------------------------------------------------------------------
-    bool dead = false, rayActive = false, travDone = true, exactOnly = false, hit = false;
+    bool dead = false, rayActive = false, travDone = true, exactOnly = false, hit = false, cullOk = false;
     uint32_t depth = 0, rng = 0, pix = 0, smp = 0;
     size_t slotIndex = 0;
     f3 color = F3(0, 0, 0), att = F3(1, 1, 1);
@@ -180,6 +180,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             if (COUNT) { tl.rays++; tl.visits++; }
             if (CULL) update_segment();                                                    // closest = tMax: nothing is culled yet
             const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
+            if (NODES == 3) {   // the slack the records were grown by covers rays that start inside the scene's box (+ 0.1 %): others are not culled
+                const float grow = 1.0e-3f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
+                cullOk = o.x >= lo.x - grow && o.x <= hi.x + grow && o.y >= lo.y - grow && o.y <= hi.y + grow && o.z >= lo.z - grow && o.z <= hi.z + grow;
+            }
             if (box_test(o, d, rinv, exactOnly, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) {
                 if (sc.N == 1) enqueue(0u);                                                // the root is the only leaf
                 else { cur = 0; travDone = false; }
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             if (can) {
                 // CN: 32-byte compressed records; rays with a zero / denormal direction component (reference yields inf / NaN)
                 // keep to the exact 64-byte records
-                if (NODES == 3 && !exactOnly) wave_step_u(sc, sm, tid, o, rinv, closest, T_MIN_RAY, cur, sp, qCount, travDone, lstack, err, leafOffset);
+                if (NODES == 3 && !exactOnly) wave_step_u(sc, sm, tid, o, rinv, cullOk ? closest : __int_as_float(0x7f800000), cullOk ? T_MIN_RAY : __int_as_float(0xff800000), cur, sp, qCount, travDone, lstack, err, leafOffset);
                 else if (NODES == 2 && !exactOnly) wave_step_w<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
                 else if (NODES == 1 && !exactOnly) wave_step_c<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
                 else wave_step<COUNT, CULL>(sc, sm, tid, leafOffset, o, d, rinv, exactOnly, cur, sp, qHead, qCount, travDone, lstack, tl, err, segLo, segHi);
