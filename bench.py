@@ -82,7 +82,7 @@ def workload(cfg_name, spp_override=0):
                     f"{cfg['width']}x{cfg['height']}, {spp} spp, max depth {sc['max_depth']}, randomState {cfg['random_state']}",
         "scene": cfg["spec"], "triangles": len(sc["triangles"]), "spheres": len(sc["spheres"]),
         "width": cfg["width"], "height": cfg["height"], "spp": spp, "max_depth": sc["max_depth"],
-        "mode": "reference-parity (metal/dielectric absorb, exact traversal order)",
+        "mode": "reference-parity (metal/dielectric absorb like the shader; frame bit-identical to the oracle)",
     }
     return cfg, sc, ubo, spp, desc
 
@@ -434,6 +434,8 @@ def run_b200(args):
                                f"samples{world}: sample ranges of {spp // world} spp per rank, scene replicated, NCCL sum-reduce" if by_samples else
                                f"tile{world}: 8-row bands interleaved over {world} rank(s), scene replicated, NCCL all-gather")
         desc["l2"] = "256 MiB buffer written between timed steps (L2 flush)"
+        desc["traversal"] = ("reference visiting order, no t-interval (--reference-order)" if args.reference_order or args.kernel != "wave" else
+                             "library default: 4-ary records walked nearest-first with t-culling when the scene qualifies, else the reference's order")
         desc["primary_sharing"] = ("on: the samples of a pixel share one traversal of their identical (un-jittered) primary ray; value counts "
                                    "the reference's rays, breakdown.rays_traversed_per_step the rays walked" if sharing else "off")
         if args.mode == "culled":
