@@ -475,6 +475,38 @@ def test_nearest_first_scene_scales(device, scale):
     _check_against_oracle(device, sc, ubo, W, H, spp, [capi.TRACE_WIDE_NODES, capi.TRACE_WIDE_NODES | capi.TRACE_REFERENCE_ORDER])
 
 
+@pytest.mark.parametrize("spec,rs", [("meshRoom:70:5", 3), ("meshRoom:110:9", 4), ("heightField:90:70:6:40", 5),
+                                     ("sphereField:12000:7", 6), ("simpleScene", 7), ("complexScene", 8)])
+def test_nearest_first_equals_reference_order_mid_size(device, spec, rs):
+    """The generators behind C2..C5 at sizes where a 320x240 / 8 spp / depth 8 frame takes milliseconds: the nearest-first
+    t-culled walk (library default for these sizes, and forced on the two small reference scenes), the same records in the
+    reference's order, and the exact records must agree on the whole frame, the primary hit ids and the RNG states; the
+    exact-record frame is checked against the oracle on two rows."""
+    from raytracergpu_mastersproject_b200 import Buffer, Raytracer, capi, make_ubo, scenes
+    W, H, spp = 320, 240, 8
+    sc = scenes.load_scene(spec)
+    T, S = len(sc["triangles"]), len(sc["spheres"])
+    ubo = make_ubo(T, S, len(sc["materials"]), 8, rs, sc["vfov"])
+    rt = Raytracer(device, W, H)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.build_bvh(ubo)
+    hp = Buffer(device, 4, W * H); rg = Buffer(device, 4, W * H)
+    out = {}
+    for name, fl in (("exact", capi.TRACE_EXACT_NODES), ("default", 0), ("nearest", capi.TRACE_WIDE_NODES),
+                     ("ordered", capi.TRACE_WIDE_NODES | capi.TRACE_REFERENCE_ORDER),
+                     ("nearest-unshared", capi.TRACE_WIDE_NODES | capi.TRACE_NO_PRIMARY_SHARING)):
+        hp.zero(); rg.zero()
+        rt.clear_image(); rt.raytrace(ubo, spp, flags=fl, hit_prim=hp, rng_out=rg); device.wait_idle()
+        out[name] = (rt.read_image().copy(), hp.read(np.uint32), rg.read(np.uint32))
+    for name in out:
+        assert np.array_equal(_bits(out[name][0]), _bits(out["exact"][0])), f"{spec}: {name} image differs from the exact-record walk"
+        assert np.array_equal(out[name][1], out["exact"][1]), f"{spec}: {name} primary hit ids differ"
+        assert np.array_equal(out[name][2], out["exact"][2]), f"{spec}: {name} RNG states differ"
+    ref = O.build_bvh(sc["models"], sc["triangles"], sc["spheres"])
+    r = O.raytrace(ubo, W, H, ref["tris"], ref["sphs"], sc["materials"], ref["nodes"], spp, rows=(100, 102), want_hits=False, want_rng=False)
+    assert np.array_equal(_bits(out["exact"][0][100:102]), _bits(r["image"][100:102]))
+
+
 def test_empty_and_zero_sample_submissions(device):
     from raytracergpu_mastersproject_b200 import RtbError, capi
     sc = SU.random_scene(44, n_tris=20, n_spheres=2)
