@@ -405,6 +405,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     p.workCounter = (unsigned int*)c->workCounter.p;
     p.errFlag = (unsigned int*)c->errFlag.p;
     { const char* e = getenv("RTB_WAVE_TMIN"); p.tMin = e ? (uint32_t)atoi(e) : 0u; }
+    { const char* e = getenv("RTB_WAVE_SORTED_PUSH"); p.sortedPush = e ? (uint32_t)atoi(e) : (c->bS > c->bT ? 1u : 0u); }   // measured: +16 % C3, -2..7 % C2/C4/C5
     { const char* e = getenv("RTB_WAVE_QGATE"); p.qGate = e ? (uint32_t)atoi(e) : 4u; }   // tuning knob, results unaffected
     const bool count = (a->flags & RTB_TRACE_COUNT) != 0, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;
     int launches = 1;

@@ -136,6 +136,7 @@ struct TraceParams {
     unsigned int* workCounter;         // persistent-thread tile counter
     unsigned int* errFlag;             // bit0: traversal stack overflow
     uint32_t tilesX, tilesY;
+    uint32_t sortedPush;               // nearest-first kernel: pick the variant that stacks waiting entries farthest-first
     uint32_t qGate;                    // nearest-first kernel: a lane keeps stepping while its FIFO holds <= qGate candidates
     uint32_t tMin;                     // wave kernel: minimum stepping lanes to stay in the traverse phase (0 = default)
     // wave kernel, per pass: (pixel, sample) work items

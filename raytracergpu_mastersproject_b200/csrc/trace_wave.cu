@@ -51,6 +51,7 @@ constexpr int WIDE_MIN_BLOCKS = RTB_WIDE_MINB;   // resident CTAs per SM for the
 // stretch the slack), hence a flag: tests/test_gpu_parity.py checks images and hit ids stay bit-identical on the test
 // scenes and bench.py --mode culled reports it as a separate, labelled line.
 // NODES: 0 exact 64-B pairs | 1 compressed 32-B pairs | 2 4-ary 64-B records, reference order | 3 4-ary records, nearest-first + t-culled
+//        | 4 = 3 with the waiting entries stacked farthest-first (pays off on overlapping sphere fields: +16 % C3, -2..7 % C2 / C4 / C5)
 template <bool COUNT, bool EXT, bool CULL, int NODES>
 __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : WAVE_MIN_BLOCKS) trace_wave_kernel(const TraceParams p) {
     __shared__ WaveSmem<WAVE_THREADS> sm;
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
     const float T_MIN_RAY = 0.001f, T_MAX_RAY = 10000000.0f;                    // sceneHit :268-269
     constexpr bool CN = NODES != 0;                       // conservative internal boxes: leaves are re-checked exactly
     constexpr uint32_t Q_ROOM = NODES >= 2 ? 4u : 2u;     // free FIFO entries a turn may need
-    const uint32_t qGate = NODES == 3 ? min(p.qGate, QCAP - Q_ROOM) : QCAP - Q_ROOM;   // a lane steps while its FIFO holds <= qGate candidates
+    const uint32_t qGate = NODES >= 3 ? min(p.qGate, QCAP - Q_ROOM) : QCAP - Q_ROOM;   // a lane steps while its FIFO holds <= qGate candidates
 
     // ---- per-lane state -------------------------------------------------------------------------------------------
     bool dead = false, rayActive = false, travDone = true, exactOnly = false, hit = false, cullOk = false;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             if (COUNT) { tl.rays++; tl.visits++; }
             if (CULL) update_segment();                                                    // closest = tMax: nothing is culled yet
             const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
-            if (NODES == 3) {   // the slack the records were grown by covers rays that start inside the scene's box (+ 0.1 %): others are not culled
+            if (NODES >= 3) {   // the slack the records were grown by covers rays that start inside the scene's box (+ 0.1 %): others are not culled
                 const float grow = 1.0e-3f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
                 cullOk = o.x >= lo.x - grow && o.x <= hi.x + grow && o.y >= lo.y - grow && o.y <= hi.y + grow && o.z >= lo.z - grow && o.z <= hi.z + grow;
             }
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             if (can) {
                 // CN: 32-byte compressed records; rays with a zero / denormal direction component (reference yields inf / NaN)
                 // keep to the exact 64-byte records
-                if (NODES == 3 && !exactOnly) wave_step_u(sc, sm, tid, o, rinv, cullOk ? closest : __int_as_float(0x7f800000), cullOk ? T_MIN_RAY : __int_as_float(0xff800000), cur, sp, qCount, travDone, lstack, err, leafOffset);
+                if (NODES >= 3 && !exactOnly) wave_step_u<NODES == 4>(sc, sm, tid, o, rinv, cullOk ? closest : __int_as_float(0x7f800000), cullOk ? T_MIN_RAY : __int_as_float(0xff800000), cur, sp, qCount, travDone, lstack, err, leafOffset);
                 else if (NODES == 2 && !exactOnly) wave_step_w<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
                 else if (NODES == 1 && !exactOnly) wave_step_c<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
                 else wave_step<COUNT, CULL>(sc, sm, tid, leafOffset, o, d, rinv, exactOnly, cur, sp, qHead, qCount, travDone, lstack, tl, err, segLo, segHi);
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
                 qHead = (qHead + 1) & (QCAP - 1);
                 qCount--;
                 const float before = closest;
-                if (NODES == 3 && !exactOnly) {
+                if (NODES >= 3 && !exactOnly) {
                     bool poison = false;
                     if (leaf_box_passes(sc, g, o, d, rinv, false)) leaf_test_unordered<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl, poison);
                     if (poison) {                                         // NaN hit: the outcome depends on the reference's order -> re-trace in it
@@ -258,7 +259,10 @@ static void launch_wave_variant(cudaStream_t st, const TraceParams& p, int smCou
 
 static void dispatch_wave(cudaStream_t st, const TraceParams& p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint64_t need) {
     const int v = (count ? 4 : 0) | (ext ? 2 : 0) | (cull ? 1 : 0);
-    if (nodesMode == 3) {
+    if (nodesMode == 3 && p.sortedPush) {
+        if (ext) launch_wave_variant<false, true, false, 4>(st, p, smCount, need);
+        else launch_wave_variant<false, false, false, 4>(st, p, smCount, need);
+    } else if (nodesMode == 3) {
         if (ext) launch_wave_variant<false, true, false, 3>(st, p, smCount, need);
         else launch_wave_variant<false, false, false, 3>(st, p, smCount, need);
     } else if (nodesMode == 2) {

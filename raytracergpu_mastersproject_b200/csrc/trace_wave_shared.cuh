@@ -399,7 +399,7 @@ __device__ __forceinline__ void wave_step_w(const TraceScene& sc, WaveSmem<THREA
 // `closest` or before tMin.  Entries are taken nearest-first (the nearest surviving internal entry is descended, the others
 // wait on the stack, all surviving leaves are queued); the L phase resolves equal-t ties like the reference's order would
 // (leaf_test_unordered).  closest only shrinks, so a dropped entry stays irrelevant.
-template <int THREADS>
+template <bool SORTED_PUSH, int THREADS>
 __device__ __forceinline__ void wave_step_u(const TraceScene& sc, WaveSmem<THREADS>& sm, const unsigned tid, const f3 o, const f3 rinv,
                                             const float closest, const float tMinRay, uint32_t& cur, int& sp, uint32_t& qCount,
                                             bool& travDone, uint32_t* lstack, unsigned& err, const uint32_t leafOffset) {
@@ -452,7 +452,23 @@ __device__ __forceinline__ void wave_step_u(const TraceScene& sc, WaveSmem<THREA
         { const bool en = enqMask & 2u; if (en) sm.queue[qCount][tid] = id1 - leafOffset; qCount += en ? 1u : 0u; }
         { const bool en = enqMask & 4u; if (en) sm.queue[qCount][tid] = id2 - leafOffset; qCount += en ? 1u : 0u; }
         { const bool en = enqMask & 8u; if (en) sm.queue[qCount][tid] = id3 - leafOffset; qCount += en ? 1u : 0u; }
-        if (sp <= SSTACK - 3) {
+        if (SORTED_PUSH && sp <= SSTACK - 3) {
+            // farthest first, so that the nearest waiting entry is popped first: slot of entry e = number of waiting entries
+            // that are farther (ties: higher index counts as farther)
+            const uint32_t m0 = pushMask & 1u, m1 = (pushMask >> 1) & 1u, m2 = (pushMask >> 2) & 1u, m3 = (pushMask >> 3) & 1u;
+            const uint32_t c01 = tnE[1] >= tnE[0], c02 = tnE[2] >= tnE[0], c03 = tnE[3] >= tnE[0], c12 = tnE[2] >= tnE[1],
+                           c13 = tnE[3] >= tnE[1], c23 = tnE[3] >= tnE[2];
+            // every present pair (e < f) adds one to exactly one of the two slots, so the slots are a permutation even with NaNs
+            const uint32_t r0 = (m1 & c01) + (m2 & c02) + (m3 & c03);
+            const uint32_t r1 = (m0 & (c01 ^ 1u)) + (m2 & c12) + (m3 & c13);
+            const uint32_t r2 = (m0 & (c02 ^ 1u)) + (m1 & (c12 ^ 1u)) + (m3 & c23);
+            const uint32_t r3 = (m0 & (c03 ^ 1u)) + (m1 & (c13 ^ 1u)) + (m2 & (c23 ^ 1u));
+            if (pushMask & 1u) sm.stack[sp + r0][tid] = id0;
+            if (pushMask & 2u) sm.stack[sp + r1][tid] = id1;
+            if (pushMask & 4u) sm.stack[sp + r2][tid] = id2;
+            if (pushMask & 8u) sm.stack[sp + r3][tid] = id3;
+            sp += __popc(pushMask);
+        } else if (sp <= SSTACK - 3) {
             { const bool pu = pushMask & 8u; if (pu) sm.stack[sp][tid] = id3; sp += pu ? 1 : 0; }
             { const bool pu = pushMask & 4u; if (pu) sm.stack[sp][tid] = id2; sp += pu ? 1 : 0; }
             { const bool pu = pushMask & 2u; if (pu) sm.stack[sp][tid] = id1; sp += pu ? 1 : 0; }
