@@ -19,6 +19,7 @@ per rank, no data-path collective while tracing), then ONE NCCL all-gather assem
            here: no Vulkan ICD / lavapipe in the image), timed on a bounded sample of the same workload.
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -54,6 +55,8 @@ def parse_args():
     ap.add_argument("--nodes", default="auto", choices=["auto", "exact", "compressed", "wide"],
                     help="traversal records: auto (library default: 4-ary for >= 8192 primitives), exact 64-byte child pairs, "
                          "32-byte compressed, 64-byte 4-ary (A/B switch, same results)")
+    ap.add_argument("--emulate-rank", default="", help="debugging: 'r/n' renders only the bands rank r of n would own, on one GPU, "
+                                                         "without the collective (the per-rank workload of a tile-mode run, e.g. for ncu)")
     ap.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
                     help="N > 1: tiles = 8-row bands + all-gather (bit-identical, default); samples = sample ranges + sum-reduce (C5)")
     ap.add_argument("--mode", default="exact", choices=["exact", "culled"],
@@ -91,48 +94,64 @@ def workload(cfg_name, spp_override=0):
 # clocks sampling (B200_PROFILING.md recipe)
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 20 ms from well before the warm-up (it needs a few hundred ms to start); only the samples whose
+    own timestamp falls inside the timed region (+- one period) are reported, falling back to the warm-up + timed span when a
+    very short timed region caught none."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t_load = self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
 
+    def mark_load(self):      # the GPU is under the benchmark's load from here (warm-up)
+        self.t_load = datetime.datetime.now()
+
+    def mark_begin(self):
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.p.kill()
         self.f.flush(); self.f.seek(0)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 10:
                 continue
             try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(parts[2]), float(parts[3]), [n for n, v in zip(names, parts[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
         os.unlink(self.f.name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        pad = datetime.timedelta(milliseconds=20)
+        window, scope = [r for r in rows if self.t0 and self.t1 and self.t0 - pad <= r[0] <= self.t1 + pad], "timed region"
+        if not window:
+            window, scope = [r for r in rows if self.t_load and self.t1 and self.t_load <= r[0] <= self.t1 + pad], "warm-up + timed region"
+        if not window:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
+        reasons = sorted({n for r in window for n in r[3]})
+        return {"sm_mhz": float(np.median([r[1] for r in window])), "sm_max_mhz": float(max(r[2] for r in window)), "reasons": reasons,
+                "samples": len(window), "scope": scope}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -232,7 +251,9 @@ def run_b200(args):
     # band sharding of the frame (bit-identical to 1 GPU, tests/test_gpu_parity.py::test_tile_sharding_bit_identical)
     from raytracergpu_mastersproject_b200.sharding import BandLayout, assemble_gathered, single_gpu_layout
     by_samples = world > 1 and args.shard == "samples"
-    layout = BandLayout(H, world, BAND_ROWS) if (world > 1 and not by_samples) else single_gpu_layout(H)
+    emu = tuple(int(x) for x in args.emulate_rank.split("/")) if args.emulate_rank and world == 1 else None
+    layout = (BandLayout(H, world, BAND_ROWS) if (world > 1 and not by_samples) else
+              BandLayout(H, emu[1], BAND_ROWS) if emu else single_gpu_layout(H))
     rows, band_rows = layout.local_rows, layout.band_rows
     from raytracergpu_mastersproject_b200.sharding import sample_range
     my_first, my_count = sample_range(spp, world, rank) if by_samples else (0, spp)
@@ -257,6 +278,8 @@ def run_b200(args):
     targs.imageWidth, targs.imageHeight, targs.localRows = W, H, rows
     tiled = world > 1 and not by_samples
     targs.bandRows, targs.bandFirst, targs.bandStep = band_rows, (rank if tiled else 0), (world if tiled else 1)
+    if emu:
+        targs.bandFirst, targs.bandStep = emu[0], emu[1]
     targs.sampleSkip, targs.sampleCount, targs.flags = my_first, my_count, 0
 
     vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
@@ -282,8 +305,10 @@ def run_b200(args):
         elif world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), image.view(-1))
             final.copy_(assemble_gathered(gathered, layout))      # rank r, local band b -> global band b*world + r
-        capi.check(L.rtb_resolve_rgba8(h, vp(final), W, H, spp, vp(rgba8)))
+        capi.check(L.rtb_resolve_rgba8(h, vp(final), W, rows if emu else H, spp, vp(rgba8)))
 
+    sampler = ClockSampler(local_rank)     # started early: nvidia-smi needs a few hundred ms before its first sample
+    sampler.start()
     # ---- work counters (deterministic; one instrumented, untimed frame) ----
     counters.zero_()
     frame(count=True)
@@ -310,17 +335,17 @@ def run_b200(args):
     rays_traversed = rays - int(saved[0])
 
     # ---- warm-up ----
+    sampler.mark_load()
     for _ in range(max(args.warmup, 0)):
         flush.zero_()
         frame()
     torch.cuda.synchronize()
 
     # ---- timed: exactly K steps, L2 flushed between steps, device-timed ----
-    sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    sampler.mark_begin()
     launches0 = dev.launch_count()
     step_ev, trace_ev = [], []
     for _ in range(args.steps):
@@ -333,6 +358,7 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark_end()
     launches = dev.launch_count() - launches0
     clocks = sampler.stop()
     step_ms = sum(a.elapsed_time(b) for a, b in step_ev)
