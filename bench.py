@@ -147,6 +147,9 @@ class ClockSampler:
         window, scope = [r for r in rows if self.t0 and self.t1 and self.t0 - pad <= r[0] <= self.t1 + pad], "timed region"
         if not window:
             window, scope = [r for r in rows if self.t_load and self.t1 and self.t_load <= r[0] <= self.t1 + pad], "warm-up + timed region"
+        if not window and self.t0 and self.t1:      # region shorter than the sampling period: the samples right around it
+            near = datetime.timedelta(milliseconds=500)
+            window, scope = [r for r in rows if self.t0 - near <= r[0] <= self.t1 + near], "within 0.5 s of the timed region (shorter than the sampling period)"
         if not window:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
         reasons = sorted({n for r in window for n in r[3]})
