@@ -1,0 +1,182 @@
+"""Generates tests/golden/spirv_*.npz by executing THE REFERENCE'S OWN COMPILED SHADERS.
+
+The reference commits its compute shaders as SPIR-V binaries (`RaytracerGPU_MastersProject/shaders/compiled/*.spv`, built by its
+`compile.bat` with glslc).  No Vulkan driver exists in this image, but `oracle/spirv_interp.py` executes those binaries on the CPU,
+instruction by instruction, in the dispatch order and with the dispatch sizes of `RaytracerBVH.cpp:734-1050` /
+`Raytracer.cpp:394-538` / `LogisticMap.cpp:384`.  The vectors written here are therefore outputs of the reference itself (its
+binaries, not a restatement of its sources); the driver-defined built-in arithmetic follows the pins listed in
+`oracle/spirv_interp.py` (sin / cos = the oracle's pinned recipe, the single thing borrowed from the oracle).
+
+This script needs `/root/reference` and therefore only runs in the build container:
+    python tests/golden/make_spirv_golden.py            # ~2 minutes
+The fixtures it writes are committed; `tests/test_spirv_golden.py` checks the C oracle (CPU) and the CUDA path (GPU) against them.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import scene_util as SU  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+SPV_DIR = os.environ.get("RTB_REFERENCE_SPV", "/root/reference/RaytracerGPU_MastersProject/shaders/compiled")
+
+# name -> scene (tests/scene_util.random_scene arguments, or "dups"), image size, dispatches (= raysPerPixel), programs to run
+CASES = {
+    # K1..K6 + raytraceBVH.comp (BVH program) + raytrace.comp (non-BVH program) + fragment resolve
+    "room": dict(scene=dict(seed=1, n_tris=30, n_spheres=6), W=48, H=40, spp=3, depth=8, random_state=12345,
+                 programs=("bvh", "linear", "resolve")),
+    # primitives pre-sorted by the reference's Morton code (the layout the big configs use), other seed / depth
+    "sorted": dict(scene=dict(seed=2, n_tris=90, n_spheres=14, sort_morton=True), W=40, H=40, spp=2, depth=5, random_state=777,
+                   programs=("bvh",)),
+    # no room: most rays miss, spheres dominate; odd image size (partial workgroups)
+    "spheres": dict(scene=dict(seed=3, n_tris=0, n_spheres=40, room=False), W=37, H=29, spp=2, depth=8, random_state=4242,
+                    programs=("bvh", "linear")),
+    # duplicated primitives: equal Morton codes -> the index tie-break of ConstructHLBVH.comp:64-67; build only
+    "dups": dict(scene="dups", W=8, H=8, spp=1, depth=2, random_state=9, programs=("bvh",)),
+    # smallest trees: N = 2 (one internal node) and N = 3
+    "two": dict(scene=dict(seed=5, n_tris=1, n_spheres=1, room=False), W=8, H=8, spp=1, depth=2, random_state=1, programs=("bvh",)),
+    "three": dict(scene=dict(seed=6, n_tris=2, n_spheres=1, room=False), W=8, H=8, spp=1, depth=2, random_state=2, programs=("bvh",)),
+}
+LOGISTIC = dict(points=2048, W=96, H=64, steps=3, seed=11)
+
+
+def make_scene(spec):
+    if spec == "dups":
+        base = SU.random_scene(4, n_tris=12, n_spheres=4)
+        sc = dict(base)
+        sc["triangles"] = np.concatenate([base["triangles"], base["triangles"][6:], base["triangles"][6:12]])
+        sc["spheres"] = np.concatenate([base["spheres"], base["spheres"], base["spheres"][:2]])
+        return sc
+    return SU.random_scene(**spec)
+
+
+def _sincos(x):
+    s, c = O.pin_sincos(x)
+    return float(s), float(c)
+
+
+def module(name):
+    from oracle.spirv_interp import Module
+    return Module(os.path.join(SPV_DIR, name + ".spv"), sincos=_sincos)
+
+
+def run_build(sc, ubo):
+    """S1 as recorded at RaytracerBVH.cpp:778-991: the six build dispatches, every intermediate buffer kept."""
+    T, S = len(sc["triangles"]), len(sc["spheres"]); N = T + S
+    ub = bytearray(ubo.tobytes())
+    tris = bytearray(sc["triangles"].tobytes()) if T else bytearray(64)
+    sphs = bytearray(sc["spheres"].tobytes()) if S else bytearray(32)
+    models = bytearray(sc["models"].tobytes())
+    scratch = bytearray(80)                                                         # 20 floats, RaytracerBVH.cpp:480-508
+    out = {}
+    module("ModelSpaceToWorldSpace.comp").dispatch((N // 32 + 1, 1, 1), {0: ub, 1: models, 2: tris, 3: sphs})            # :789
+    out["tris_w"] = np.frombuffer(bytes(tris), O.TRIANGLE)[:T].copy(); out["sphs_w"] = np.frombuffer(bytes(sphs), O.SPHERE)[:S].copy()
+    enc = bytearray(32)
+    module("GetEnclosingAABB.comp").dispatch((1, 1, 1), {0: ub, 1: enc, 2: tris, 3: sphs, 4: scratch}, lockstep=True)     # :842
+    out["enclosing"] = np.frombuffer(bytes(enc), O.ENCLOSING).copy()
+    m1, m2 = bytearray(12 * N), bytearray(12 * N)
+    module("GenerateMortonCodesOfPrimitives.comp").dispatch((N // 32 + 1, 1, 1), {0: ub, 1: enc, 2: tris, 3: sphs, 4: m1, 5: scratch})   # :879
+    out["morton_unsorted"] = np.frombuffer(bytes(m1), O.MORTON).copy()
+    module("RadixSortSimple.comp").dispatch((1, 1, 1), {0: ub, 1: m1, 2: m2}, lockstep=True)                               # :916
+    out["morton"] = np.frombuffer(bytes(m1), O.MORTON).copy()
+    nodes, cinfo = bytearray(40 * (2 * N - 1)), bytearray(8 * (2 * N - 1))
+    module("ConstructHLBVH.comp").dispatch((N // 256 + 1, 1, 1), {0: ub, 1: tris, 2: sphs, 3: m1, 4: nodes, 5: cinfo})      # :954
+    out["nodes_unfitted"] = np.frombuffer(bytes(nodes), O.NODE).copy(); out["cinfo_unfitted"] = np.frombuffer(bytes(cinfo), O.CINFO).copy()
+    module("ConstructAABBsOfInternalNodes.comp").dispatch((N // 32 + 1, 1, 1), {0: ub, 1: nodes, 2: cinfo})                 # :991
+    out["nodes"] = np.frombuffer(bytes(nodes), O.NODE).copy(); out["cinfo"] = np.frombuffer(bytes(cinfo), O.CINFO).copy()
+    return out
+
+
+def run_trace(shader, ubo, W, H, spp, tris_w, sphs_w, mats, nodes):
+    """S2 as recorded at RaytracerBVH.cpp:998-1050 (Raytracer.cpp:485-509 for the non-BVH program): the image is cleared to
+    (0, 0, 0, 1) (:772) and the shader is dispatched raysPerPixel times over (W/32+1, H/32+1) groups of 32x32."""
+    from oracle.spirv_interp import Image
+    img = np.zeros((H, W, 4), np.float32); img[..., 3] = 1.0
+    im = Image(img.tolist())
+    res = {0: bytearray(ubo.tobytes()), 1: im, 2: bytearray(tris_w.tobytes()) or bytearray(64), 3: bytearray(sphs_w.tobytes()) or bytearray(32),
+           4: bytearray(mats.tobytes())}
+    if nodes is not None:
+        res[5] = bytearray(nodes.tobytes()); res[6] = bytearray(80)
+    else:
+        res[5] = bytearray(80)
+    m = module(shader)
+    per_dispatch = []
+    for _ in range(spp):
+        # threads outside the image return before touching memory (raytraceBVH.comp:346-347): skipped, not interpreted
+        m.dispatch((W // 32 + 1, H // 32 + 1, 1), res, only=lambda g: g[0] < W and g[1] < H)
+        per_dispatch.append(np.array(im.px, np.float32))
+    return np.stack(per_dispatch), m.n_executed
+
+
+def run_resolve(image, rays_per_pixel):
+    """SingleTriangleFullScreen.frag per pixel (uv = pixel centre, nearest texel), then the fixed-function UNORM8 conversion."""
+    from oracle.spirv_interp import Image, f32
+    H, W, _ = image.shape
+    m = module("SingleTriangleFullScreen.frag")
+    im = Image(image.tolist())
+    ubo = bytearray(np.array([rays_per_pixel, 0, 0, 0], np.uint32).tobytes())
+    out = np.zeros((H, W, 4), np.float32)
+    for y in range(H):
+        for x in range(W):
+            uv = [f32((x + 0.5) / W), f32((y + 0.5) / H)]
+            out[y, x] = m.run_stage({0: uv}, {0: ubo, 1: im})[0]
+    return out
+
+
+def run_logistic(cfg):
+    """logistic.comp, LogisticMap.cpp:384: `steps` dispatches of points/1024 groups; the rgba8 image is never cleared in between."""
+    from oracle.spirv_interp import Image
+    rng = np.random.default_rng(cfg["seed"])
+    n, W, H = cfg["points"], cfg["W"], cfg["H"]
+    pts = np.zeros((n, 2), np.float32)
+    pts[:, 0] = rng.uniform(0.0, 1.0, n); pts[:, 1] = rng.uniform(2.5, 4.0, n)
+    pts[0] = (0.5, 4.0); pts[1] = (0.0, 3.0); pts[2] = (1.0, 3.9)              # edge values: x' = 1 -> y = 0; x' = 0 -> y = H (outside)
+    color = np.array([0.25, 0.5, 1.0, 1.0], np.float32)
+    ubo = bytearray(np.array([*color, 0.0, W, H, 0.0], np.float32).tobytes())
+    buf = bytearray(pts.tobytes())
+    im = Image(np.zeros((H, W, 4), np.float32).tolist())
+    m = module("logistic.comp")
+    states = []
+    for _ in range(cfg["steps"]):
+        m.dispatch((n // 1024, 1, 1), {0: ubo, 1: buf, 2: im})
+        states.append(np.frombuffer(bytes(buf), np.float32).reshape(n, 2).copy())
+    return dict(points0=pts, color=color, points=np.stack(states), plotted=(np.array(im.px, np.float32).sum(-1) > 0))
+
+
+def generate(name):
+    c = CASES[name]
+    sc = make_scene(c["scene"])
+    ubo = SU.make_ubo(sc, max_depth=c["depth"], random_state=c["random_state"])
+    t0 = time.time()
+    out = dict(models=sc["models"], triangles=sc["triangles"], spheres=sc["spheres"], materials=sc["materials"], ubo=ubo,
+               W=np.int32(c["W"]), H=np.int32(c["H"]), spp=np.int32(c["spp"]))
+    b = run_build(sc, ubo)
+    out.update(b)
+    n_ins = 0
+    if "bvh" in c["programs"]:
+        out["images_bvh"], k = run_trace("raytraceBVH.comp", ubo, c["W"], c["H"], c["spp"], b["tris_w"], b["sphs_w"], sc["materials"], b["nodes"])
+        n_ins += k
+    if "linear" in c["programs"]:
+        out["images_linear"], k = run_trace("raytrace.comp", ubo, c["W"], c["H"], c["spp"], b["tris_w"], b["sphs_w"], sc["materials"], None)
+        n_ins += k
+    if "resolve" in c["programs"]:
+        out["resolved"] = run_resolve(out["images_bvh"][-1], c["spp"])
+    print(f"{name}: {len(sc['triangles'])} triangles, {len(sc['spheres'])} spheres, {c['W']}x{c['H']} x{c['spp']}: "
+          f"{n_ins} SPIR-V instructions traced, {time.time() - t0:.1f} s")
+    return out
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or (list(CASES) + ["logistic"])
+    for name in names:
+        if name == "logistic":
+            np.savez_compressed(os.path.join(HERE, "spirv_logistic.npz"), **run_logistic(LOGISTIC))
+            print("logistic done")
+        else:
+            np.savez_compressed(os.path.join(HERE, f"spirv_{name}.npz"), **generate(name))

@@ -1,0 +1,165 @@
+"""Parity against THE REFERENCE'S OWN BINARIES.
+
+tests/golden/spirv_*.npz hold the outputs of the reference's compiled shaders (shaders/compiled/*.spv), executed in the build
+container by oracle/spirv_interp.py (generator: tests/golden/make_spirv_golden.py; every buffer after every dispatch of S1, the
+image after every dispatch of S2, for both ray tracing programs, plus the logistic-map program and the fragment resolve).
+  * CPU tests: the C oracle must reproduce every one of those buffers bit for bit, stage by stage (each stage is fed the
+    golden output of the previous one, so a mismatch names the shader it belongs to) -- this is what pins the oracle;
+  * GPU tests: the CUDA path, through the C-ABI, must reproduce them as well.
+Nothing here reads /root/reference: the fixtures are committed.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = sorted(os.path.basename(p)[len("spirv_"):-len(".npz")] for p in glob.glob(os.path.join(HERE, "golden", "spirv_*.npz"))
+               if not p.endswith("spirv_logistic.npz"))
+
+
+def _load(name):
+    return np.load(os.path.join(HERE, "golden", f"spirv_{name}.npz"))
+
+
+def _same(a, b):
+    return np.ascontiguousarray(a).tobytes() == np.ascontiguousarray(b).tobytes()
+
+
+def test_fixture_set_is_complete():
+    assert CASES == ["dups", "room", "sorted", "spheres", "three", "two"]
+    assert os.path.exists(os.path.join(HERE, "golden", "spirv_logistic.npz"))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_build_stages_match_reference_binaries(name):
+    g = _load(name)
+    T, S = len(g["triangles"]), len(g["spheres"]); N = T + S
+    # K1 ModelSpaceToWorldSpace.comp.spv
+    tw, sw = O.model_to_world(g["models"], g["triangles"], g["spheres"])
+    assert _same(tw, g["tris_w"]) and _same(sw, g["sphs_w"]), "K1 model -> world"
+    # K2 GetEnclosingAABB.comp.spv (pin U4: uninitialised locals read as zero -- the binary's OpVariable has no initialiser)
+    assert _same(O.enclosing_aabb(g["tris_w"], g["sphs_w"]), g["enclosing"]), "K2 enclosing box"
+    # K3 GenerateMortonCodesOfPrimitives.comp.spv
+    assert _same(O.morton_codes(g["tris_w"], g["sphs_w"], g["enclosing"]), g["morton_unsorted"]), "K3 Morton codes"
+    # K4 RadixSortSimple.comp.spv (whole 12-byte records: the sort is stable)
+    assert _same(O.radix_sort(g["morton_unsorted"]), g["morton"]), "K4 radix sort"
+    # K5 ConstructHLBVH.comp.spv
+    nodes, cinfo = O.construct_hlbvh(g["tris_w"], g["sphs_w"], g["morton"])
+    assert _same(nodes, g["nodes_unfitted"]) and _same(cinfo, g["cinfo_unfitted"]), "K5 topology / leaves / parents"
+    # K6 ConstructAABBsOfInternalNodes.comp.spv
+    nodes2, cinfo2 = O.refit_aabbs(g["nodes_unfitted"], g["cinfo_unfitted"], N)
+    assert _same(nodes2, g["nodes"]) and _same(cinfo2, g["cinfo"]), "K6 refit"
+    # and the fused entry point
+    b = O.build_bvh(g["models"], g["triangles"], g["spheres"])
+    assert _same(b["nodes"], g["nodes"]) and _same(b["morton"], g["morton"]) and _same(b["enclosing"], g["enclosing"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_trace_matches_reference_binaries(name):
+    g = _load(name)
+    W, H, spp = int(g["W"]), int(g["H"]), int(g["spp"])
+    image = None
+    for s in range(spp):        # one dispatch of raytraceBVH.comp.spv at a time: the image (rgb sum + alpha seed) after each
+        r = O.raytrace(g["ubo"], W, H, g["tris_w"], g["sphs_w"], g["materials"], g["nodes"], 1, image=image, want_hits=False, want_rng=False)
+        image = r["image"]
+        assert np.array_equal(image.view(np.uint32), g["images_bvh"][s].view(np.uint32)), f"raytraceBVH.comp dispatch {s}"
+    r = O.raytrace(g["ubo"], W, H, g["tris_w"], g["sphs_w"], g["materials"], g["nodes"], spp, want_hits=False, want_rng=False)
+    assert np.array_equal(r["image"].view(np.uint32), g["images_bvh"][-1].view(np.uint32))
+    if "images_linear" in g.files:      # raytrace.comp.spv, the non-BVH program
+        r = O.raytrace(g["ubo"], W, H, g["tris_w"], g["sphs_w"], g["materials"], None, spp, opt=O.make_options(linear_scan=True),
+                       want_hits=False, want_rng=False)
+        assert np.array_equal(r["image"].view(np.uint32), g["images_linear"][-1].view(np.uint32)), "raytrace.comp"
+    if "resolved" in g.files:           # SingleTriangleFullScreen.frag.spv + UNORM8 conversion
+        want = np.floor(np.clip(g["resolved"], 0.0, 1.0).astype(np.float32) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+        assert np.array_equal(O.resolve_rgba8(g["images_bvh"][-1], spp), want), "fragment resolve"
+
+
+def test_golden_traces_are_not_trivial():
+    """the fixtures exercise what they claim: hits, misses, multi-bounce paths, both primitive types, every material type"""
+    g = _load("room")
+    img = g["images_bvh"][-1]
+    lit = (img[..., :3].sum(-1) > 0).sum()
+    assert lit > 50 and lit < img.shape[0] * img.shape[1]
+    assert len(np.unique(g["images_bvh"][0][..., 3])) > 0.9 * img.shape[0] * img.shape[1]      # alpha = per-pixel seed chain
+    types = set()
+    for n in ("room", "sorted", "spheres"):
+        types |= set(_load(n)["materials"]["materialType"].tolist())
+    assert types == {0, 1, 2, 3}            # light, diffuse, and the two absorbing types (D4) all occur
+    r = O.raytrace(g["ubo"], int(g["W"]), int(g["H"]), g["tris_w"], g["sphs_w"], g["materials"], g["nodes"], int(g["spp"]))
+    c = r["counters"]
+    assert c["rays"] > 1.3 * c["samples"] and c["triTests"] > 0 and c["sphTests"] > 0
+    d = _load("dups")
+    codes = d["morton"]["code"]
+    assert (np.diff(codes.astype(np.int64)) == 0).sum() >= 10, "dups must contain equal Morton codes"
+
+
+def test_oracle_logistic_matches_reference_binary():
+    g = np.load(os.path.join(HERE, "golden", "spirv_logistic.npz"))
+    pts = g["points0"].copy()
+    H, W = g["plotted"].shape
+    img = np.zeros((H, W, 4), np.uint8)
+    for s in range(len(g["points"])):
+        O.logistic_step(pts, img, tuple(float(x) for x in g["color"]))
+        assert _same(pts, g["points"][s]), f"logistic.comp dispatch {s}"
+    assert np.array_equal(img.sum(-1) > 0, g["plotted"])
+    want = np.floor(g["color"] * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+    assert (img[g["plotted"]] == want).all()
+
+
+# ------------------------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_matches_reference_binaries(device, name):
+    from raytracergpu_mastersproject_b200 import Raytracer, capi
+    g = _load(name)
+    W, H, spp = int(g["W"]), int(g["H"]), int(g["spp"])
+    T, S = len(g["triangles"]), len(g["spheres"]); N = T + S
+    rt = Raytracer(device, W, H)
+    rt.update_scene(g["models"], g["triangles"], g["spheres"], g["materials"])
+    rt.build_bvh(g["ubo"])
+    device.wait_idle()
+    assert _same(rt.triangles.read(O.TRIANGLE, T), g["tris_w"]) and _same(rt.spheres.read(O.SPHERE, S), g["sphs_w"])
+    assert _same(rt.enclosing.read(O.ENCLOSING, 1), g["enclosing"])
+    assert _same(rt.morton1.read(O.MORTON, N), g["morton"])
+    assert _same(rt.nodes.read(O.NODE, 2 * N - 1), g["nodes"])
+    # progressive: one sample per submission == one dispatch of raytraceBVH.comp each
+    rt.clear_image()
+    for s in range(spp):
+        rt.raytrace(g["ubo"], 1); device.wait_idle()
+        assert np.array_equal(rt.read_image().view(np.uint32), g["images_bvh"][s].view(np.uint32)), f"dispatch {s}"
+    # fused submission, every traversal variant
+    for fl in (0, capi.TRACE_WIDE_NODES, capi.TRACE_WIDE_NODES | capi.TRACE_REFERENCE_ORDER, capi.TRACE_EXACT_NODES,
+               capi.TRACE_COMPRESSED_NODES, capi.TRACE_SIMPLE_KERNEL, capi.TRACE_STREAM_KERNEL, capi.TRACE_NO_PRIMARY_SHARING):
+        rt.clear_image(); rt.raytrace(g["ubo"], spp, flags=fl); device.wait_idle()
+        assert np.array_equal(rt.read_image().view(np.uint32), g["images_bvh"][-1].view(np.uint32)), f"flags {fl}"
+    if "resolved" in g.files:
+        want = np.floor(np.clip(g["resolved"], 0.0, 1.0).astype(np.float32) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+        assert np.array_equal(rt.resolve_rgba8(spp), want)
+    if "images_linear" in g.files:
+        rt.update_scene(g["models"], g["triangles"], g["spheres"], g["materials"])
+        rt.prepare_linear(g["ubo"])
+        rt.clear_image(); rt.raytrace(g["ubo"], spp, flags=capi.TRACE_LINEAR_SCAN); device.wait_idle()
+        assert np.array_equal(rt.read_image().view(np.uint32), g["images_linear"][-1].view(np.uint32)), "raytrace.comp"
+
+
+@pytest.mark.gpu
+def test_cuda_logistic_matches_reference_binary(device):
+    import ctypes as C
+
+    from raytracergpu_mastersproject_b200 import Buffer, capi
+    g = np.load(os.path.join(HERE, "golden", "spirv_logistic.npz"))
+    H, W = g["plotted"].shape
+    n = len(g["points0"])
+    pts = Buffer(device, 8, n); pts.write(g["points0"])
+    img = Buffer(device, 4, W * H); img.zero()
+    col = np.ascontiguousarray(g["color"], np.float32)
+    for s in range(len(g["points"])):
+        capi.check(capi.lib().rtb_logistic_step(device.handle, pts._p, n, img._p, W, H, col.ctypes.data_as(C.c_void_p)))
+        device.wait_idle()
+        assert _same(pts.read(np.float32, 2 * n).reshape(n, 2), g["points"][s]), f"logistic.comp dispatch {s}"
+    out = img.read(np.uint8, W * H * 4).reshape(H, W, 4)
+    assert np.array_equal(out.sum(-1) > 0, g["plotted"])
