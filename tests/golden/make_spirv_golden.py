@@ -39,6 +39,14 @@ CASES = {
                     programs=("bvh", "linear")),
     # duplicated primitives: equal Morton codes -> the index tie-break of ConstructHLBVH.comp:64-67; build only
     "dups": dict(scene="dups", W=8, H=8, spp=1, depth=2, random_state=9, programs=("bvh",)),
+    # a deeper tree (440 primitives): stack pushes / pops, long leaf sequences
+    "mesh": dict(scene=dict(seed=7, n_tris=400, n_spheres=40), W=32, H=32, spp=1, depth=8, random_state=31337, programs=("bvh",)),
+    # degenerate geometry: zero-area triangles (NaN normals -> NaN hit distances), a zero-radius sphere, coordinates that
+    # overflow to inf in the cross products; axis-parallel rays through the odd-sized image centre
+    "degenerate": dict(scene="degenerate", W=33, H=33, spp=2, depth=6, random_state=5, programs=("bvh", "linear")),
+    # large zero-area triangles in front of the room: their boxes are hit, the normal is NaN, the NaN hit distance is ACCEPTED by
+    # the shader's comparisons (raytraceBVH.comp:130,137) and poisons closestSoFar for the rest of that ray
+    "slivers": dict(scene="slivers", W=32, H=32, spp=2, depth=6, random_state=6, programs=("bvh", "linear")),
     # smallest trees: N = 2 (one internal node) and N = 3
     "two": dict(scene=dict(seed=5, n_tris=1, n_spheres=1, room=False), W=8, H=8, spp=1, depth=2, random_state=1, programs=("bvh",)),
     "three": dict(scene=dict(seed=6, n_tris=2, n_spheres=1, room=False), W=8, H=8, spp=1, depth=2, random_state=2, programs=("bvh",)),
@@ -52,6 +60,28 @@ def make_scene(spec):
         sc = dict(base)
         sc["triangles"] = np.concatenate([base["triangles"], base["triangles"][6:], base["triangles"][6:12]])
         sc["spheres"] = np.concatenate([base["spheres"], base["spheres"], base["spheres"][:2]])
+        return sc
+    if spec == "degenerate":
+        sc = SU.random_scene(8, n_tris=24, n_spheres=5)
+        t = sc["triangles"]
+        t["v1"][8] = t["v0"][8]                                   # zero-area: two equal vertices
+        t["v1"][9] = t["v0"][9]; t["v2"][9] = t["v0"][9]          # a point
+        t["v2"][10] = t["v0"][10] + 2.0 * (t["v1"][10] - t["v0"][10])   # collinear vertices
+        t["v0"][11][:3] = (1e20, -1e20, 1e20)                     # products overflow to inf
+        t["v0"][12][:3] = (0.0, 0.0, 0.0); t["v1"][12][:3] = (1e-30, 0.0, 0.0); t["v2"][12][:3] = (0.0, 1e-30, 0.0)   # denormal area
+        sc["spheres"]["radius"][1] = 0.0
+        sc["spheres"]["radius"][2] = -3.0
+        return sc
+    if spec == "slivers":
+        sc = SU.random_scene(9, n_tris=16, n_spheres=3)
+        t = sc["triangles"]
+        for i, (a, b) in enumerate([((100, 100, 300), (400, 400, 320)), ((150, 400, 200), (420, 120, 260))]):
+            k = 6 + i                                              # first random triangles (model index kept -> identity below)
+            t["modelIndex"][k] = 0
+            t["v0"][k][:3] = a; t["v1"][k][:3] = b
+            t["v2"][k][:3] = 0.5 * (np.float32(a) + np.float32(b))    # collinear: cross(u, v) = 0 -> normalize -> NaN
+        t["modelIndex"][8] = 0
+        t["v0"][8][:3] = t["v1"][8][:3] = t["v2"][8][:3] = (275, 275, 100)   # a point
         return sc
     return SU.random_scene(**spec)
 

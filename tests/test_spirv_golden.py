@@ -30,7 +30,7 @@ def _same(a, b):
 
 
 def test_fixture_set_is_complete():
-    assert CASES == ["dups", "room", "sorted", "spheres", "three", "two"]
+    assert CASES == ["degenerate", "dups", "mesh", "room", "slivers", "sorted", "spheres", "three", "two"]
     assert os.path.exists(os.path.join(HERE, "golden", "spirv_logistic.npz"))
 
 
@@ -122,7 +122,8 @@ def test_cuda_matches_reference_binaries(device, name):
     rt.update_scene(g["models"], g["triangles"], g["spheres"], g["materials"])
     rt.build_bvh(g["ubo"])
     device.wait_idle()
-    assert _same(rt.triangles.read(O.TRIANGLE, T), g["tris_w"]) and _same(rt.spheres.read(O.SPHERE, S), g["sphs_w"])
+    assert T == 0 or _same(rt.triangles.read(O.TRIANGLE, T), g["tris_w"])
+    assert S == 0 or _same(rt.spheres.read(O.SPHERE, S), g["sphs_w"])
     assert _same(rt.enclosing.read(O.ENCLOSING, 1), g["enclosing"])
     assert _same(rt.morton1.read(O.MORTON, N), g["morton"])
     assert _same(rt.nodes.read(O.NODE, 2 * N - 1), g["nodes"])
