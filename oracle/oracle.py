@@ -1,6 +1,7 @@
 """ctypes front-end of the CPU ORACLE (oracle/rt_oracle.c).
 
-TEST INFRASTRUCTURE ONLY -- "parity unpinned" (the reference has no golden vectors; see rt_oracle.h).
+TEST INFRASTRUCTURE ONLY.  Pinned against the reference's own compiled shaders (tests/golden/spirv_*.npz, produced by
+oracle/spirv_interp.py from shaders/compiled/*.spv; see rt_oracle.h for what that does and does not cover).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
 Nothing under raytracergpu_mastersproject_b200/ does.
 """

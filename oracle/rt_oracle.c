@@ -1,7 +1,8 @@
 /*
  * rt_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).  See rt_oracle.h for the contract.
  *
- * PARITY UNPINNED by the reference (it has no tests / golden vectors); pinned by hand-derived KATs only.
+ * Pinned bit for bit against the reference's own compiled shaders (shaders/compiled/*.spv run by oracle/spirv_interp.py ->
+ * tests/golden/spirv_*.npz, tests/test_spirv_golden.py); driver-defined built-in arithmetic pinned by convention (U1..U14).
  *
  * Every function restates one reference shader and cites it.  The code follows the shader text literally
  * (same stack traversal, same 40-byte node records, one "dispatch" per sample) -- it is deliberately NOT

@@ -4,12 +4,15 @@
  * A plain-C restatement of the compute shaders of silvercorked/RaytracerGPU_MastersProject
  * (paths below are relative to RaytracerGPU_MastersProject/ in the reference tree).
  *
- * PARITY UNPINNED: the reference ships no tests, no golden vectors and no fixtures for this path, and its
- * shaders (GLSL for a Vulkan driver) cannot be executed in this image (no Vulkan loader/ICD, no glslc).
- * The oracle is therefore pinned only against (a) the known-answer vectors derived by hand from the shader
- * sources (tests/test_oracle_kat.py) and (b) structural properties (tests/).  Where the
- * shaders rely on undefined / driver-defined behaviour the oracle follows the pins of SURVEY.md Appendix B
- * (U1..U14); each pin is repeated at the place it is applied.
+ * HOW IT IS PINNED: the reference ships no tests, golden vectors or fixtures for this path and cannot run on a device
+ * in this image (no Vulkan loader/ICD, no glslc) -- but it ships every shader COMPILED (shaders/compiled/*.spv).
+ * oracle/spirv_interp.py executes those binaries on the CPU; tests/golden/make_spirv_golden.py committed their outputs
+ * (every buffer after every dispatch, nine scenes) as tests/golden/spirv_*.npz, and tests/test_spirv_golden.py checks
+ * that every function below reproduces them BIT FOR BIT, stage by stage.  What the binaries do not define -- the
+ * arithmetic of the driver's built-ins (normalize, dot association, sin / cos / tan, min / max of NaN, out-of-range
+ * float->uint) -- follows the pins of SURVEY.md Appendix B (U1..U14), shared with the interpreter and repeated at the
+ * place each is applied: that part is pinned by convention, not by the reference.  Additional checks: hand-derived
+ * known-answer vectors (tests/test_oracle_kat.py) and structural properties (tests/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
  * library.  The product (raytracergpu_mastersproject_b200/) never includes, links or calls it.

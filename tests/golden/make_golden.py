@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz from the CPU oracle (oracle/rt_oracle.c).
 
-The reference ships no golden vectors and cannot run here, so these fixtures pin the ORACLE's own
-outputs: they guard the oracle (and through it the CUDA path) against drift, they do not add reference authority.
+These fixtures pin the ORACLE's own outputs on larger scenes: they guard the oracle (and through it the CUDA path) against
+drift, they do not add reference authority -- that comes from make_spirv_golden.py (outputs of the reference's compiled shaders).
 Inputs are the seeded scenes of tests/scene_util.py plus the host's complexScene; regenerate with
     python tests/golden/make_golden.py
 """

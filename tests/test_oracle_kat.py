@@ -1,6 +1,6 @@
 """CPU: the oracle against the known-answer vectors derived by hand from the shader sources
-and against structural properties.  The reference ships no golden vectors of its own ("parity unpinned"), so these
-are the pins of the oracle."""
+and against structural properties.  The reference ships no golden vectors of its own; the stronger pin -- outputs of the
+reference's compiled shaders -- lives in tests/test_spirv_golden.py, these vectors complement it."""
 import math
 import struct
 
