@@ -179,6 +179,43 @@ def run_logistic(cfg):
     return dict(points0=pts, color=color, points=np.stack(states), plotted=(np.array(im.px, np.float32).sum(-1) > 0))
 
 
+def generate_c1(n_pixels=1500, spp=2, random_state=12345):
+    """BASELINE config C1 on its real scene: the host's complexScene (Scenes.cpp:337-398 with the stand-in models) at the
+    reference's 800x800 window, S1 by the reference binaries on all 1 000+ primitives, S2 by raytraceBVH.comp.spv on a seeded
+    sample of pixels (every pixel is independent) -- including the shader's debug pixel (175, 650), whose scratch[] writes
+    (raytraceBVH.comp:40-45,256-263,288-313) are kept as well."""
+    from oracle.spirv_interp import Image
+    from raytracergpu_mastersproject_b200 import scenes
+    sc = scenes.load_scene("complexScene")
+    W = H = 800
+    ubo = SU.make_ubo(sc, max_depth=sc["max_depth"], random_state=random_state, vfov=sc["vfov"])
+    t0 = time.time()
+    b = run_build(sc, ubo)
+    rng = np.random.default_rng(2024)
+    px = {(175, 650), (0, 0), (799, 799), (400, 400)}
+    while len(px) < n_pixels:
+        px.add((int(rng.integers(0, W)), int(rng.integers(0, H))))
+    px = sorted(px)
+    img = np.zeros((H, W, 4), np.float32); img[..., 3] = 1.0
+    im = Image(img.tolist())
+    scratch = bytearray(80)
+    res = {0: bytearray(ubo.tobytes()), 1: im, 2: bytearray(b["tris_w"].tobytes()), 3: bytearray(b["sphs_w"].tobytes()),
+           4: bytearray(sc["materials"].tobytes()), 5: bytearray(b["nodes"].tobytes()), 6: scratch}
+    m = module("raytraceBVH.comp")
+    want = set(px)
+    vals = []
+    for _ in range(spp):
+        m.dispatch((W // 32 + 1, H // 32 + 1, 1), res, only=lambda g: (g[0], g[1]) in want)
+        vals.append(np.array([im.px[y][x] for (x, y) in px], np.float32))
+    print(f"c1pixels: {len(sc['triangles'])} triangles, {len(sc['spheres'])} spheres, {len(px)} pixels x{spp}: {m.n_executed} SPIR-V "
+          f"instructions traced, {time.time() - t0:.1f} s")
+    out = dict(models=sc["models"], triangles=sc["triangles"], spheres=sc["spheres"], materials=sc["materials"], ubo=ubo,
+               W=np.int32(W), H=np.int32(H), spp=np.int32(spp), pixels=np.array(px, np.int32), values=np.stack(vals),
+               scratch=np.frombuffer(bytes(scratch), np.float32).copy())
+    out.update(b)
+    return out
+
+
 def generate(name):
     c = CASES[name]
     sc = make_scene(c["scene"])
@@ -203,9 +240,11 @@ def generate(name):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["logistic"])
+    names = sys.argv[1:] or (list(CASES) + ["logistic", "c1pixels"])
     for name in names:
-        if name == "logistic":
+        if name == "c1pixels":
+            np.savez_compressed(os.path.join(HERE, "spirv_c1pixels.npz"), **generate_c1())
+        elif name == "logistic":
             np.savez_compressed(os.path.join(HERE, "spirv_logistic.npz"), **run_logistic(LOGISTIC))
             print("logistic done")
         else:

@@ -18,7 +18,7 @@ from oracle import oracle as O
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = sorted(os.path.basename(p)[len("spirv_"):-len(".npz")] for p in glob.glob(os.path.join(HERE, "golden", "spirv_*.npz"))
-               if not p.endswith("spirv_logistic.npz"))
+               if not p.endswith(("spirv_logistic.npz", "spirv_c1pixels.npz")))
 
 
 def _load(name):
@@ -97,6 +97,25 @@ def test_golden_traces_are_not_trivial():
     assert (np.diff(codes.astype(np.int64)) == 0).sum() >= 10, "dups must contain equal Morton codes"
 
 
+def test_oracle_c1_matches_reference_binaries():
+    """BASELINE config C1 (the default complexScene, 800x800): S1 of the reference binaries on the whole scene, S2 on 1 500 sampled
+    pixels (incl. the shader's debug pixel), two dispatches."""
+    g = _load("c1pixels")
+    W, H, spp = int(g["W"]), int(g["H"]), int(g["spp"])
+    b = O.build_bvh(g["models"], g["triangles"], g["spheres"])
+    for k in ("tris_w", "sphs_w", "enclosing", "morton", "nodes", "cinfo"):
+        assert _same(b[{"tris_w": "tris", "sphs_w": "sphs"}.get(k, k)], g[k]), k
+    xs, ys = g["pixels"][:, 0], g["pixels"][:, 1]
+    image = None
+    for s in range(spp):
+        image = O.raytrace(g["ubo"], W, H, b["tris"], b["sphs"], g["materials"], b["nodes"], 1, image=image, want_hits=False, want_rng=False)["image"]
+        assert np.array_equal(image[ys, xs].view(np.uint32), g["values"][s].view(np.uint32)), f"dispatch {s}"
+    # the scene arrays in the fixture are what the C++ host builds today (Scenes.cpp complexScene + flatten)
+    from raytracergpu_mastersproject_b200 import scenes
+    sc = scenes.load_scene("complexScene")
+    assert _same(sc["triangles"], g["triangles"]) and _same(sc["models"], g["models"]) and _same(sc["materials"], g["materials"])
+
+
 def test_oracle_logistic_matches_reference_binary():
     g = np.load(os.path.join(HERE, "golden", "spirv_logistic.npz"))
     pts = g["points0"].copy()
@@ -145,6 +164,28 @@ def test_cuda_matches_reference_binaries(device, name):
         rt.prepare_linear(g["ubo"])
         rt.clear_image(); rt.raytrace(g["ubo"], spp, flags=capi.TRACE_LINEAR_SCAN); device.wait_idle()
         assert np.array_equal(rt.read_image().view(np.uint32), g["images_linear"][-1].view(np.uint32)), "raytrace.comp"
+
+
+@pytest.mark.gpu
+def test_cuda_c1_matches_reference_binaries(device):
+    from raytracergpu_mastersproject_b200 import Raytracer, capi
+    g = _load("c1pixels")
+    W, H, spp = int(g["W"]), int(g["H"]), int(g["spp"])
+    N = len(g["triangles"]) + len(g["spheres"])
+    rt = Raytracer(device, W, H)
+    rt.update_scene(g["models"], g["triangles"], g["spheres"], g["materials"])
+    rt.build_bvh(g["ubo"])
+    device.wait_idle()
+    assert _same(rt.nodes.read(O.NODE, 2 * N - 1), g["nodes"]) and _same(rt.morton1.read(O.MORTON, N), g["morton"])
+    assert _same(rt.enclosing.read(O.ENCLOSING, 1), g["enclosing"]) and _same(rt.cinfo.read(O.CINFO, 2 * N - 1), g["cinfo"])
+    xs, ys = g["pixels"][:, 0], g["pixels"][:, 1]
+    rt.clear_image()
+    for s in range(spp):
+        rt.raytrace(g["ubo"], 1); device.wait_idle()
+        assert np.array_equal(rt.read_image()[ys, xs].view(np.uint32), g["values"][s].view(np.uint32)), f"dispatch {s}"
+    for fl in (0, capi.TRACE_WIDE_NODES, capi.TRACE_EXACT_NODES, capi.TRACE_SIMPLE_KERNEL):
+        rt.clear_image(); rt.raytrace(g["ubo"], spp, flags=fl); device.wait_idle()
+        assert np.array_equal(rt.read_image()[ys, xs].view(np.uint32), g["values"][-1].view(np.uint32)), f"flags {fl}"
 
 
 @pytest.mark.gpu
