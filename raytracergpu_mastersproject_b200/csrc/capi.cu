@@ -43,11 +43,11 @@ struct rtb_ctx {
     // build scratch (grow-only)
     Scratch sortKeys[2], sortVals[2], sortCounts, encRed, enclosing, cinfo, nodes;
     // the bound raytrace set: traversal records derived from the reference-layout arrays
-    Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag;
+    Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag, parkBuf;
     Scratch etaNode, etaParent, etaArrivals;   // per-node hit-point slack (launch_eta) and its scratch
     bool unorderedOk = false;         // eta small enough for the nearest-first, t-culled traversal
     Scratch cnodes, leafBox, wide;    // compressed 32-byte / wide 64-byte traversal records + exact leaf boxes
-    Scratch activePix, sampleBuf, primaryHits;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
+    Scratch activePix, activeXY, sampleBuf, primaryHits;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
     Scratch poolSlot, poolColor, poolAtt, poolOrg, poolDir, poolNrm, poolList, poolCnt;   // streaming kernel: path pool
     bool bound = false, boundNodes = false, cnodesReady = false, wideReady = false, leafBoxReady = false;
     const void* boundNodesPtr = nullptr;
@@ -116,7 +116,7 @@ int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tr
     if (ensure(c, c->psphMat, sizeof(uint32_t) * (size_t)S)) return 1;
     if (ensure(c, c->pmats, sizeof(float4) * (size_t)M)) return 1;
     if (ensure(c, c->rootBox, sizeof(float4) * 2)) return 1;
-    if (ensure(c, c->workCounter, 16)) return 1;
+    if (ensure(c, c->workCounter, 32)) return 1;
     if (ensure(c, c->errFlag, 16)) return 1;
     if (nodes && !pairsDone) launch_pack_pairs(c->stream, nodes, N, c->pairs.p, c->rootBox.p);
     launch_pack_prims(c->stream, tris, T, sphs, S, mats, M, c->ptris.p, c->psphs.p, c->psphMat.p, c->pmats.p);
@@ -175,8 +175,8 @@ int rtb_ctx_destroy(rtb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (Scratch* s : { &c->sortKeys[0], &c->sortKeys[1], &c->sortVals[0], &c->sortVals[1], &c->sortCounts, &c->encRed, &c->enclosing,
                         &c->cinfo, &c->nodes, &c->pairs, &c->ptris, &c->psphs, &c->psphMat, &c->pmats, &c->rootBox, &c->workCounter,
-                        &c->errFlag, &c->etaNode, &c->etaParent, &c->etaArrivals, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->sampleBuf, &c->primaryHits, &c->poolSlot, &c->poolColor,
-                        &c->poolAtt, &c->poolOrg, &c->poolDir, &c->poolNrm, &c->poolList, &c->poolCnt })
+                        &c->errFlag, &c->etaNode, &c->etaParent, &c->etaArrivals, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->activeXY, &c->sampleBuf, &c->primaryHits, &c->poolSlot, &c->poolColor,
+                        &c->poolAtt, &c->poolOrg, &c->poolDir, &c->poolNrm, &c->poolList, &c->poolCnt, &c->parkBuf })
         release(*s);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -407,6 +407,8 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     { const char* e = getenv("RTB_WAVE_TMIN"); p.tMin = e ? (uint32_t)atoi(e) : 0u; }
     { const char* e = getenv("RTB_WAVE_SORTED_PUSH"); p.sortedPush = e ? (uint32_t)atoi(e) : (c->bS > c->bT ? 1u : 0u); }   // measured: +16 % C3, -2..7 % C2/C4/C5
     { const char* e = getenv("RTB_WAVE_QGATE"); p.qGate = e ? (uint32_t)atoi(e) : 4u; }   // tuning knob, results unaffected
+    { const char* e = getenv("RTB_WAVE_COOP"); p.coopMax = e ? (uint32_t)atoi(e) : 8u; }  // tail hand-over threshold (live lanes per warp); results unaffected
+    { const char* e = getenv("RTB_WAVE_COOP_TURNS"); p.coopTurns = e ? (uint32_t)atoi(e) : 32u; }  // long-ray hand-over threshold (turns); results unaffected
     const bool count = (a->flags & RTB_TRACE_COUNT) != 0, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;
     int launches = 1;
     const bool linear = (a->flags & RTB_TRACE_LINEAR_SCAN) != 0;
@@ -420,11 +422,12 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
         size_t perPass = budget / (pixels * sizeof(float4));
         if (perPass < 1) perPass = 1;
         if (perPass > a->sampleCount) perPass = a->sampleCount;
-        if (ensure(c, c->activePix, pixels * sizeof(uint32_t))) return 1;
+        if (ensure(c, c->activePix, pixels * sizeof(uint32_t)) || ensure(c, c->activeXY, pixels * sizeof(uint32_t))) return 1;
         if (ensure(c, c->sampleBuf, pixels * perPass * sizeof(float4))) return 1;
         p.workCounter64 = (unsigned long long*)c->workCounter.p;
         p.activeCount = (unsigned int*)c->workCounter.p + 2;
         p.activePix = (uint32_t*)c->activePix.p;
+        p.activeXY = (uint32_t*)c->activeXY.p;
         p.sampleBuf = (float4*)c->sampleBuf.p;
         p.slotCapacity = (uint32_t)pixels;
         const bool cull = (a->flags & RTB_TRACE_CULLED) != 0;
@@ -476,9 +479,15 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
             if (nodesMode == 2 && c->unorderedOk && !cull && !(a->flags & RTB_TRACE_REFERENCE_ORDER)) nodesMode = 3;
             p.primaryHits = nullptr; p.primaryMode = 0;
             if (!count && a->sampleCount > 1 && !(a->flags & RTB_TRACE_NO_PRIMARY_SHARING)) {
-                if (ensure(c, c->primaryHits, pixels * 2 * sizeof(float4))) return 1;
+                if (ensure(c, c->primaryHits, pixels * 3 * sizeof(float4))) return 1;
                 p.primaryHits = (float4*)c->primaryHits.p;
             }
+            if (nodesMode == 3 && (p.coopMax || p.coopTurns)) {      // parking is optional for a lane: a full buffer just means "walk it yourself"
+                const size_t cap = (size_t)c->smCount * 8 * 128;
+                if (ensure(c, c->parkBuf, cap * 15 * sizeof(float4))) return 1;
+                p.parkBuf = (float4*)c->parkBuf.p; p.parkCapacity = (uint32_t)cap;
+                p.parkCount = (unsigned int*)c->workCounter.p + 4; p.parkCursor = (unsigned int*)c->workCounter.p + 5;
+            } else { p.coopMax = 0; p.coopTurns = 0; }
             launches = extra + launch_trace_wave(c->stream, p, count, ext, cull, nodesMode, c->smCount, (uint32_t)perPass);
         }
     }

@@ -139,17 +139,28 @@ struct TraceParams {
     uint32_t sortedPush;               // nearest-first kernel: pick the variant that stacks waiting entries farthest-first
     uint32_t qGate;                    // nearest-first kernel: a lane keeps stepping while its FIFO holds <= qGate candidates
     uint32_t tMin;                     // wave kernel: minimum stepping lanes to stay in the traverse phase (0 = default)
+    // tail hand-over (trace_wave.cu): once the work queue is drained, a warp with <= coopMax live lanes parks the paths whose next
+    // ray is about to start; trace_tail_kernel finishes them one ray per WARP (0 = off)
+    uint32_t coopMax;
+    // long-ray hand-over: a ray still being walked after coopTurns turns of its lane (a ray tangent to a finely tessellated
+    // surface crosses thousands of leaf boxes) is parked with its pending stack and finished by the tail kernel (0 = off)
+    uint32_t coopTurns;
+    float4* parkBuf;                   // [parkCapacity][PARK_STRIDE]: see trace_wave.cu
+    unsigned int* parkCount;           // paths parked by the main launch
+    unsigned int* parkCursor;          // fetch cursor of the tail launch
+    uint32_t parkCapacity;
     // wave kernel, per pass: (pixel, sample) work items
     unsigned long long* workCounter64; // [0] work-item counter, [1] (as unsigned*) active-pixel count
     unsigned int* activeCount;         // = (unsigned*)(workCounter64 + 1)
     uint32_t* activePix;               // [pixels] local pixel index of every pixel whose primary ray enters the root box
+    uint32_t* activeXY;                // [pixels] x | (global row << 16) of the same pixels (saves the item fetch four integer divisions)
     float4* sampleBuf;                 // [samplesPerPass][slotCapacity]: (colour.xyz, incoming alpha) per (sample, active pixel)
     uint32_t slotCapacity;
     uint32_t firstPass, lastPass;
     // primary-hit sharing (trace_wave.cu): 0 off | 1 this launch traces ONE primary ray per active pixel and stores its hit |
     // 2 every (pixel, sample) item starts from the stored hit
     uint32_t primaryMode;
-    float4* primaryHits;               // [pixels][2]: (t, normal.xyz), (prim, mat, hit, backFace)
+    float4* primaryHits;               // [pixels][3]: (t, normal.xyz), (prim, mat, hit, backFace), (primary direction.xyz, -)
     StreamPool pool;
     f3 background;                     // _BACKGROUND_COLOR (0 for the BVH program, (0.1,0.1,0.3) for the non-BVH program)
 };

@@ -31,12 +31,23 @@
 // with a zero / denormal direction component, where the reference produces inf / NaN) the exact division path of
 // trace_common.cuh runs.
 // Results are bit-identical either way (tests/test_gpu_parity.py compares images, hit ids, RNG states and visit counters).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "trace_wave_shared.cuh"
 
 namespace rtb {
 
 constexpr int WAVE_THREADS = 128;
+// parked path / ray record, float4 units: 0 (o, rng) 1 (d, depth) 2 (colour, pixel) 3 (attenuation, sample)
+// 4 (slot lo, slot hi, cur, flags: bit 0 ray in flight | bit 1 hit | sp << 8) 5 (rec.t, rec.normal) 6 (mat, prim, back, closest) 7..14 stack[32]
+constexpr unsigned PARK_STRIDE = 15;
+#ifdef RTB_TAIL_PROBE   // debug build only (make EXTRA=-DRTB_TAIL_PROBE): per-warp timeline of the main launch, dumped to $RTB_TAIL_PROBE_FILE
+__device__ uint4 g_probeLane[8192 * 32];             // per lane: its longest ray (T steps, pixel, sample | depth << 16 | exact << 31, L tests)
+__device__ unsigned long long g_probe[3][8192];     // [0] first item pulled, [1] first lane retired (queue drained), [2] warp exit
+__device__ __forceinline__ unsigned long long probe_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
 #ifndef RTB_WIDE_MINB
 #define RTB_WIDE_MINB 7
 #endif
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
 
     // ---- per-lane state -------------------------------------------------------------------------------------------
     bool dead = false, rayActive = false, travDone = true, exactOnly = false, hit = false, cullOk = false;
-    uint32_t depth = 0, rng = 0, pix = 0, smp = 0;
+    uint32_t depth = 0, rng = 0, pix = 0, smp = 0, turns = 0;
     size_t slotIndex = 0;
     f3 color = F3(0, 0, 0), att = F3(1, 1, 1);
     f3 o = F3(0, 0, 0), d = F3(0, 0, 1), rinv = F3(0, 0, 0);
@@ -92,23 +103,65 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
     unsigned err = 0;
     Tally tl = { 0, 0, 0, 0, 0 };
 
+#ifdef RTB_TAIL_PROBE
+    const unsigned pw = (blockIdx.x * WAVE_THREADS + tid) >> 5;
+    bool probeDrained = false;
+    uint32_t prSteps = 0, prLeaf = 0; uint4 prMax = make_uint4(0, 0, 0, 0);
+    if (lane == 0 && pw < 8192) { g_probe[0][pw] = probe_now(); g_probe[1][pw] = 0; }
+#endif
     auto enqueue = [&](uint32_t g) {
         sm.queue[(qHead + qCount) & (QCAP - 1)][tid] = g;
         qCount++;
     };
 
     while (true) {
+        // Tail hand-over (NODES >= 3): lanes only die once the work queue is drained.  From then on a warp with few live lanes
+        // stops starting rays: a path whose next ray is about to start is parked for trace_tail_kernel (one ray per WARP) and
+        // the lane retires; rays already in flight are finished here.
+        bool tailMode = false;
+        if (NODES >= 3 && p.coopMax != 0u && p.primaryMode != 1u) {
+            const unsigned deadBal = __ballot_sync(FULL, dead);
+            tailMode = deadBal != 0u && 32u - (unsigned)__popc(deadBal) <= p.coopMax;
+        }
+        // Long-ray hand-over: every FIFO is empty here (the L phase drains them), so a ray's whole pending set is cur + its stack.
+        if (NODES >= 3 && p.coopTurns != 0u && rayActive && !travDone) {
+            turns++;
+            if (turns > p.coopTurns && !exactOnly && sp <= SSTACK) {
+                const uint32_t k = atomicAdd(p.parkCount, 1u);
+                if (k < p.parkCapacity) {
+                    float4* e = p.parkBuf + (size_t)PARK_STRIDE * k;
+                    e[0] = make_float4(o.x, o.y, o.z, __uint_as_float(rng));
+                    e[1] = make_float4(d.x, d.y, d.z, __uint_as_float(depth));
+                    e[2] = make_float4(color.x, color.y, color.z, __uint_as_float(pix));
+                    e[3] = make_float4(att.x, att.y, att.z, __uint_as_float(smp));
+                    e[4] = make_float4(__uint_as_float((uint32_t)slotIndex), __uint_as_float((uint32_t)((unsigned long long)slotIndex >> 32)),
+                                       __uint_as_float(cur), __uint_as_float(1u | (hit ? 2u : 0u) | ((uint32_t)sp << 8)));
+                    e[5] = make_float4(rec.t, rec.normal.x, rec.normal.y, rec.normal.z);
+                    e[6] = make_float4(__uint_as_float(rec.mat), __uint_as_float(rec.prim), __uint_as_float((uint32_t)rec.back), closest);
+#pragma unroll
+                    for (int j = 0; j < SSTACK / 4; j++)
+                        e[7 + j] = make_float4(__uint_as_float(sm.stack[4 * j][tid]), __uint_as_float(sm.stack[4 * j + 1][tid]),
+                                               __uint_as_float(sm.stack[4 * j + 2][tid]), __uint_as_float(sm.stack[4 * j + 3][tid]));
+                    rayActive = false; travDone = true; sp = 0; cur = 0xFFFFFFFFu;      // the lane is free for the next item
+                }
+            }
+        }
         // =========================================== S: shade / generate =========================================
         while (!dead && (!rayActive || (travDone && qCount == 0))) {
             bool needItem = !rayActive;
             if (rayActive && p.primaryMode == 1u) {                       // primary-hit launch: keep the hit record, no shading
                 rayActive = false; needItem = true;
-                float4* h = p.primaryHits + 2ull * pix;
+                float4* h = p.primaryHits + 3ull * pix;
                 h[0] = make_float4(rec.t, rec.normal.x, rec.normal.y, rec.normal.z);
                 h[1] = make_float4(__uint_as_float(rec.prim), __uint_as_float(rec.mat), __uint_as_float(hit ? 1u : 0u),
                                    __uint_as_float((uint32_t)rec.back));
+                h[2] = make_float4(d.x, d.y, d.z, 0.f);
             } else if (rayActive) {                                       // the ray is finished: rayColor loop body :283-307
                 rayActive = false;
+#ifdef RTB_TAIL_PROBE
+                if (prSteps > prMax.x) prMax = make_uint4(prSteps, pix, smp | (depth << 16) | (exactOnly ? 0x80000000u : 0u), prLeaf);
+                prSteps = 0; prLeaf = 0;
+#endif
                 if (depth == 0 && smp == 0 && p.firstPass && p.hitPrim) {
                     p.hitPrim[pix] = hit ? rec.prim : 0xFFFFFFFFu;
                     if (p.hitT) p.hitT[pix] = hit ? rec.t : 0.0f;
@@ -151,30 +204,48 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
                 if ((int)lane == leader) i = atomicAdd(p.workCounter64, (unsigned long long)__popc(act));
                 i = __shfl_sync(act, i, leader) + (unsigned long long)__popc(act & ((1u << lane) - 1u));
                 if (i >= totalWork) { dead = true; break; }
-                const uint32_t g = (uint32_t)(i / groupItems), r = (uint32_t)(i % groupItems);
+                uint32_t g, r;
+                if (totalWork <= 0xFFFFFFFFull) { g = (uint32_t)i / groupItems; r = (uint32_t)i - g * groupItems; }   // warp-uniform branch
+                else { g = (uint32_t)(i / groupItems); r = (uint32_t)(i % groupItems); }
                 const uint32_t slot = g * 32u + (r & 31u);
                 if (slot >= activeCount) continue;                        // padding of the last group
                 smp = r >> 5;
                 pix = p.activePix[slot];
                 slotIndex = (size_t)smp * p.slotCapacity + slot;
-                const uint32_t x = pix % p.W, y = global_row(p, pix / p.W);
+                const uint32_t xy = p.activeXY[slot];
+                const uint32_t x = xy & 0xFFFFu, y = xy >> 16;
                 const float alphaIn = p.sampleBuf[slotIndex].w;
                 rng = (600u * x + y) * (p.randomState + 1u) + alpha_to_u32(alphaIn);       // random.glsl:10 + :350 (:351 is a no-op)
                 (void)pcg_float(rng);                                                      // nextRandom :352 (kept by the pre-pass)
                 color = F3(0.f, 0.f, 0.f); att = F3(1.f, 1.f, 1.f);
                 depth = 0;
-                o = p.cam.origin; d = primary_direction(p, x, y);
+                o = p.cam.origin;
                 if (p.primaryMode == 2u) {                                // the primary ray's hitBVH result, traced once per pixel
-                    const float4 h0 = __ldg(p.primaryHits + 2ull * pix), h1 = __ldg(p.primaryHits + 2ull * pix + 1);
+                    const float4 h0 = __ldg(p.primaryHits + 3ull * pix), h1 = __ldg(p.primaryHits + 3ull * pix + 1), h2 = __ldg(p.primaryHits + 3ull * pix + 2);
+                    d = xyz(h2);                                          // primary_direction(p, x, y), as the primary launch evaluated it
                     rec.t = h0.x; rec.normal = F3(h0.y, h0.z, h0.w);
                     rec.prim = __float_as_uint(h1.x); rec.mat = __float_as_uint(h1.y);
                     hit = __float_as_uint(h1.z) != 0u; rec.back = (int)__float_as_uint(h1.w);
                     rayActive = true; travDone = true; qCount = 0; qHead = 0; sp = 0; cur = 0xFFFFFFFFu;
                     continue;                                             // straight to shading
                 }
+                d = primary_direction(p, x, y);
+            }
+            if (NODES >= 3 && tailMode) {                                 // park the path (state at a ray boundary) and retire
+                const uint32_t k = atomicAdd(p.parkCount, 1u);
+                if (k < p.parkCapacity) {
+                    float4* e = p.parkBuf + (size_t)PARK_STRIDE * k;
+                    e[0] = make_float4(o.x, o.y, o.z, __uint_as_float(rng));
+                    e[1] = make_float4(d.x, d.y, d.z, __uint_as_float(depth));
+                    e[2] = make_float4(color.x, color.y, color.z, __uint_as_float(pix));
+                    e[3] = make_float4(att.x, att.y, att.z, __uint_as_float(smp));
+                    e[4] = make_float4(__uint_as_float((uint32_t)slotIndex), __uint_as_float((uint32_t)((unsigned long long)slotIndex >> 32)), 0.f, 0.f);
+                    rayActive = false;
+                    continue;                                             // pulls from the drained queue -> dead
+                }
             }
             // ---- start the ray (hitBVH prologue :196-201 + the root's own box test) ----
-            rayActive = true; hit = false; closest = T_MAX_RAY;
+            rayActive = true; hit = false; closest = T_MAX_RAY; turns = 0;
             sp = 0; qHead = 0; qCount = 0; cur = 0xFFFFFFFFu; travDone = true;
             rinv = F3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
             exactOnly = !(fabsf(rinv.x) < 3.0e38f && fabsf(rinv.y) < 3.0e38f && fabsf(rinv.z) < 3.0e38f);
@@ -190,6 +261,9 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
                 else { cur = 0; travDone = false; }
             }
         }
+#ifdef RTB_TAIL_PROBE
+        if (!probeDrained && __any_sync(FULL, dead)) { probeDrained = true; if (lane == 0 && pw < 8192) g_probe[1][pw] = probe_now(); }
+#endif
         if (__all_sync(FULL, dead)) break;
 
         // =========================================== T: traverse ================================================
@@ -201,6 +275,9 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
                 const bool waiting = !dead && !can;                       // lanes that L or S could put back to work
                 if (__any_sync(FULL, waiting)) break;
             }
+#ifdef RTB_TAIL_PROBE
+            if (can) prSteps++;
+#endif
             if (can) {
                 // CN: 32-byte compressed records; rays with a zero / denormal direction component (reference yields inf / NaN)
                 // keep to the exact 64-byte records
@@ -215,6 +292,9 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
         while (true) {
             const bool has = qCount > 0;
             if (!__any_sync(FULL, has)) break;
+#ifdef RTB_TAIL_PROBE
+            if (has) prLeaf++;
+#endif
             if (has) {
                 const uint32_t g = sm.queue[qHead][tid];
                 qHead = (qHead + 1) & (QCAP - 1);
@@ -235,6 +315,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
         qHead = 0;                                                        // every FIFO is empty: rewind (wave_step_w relies on it)
     }
 
+#ifdef RTB_TAIL_PROBE
+    if (lane == 0 && pw < 8192) g_probe[2][pw] = probe_now();
+    if (pw < 8192) g_probeLane[pw * 32 + lane] = prMax;
+#endif
     if (err) atomicOr(p.errFlag, err);
     if (COUNT) {
         unsigned long long v[5] = { tl.rays, tl.visits, tl.tri, tl.sph, tl.mat };
@@ -246,6 +330,199 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             if (lane == 0 && s) atomicAdd(p.counters + i, s);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// trace_tail_kernel: finishes the paths the main launch parked, ONE RAY PER WARP.  At the end of the main launch every
+// remaining path is a chain of dependent rays, each ray a chain of dependent node fetches; walked by one lane, the chain's
+// latency is the launch's tail (~2.5 ms of a C2 frame, and it does not shrink when the frame is split over more GPUs).  Here
+// all 32 lanes hold the same path state and expand up to 32 pending entries of the current ray per turn: the pending set lives
+// in a per-warp shared-memory stack, each lane decodes one 4-ary record (same records, same conservative test and t-culling
+// as wave_step_u), tests the surviving leaf candidates itself -- exact leaf box, then the reference's primitive test with the
+// order-free acceptance of leaf_test_unordered against its lane-local closest hit -- and appends the surviving internal
+// entries with ballot-ranked stores; the culling bound is the warp-wide minimum of the lane-local closest hits.  The ray's result is the
+// lexicographic minimum (t, primitive id) over the lanes: what the per-lane walk produces, because that walk's outcome does
+// not depend on the order of the tests.  A NaN hit (poison), a zero / denormal direction component or an overfull pending
+// set send the ray to hit_bvh(): the reference's own walk on the exact records.  Shading is the main kernel's S phase,
+// evaluated redundantly by every lane (uniform state, no divergence).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t COOP_CAP = 512;
+template <bool EXT>
+__global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TraceParams p) {
+    __shared__ uint32_t coopStack[WAVE_THREADS / 32][COOP_CAP];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t* stk = coopStack[threadIdx.x >> 5];
+    const TraceScene& sc = p.sc;
+    const uint32_t leafOffset = sc.N - 1;
+    const float T_MIN_RAY = 0.001f, T_MAX_RAY = 10000000.0f;
+    const float INF = __int_as_float(0x7f800000);
+    const uint32_t parked = min(*p.parkCount, p.parkCapacity);
+    unsigned err = 0;
+    Tally tl = { 0, 0, 0, 0, 0 };
+    while (true) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(p.parkCursor, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= parked) break;
+        const float4* e = p.parkBuf + (size_t)PARK_STRIDE * item;
+        const float4 q0 = e[0], q1 = e[1], q2 = e[2], q3 = e[3], q4 = e[4];
+        uint32_t resume = __float_as_uint(q4.w);                          // bit 0: the first ray is in flight (pending set + closest hit parked)
+        f3 o = xyz(q0), d = xyz(q1), color = xyz(q2), att = xyz(q3);
+        uint32_t rng = __float_as_uint(q0.w), depth = __float_as_uint(q1.w);
+        const uint32_t pix = __float_as_uint(q2.w), smp = __float_as_uint(q3.w);
+        const size_t slotIndex = (size_t)__float_as_uint(q4.x) | ((size_t)__float_as_uint(q4.y) << 32);
+        while (true) {                                                    // one ray of the path per turn
+            bool hit = false;
+            Hit rec; rec.t = 0.f; rec.normal = F3(0, 0, 0); rec.mat = 0; rec.prim = 0; rec.back = 0;
+            const f3 rinv = F3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            bool needExact = !(fabsf(rinv.x) < 3.0e38f && fabsf(rinv.y) < 3.0e38f && fabsf(rinv.z) < 3.0e38f);
+            const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
+            if (!needExact && ((resume & 1u) || box_test(o, d, rinv, false, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z))) {
+                const float grow = 1.0e-3f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
+                const bool cullOk = o.x >= lo.x - grow && o.x <= hi.x + grow && o.y >= lo.y - grow && o.y <= hi.y + grow && o.z >= lo.z - grow && o.z <= hi.z + grow;
+                float closest = T_MAX_RAY, best = T_MAX_RAY;              // lane-local closest hit; warp-wide culling bound
+                bool poison = false, fit = true;
+                uint32_t n = 1;
+                if (resume & 1u) {                                        // continue a parked ray: its stack + cur, lane 0 keeps its closest hit
+                    const uint32_t psp = resume >> 8, pcur = __float_as_uint(q4.z);
+                    const float4 q5 = e[5], q6 = e[6];
+                    if (lane < psp) stk[lane] = __float_as_uint(((const float*)(e + 7))[lane]);
+                    if (lane == 0 && pcur != 0xFFFFFFFFu) stk[psp] = pcur;
+                    n = psp + (pcur != 0xFFFFFFFFu ? 1u : 0u);
+                    closest = best = q6.w;                                // the others may only accept t <= the parked closest; ties: see the reduce
+                    if (lane == 0 && (resume & 2u)) {
+                        hit = true; rec.t = q5.x; rec.normal = F3(q5.y, q5.z, q5.w);
+                        rec.mat = __float_as_uint(q6.x); rec.prim = __float_as_uint(q6.y); rec.back = (int)__float_as_uint(q6.z);
+                    }
+                    resume = 0;
+                } else if (lane == 0) stk[0] = 0u;
+                __syncwarp();
+                while (n > 0) {
+                    const uint32_t take = n < 32u ? n : 32u;
+                    const uint32_t my = lane < take ? stk[n - 1u - lane] : 0xFFFFFFFFu;
+                    n -= take;
+                    __syncwarp();
+                    uint32_t intMask = 0, id0 = 0, id1 = 0, id2 = 0, id3 = 0;
+                    if (my != 0xFFFFFFFFu) {
+                        const uint4* rp = sc.wide + 4ull * my;
+                        const f8 h0 = ldg256(rp), h1 = ldg256(rp + 2);
+                        const uint32_t w3 = __float_as_uint(h0.lo.w);
+                        const uint32_t lox = __float_as_uint(h0.hi.x), loy = __float_as_uint(h0.hi.y), loz = __float_as_uint(h0.hi.z),
+                                       hix = __float_as_uint(h0.hi.w), hiy = __float_as_uint(h1.lo.x), hiz = __float_as_uint(h1.lo.y);
+                        id0 = __float_as_uint(h1.lo.z); id1 = __float_as_uint(h1.lo.w); id2 = __float_as_uint(h1.hi.x); id3 = __float_as_uint(h1.hi.y);
+                        const float sx = __uint_as_float((w3 & 0xFFu) << 23), sy = __uint_as_float(((w3 >> 8) & 0xFFu) << 23),
+                                    sz = __uint_as_float(((w3 >> 16) & 0xFFu) << 23);
+                        const float ax = sx * rinv.x, ay = sy * rinv.y, az = sz * rinv.z;
+                        const float bx = (h0.lo.x - o.x) * rinv.x, by = (h0.lo.y - o.y) * rinv.y, bz = (h0.lo.z - o.z) * rinv.z;
+                        const float m = fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(bx)), fmaf(255.0f, fabsf(ay), fabsf(by))), fmaf(255.0f, fabsf(az), fabsf(bz)));
+                        const float tol = -2.0e-6f * m;                   // the error budget of wave_step_u; NaN / inf -> nothing is dropped
+                        const float farLimit = (cullOk ? best : INF) - tol, nearLimit = (cullOk ? T_MIN_RAY : -INF) + tol;
+                        const bool ngx = rinv.x < 0.0f, ngy = rinv.y < 0.0f, ngz = rinv.z < 0.0f;
+                        const uint32_t nX = ngx ? hix : lox, fX = ngx ? lox : hix;
+                        const uint32_t nY = ngy ? hiy : loy, fY = ngy ? loy : hiy;
+                        const uint32_t nZ = ngz ? hiz : loz, fZ = ngz ? loz : hiz;
+                        const uint32_t meta = w3 >> 24;
+                        uint32_t passMask = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+#define RTB_B(w) __uint2float_rn(((w) >> (8 * k)) & 0xFFu)
+                            const float tn = fmaxf(fmaxf(fmaf(RTB_B(nX), ax, bx), fmaf(RTB_B(nY), ay, by)), fmaf(RTB_B(nZ), az, bz));
+                            const float tf = fminf(fminf(fmaf(RTB_B(fX), ax, bx), fmaf(RTB_B(fY), ay, by)), fmaf(RTB_B(fZ), az, bz));
+#undef RTB_B
+                            const bool pass = !((tf - tn) < tol) && !(tn > farLimit) && !(tf < nearLimit);
+                            passMask |= pass ? (1u << k) : 0u;
+                        }
+                        passMask &= meta >> 4;
+                        const uint32_t leafMask = meta & 0xFu;
+                        intMask = passMask & ~leafMask;
+                        const uint32_t enqMask = passMask & leafMask;
+#pragma unroll 1
+                        for (int k = 0; k < 4; k++) {
+                            if (!((enqMask >> k) & 1u)) continue;
+                            const uint32_t g = (k == 0 ? id0 : k == 1 ? id1 : k == 2 ? id2 : id3) - leafOffset;
+                            if (leaf_box_passes(sc, g, o, d, rinv, false)) leaf_test_unordered<false>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl, poison);
+                        }
+                    }
+                    if (n + 128u > COOP_CAP) { fit = false; break; }      // warp-uniform
+                    { const bool b = intMask & 1u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id0; n += __popc(bal); }
+                    { const bool b = intMask & 2u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id1; n += __popc(bal); }
+                    { const bool b = intMask & 4u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id2; n += __popc(bal); }
+                    { const bool b = intMask & 8u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id3; n += __popc(bal); }
+                    __syncwarp();
+                    float mn = closest;                                   // never NaN: a NaN hit only raises poison
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) mn = fminf(mn, __shfl_xor_sync(FULL, mn, off));
+                    best = mn;
+                }
+                __syncwarp();
+                if (!fit || __any_sync(FULL, poison)) {
+                    needExact = true;
+                } else {
+                    // lexicographic minimum (t, primitive id) over the lanes that hold a hit, broadcast to every lane
+                    float bt = hit ? rec.t : INF;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) bt = fminf(bt, __shfl_xor_sync(FULL, bt, off));
+                    uint32_t bp = (hit && rec.t == bt) ? rec.prim : 0xFFFFFFFFu;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) bp = min(bp, __shfl_xor_sync(FULL, bp, off));
+                    const unsigned winBal = __ballot_sync(FULL, hit && rec.t == bt && rec.prim == bp);
+                    hit = winBal != 0u;
+                    const int win = hit ? __ffs(winBal) - 1 : 0;
+                    rec.t = __shfl_sync(FULL, rec.t, win);
+                    rec.normal = F3(__shfl_sync(FULL, rec.normal.x, win), __shfl_sync(FULL, rec.normal.y, win), __shfl_sync(FULL, rec.normal.z, win));
+                    rec.mat = __shfl_sync(FULL, rec.mat, win); rec.prim = __shfl_sync(FULL, rec.prim, win); rec.back = __shfl_sync(FULL, rec.back, win);
+                }
+            }
+            if (needExact) hit = hit_bvh<false>(sc, o, d, T_MIN_RAY, T_MAX_RAY, rec, tl, err);   // the reference's walk, every lane alike
+            if (p.primaryMode == 1u) {                                    // primary-hit launch: keep the hit record, no shading
+                if (lane == 0) {
+                    float4* h = p.primaryHits + 3ull * pix;
+                    h[0] = make_float4(rec.t, rec.normal.x, rec.normal.y, rec.normal.z);
+                    h[1] = make_float4(__uint_as_float(rec.prim), __uint_as_float(rec.mat), __uint_as_float(hit ? 1u : 0u), __uint_as_float((uint32_t)rec.back));
+                    h[2] = make_float4(d.x, d.y, d.z, 0.f);
+                }
+                break;
+            }
+            // ---- the main kernel's S phase (rayColor loop body :283-307), uniform over the warp ----
+            if (depth == 0 && smp == 0 && p.firstPass && p.hitPrim && lane == 0) {
+                p.hitPrim[pix] = hit ? rec.prim : 0xFFFFFFFFu;
+                if (p.hitT) p.hitT[pix] = hit ? rec.t : 0.0f;
+            }
+            bool pathEnd = true;
+            if (!hit) {
+                color = color + F3(0.f, 0.f, 0.f) * att;
+            } else {
+                const float4 m = __ldg(sc.mats + rec.mat);
+                const uint32_t type = __float_as_uint(m.w);
+                const f3 albedo = xyz(m);
+                const f3 emitted = (type == RTB_LIGHT) ? albedo : F3(0.f, 0.f, 0.f);
+                color = color + emitted * att;
+                if (type == RTB_DIFFUSE) {
+                    const f3 P = o + rec.t * d;
+                    const f3 nd = normalize(rec.normal + random_unit_vector(rng));
+                    o = P; d = nd;
+                    att = att * albedo;
+                    pathEnd = false;
+                } else if (EXT && type != RTB_LIGHT) {
+                    f3 a2, nd;
+                    const f3 P = o + rec.t * d;
+                    if (scatter_extension(type, albedo, d, rec, rng, a2, nd)) { o = P; d = nd; att = att * a2; pathEnd = false; }
+                }
+                depth++;
+                if (depth >= p.maxDepth) pathEnd = true;
+            }
+            if (pathEnd) {
+                if (lane == 0) {
+                    float4* out = p.sampleBuf + slotIndex;
+                    out->x = color.x; out->y = color.y; out->z = color.z;   // .w keeps the sample's incoming alpha
+                    if (p.rngOut && p.lastPass && smp + 1 == p.sampleCount) p.rngOut[pix] = rng;
+                }
+                break;
+            }
+        }
+    }
+    if (err) atomicOr(p.errFlag, err);
 }
 
 template <bool COUNT, bool EXT, bool CULL, int NODES>
@@ -312,20 +589,43 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool
         p.sampleSkip = first == 0 ? skip0 : 0;                              // later passes continue from the image's alpha
         p.firstPass = first == 0;
         p.lastPass = first + p.sampleCount >= totalSamples;
-        cudaMemsetAsync(p.workCounter64, 0, 16, st);                        // work counter + active-pixel count
+        cudaMemsetAsync(p.workCounter64, 0, 32, st);                        // work counter + active-pixel count + park count / cursor
         if (count) wave_prepass_kernel<true><<<(pixels + 255) / 256, 256, 0, st>>>(p);
         else wave_prepass_kernel<false><<<(pixels + 255) / 256, 256, 0, st>>>(p);
+        const bool tail = nodesMode == 3 && (p.coopMax != 0u || p.coopTurns != 0u);
+        auto launch_tail = [&]() {                                          // finish the parked paths / rays, one ray per warp
+            int nb = 0;
+            if (ext) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_tail_kernel<true>, WAVE_THREADS, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_tail_kernel<false>, WAVE_THREADS, 0);
+            const unsigned grid = (unsigned)smCount * (unsigned)(nb > 0 ? nb : 1);
+            if (ext) trace_tail_kernel<true><<<grid, WAVE_THREADS, 0, st>>>(p);
+            else trace_tail_kernel<false><<<grid, WAVE_THREADS, 0, st>>>(p);
+            launches++;
+        };
         if (share && first == 0) {                                          // one primary ray per active pixel -> primaryHits
             p.primaryMode = 1;
             dispatch_wave(st, p, count, ext, cull, nodesMode, smCount, ((uint64_t)pixels + WAVE_THREADS - 1) / WAVE_THREADS);
+            if (tail && p.coopTurns != 0u) launch_tail();
             cudaMemsetAsync(p.workCounter64, 0, 8, st);                     // rewind the work counter, keep the active-pixel count
+            if (tail) cudaMemsetAsync((unsigned int*)p.workCounter64 + 4, 0, 16, st);   // park count / cursor
             launches++;
         }
         p.primaryMode = share ? 2u : 0u;
         const uint64_t need = ((uint64_t)pixels * p.sampleCount + WAVE_THREADS - 1) / WAVE_THREADS;   // never more lanes than items
         dispatch_wave(st, p, count, ext, cull, nodesMode, smCount, need);
+        if (tail) launch_tail();
         wave_accumulate_kernel<0><<<(pixels + 255) / 256, 256, 0, st>>>(p);
         launches += 3;
+#ifdef RTB_TAIL_PROBE
+        if (const char* pf = getenv("RTB_TAIL_PROBE_FILE")) {
+            static unsigned long long host[3][8192];
+            cudaStreamSynchronize(st);
+            cudaMemcpyFromSymbol(host, g_probe, sizeof(host));
+            static uint4 hostLane[8192 * 32];
+            cudaMemcpyFromSymbol(hostLane, g_probeLane, sizeof(hostLane));
+            if (FILE* f = fopen(pf, "wb")) { fwrite(host, 1, sizeof(host), f); fwrite(hostLane, 1, sizeof(hostLane), f); fclose(f); }
+        }
+#endif
     }
     return launches;
 }

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(256) wave_prepass_kernel(const TraceParams p) 
         slot = __shfl_sync(0xFFFFFFFFu, slot, __ffs(bal) - 1) + __popc(bal & ((1u << lane) - 1u));
         if (activePixel) {
             p.activePix[slot] = idx;
+            p.activeXY[slot] = x | (y << 16);
             for (uint32_t s = 0; s < p.sampleCount; s++) {
                 p.sampleBuf[(size_t)s * p.slotCapacity + slot] = make_float4(0.f, 0.f, 0.f, alpha);
                 uint32_t t = base + alpha_to_u32(alpha);
