@@ -1,6 +1,6 @@
 """Turns an .ncu-rep (ncu --set full --import-source on) into the text summary committed under profiles/.
 
-    python profiles/summarize_ncu.py gpurun_out/wave3_r01.ncu-rep profiles/r01_wave_ncu_summary.txt "title"
+    python profiles/summarize_ncu.py gpurun_out/wave3_r01.ncu-rep profiles/r01_wave_ncu_summary.txt "title" [launch index in the report]
 
 Reads the raw page (kernel-level counters) and the source page (per-SASS-instruction execution counts) through
 `ncu -i ... --page raw|source --csv` and prints: duration, DRAM / L2 / L1 traffic and hit rates, issue utilisation, pipe
@@ -31,13 +31,18 @@ KEYS = [
 ]
 
 
+SKIP = 0
+
+
 def page(rep, which):
-    out = subprocess.run(["ncu", "-i", rep, "--page", which, "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", which, "--csv", "-s", str(SKIP), "-c", "1"], capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
 def main():
+    global SKIP
     rep, dst, title = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
+    SKIP = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     lines = [f"# {title}", f"# source: {rep} (ncu --set full --clock-control none --import-source on)", ""]
     raw = page(rep, "raw")
     hdr, units, vals = raw[0], raw[1], raw[2]
@@ -55,6 +60,9 @@ def main():
             if v >= 0.05:
                 lines.append(f"  {h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]:28s} {v:6.2f}")
     src = page(rep, "source")
+    second = [i for i, r in enumerate(src) if i > 0 and r and r[0] == "Kernel Name"]
+    if second:                          # with a launch filter ncu prints the kernel's table twice
+        src = src[:second[0]]
     sh = src[1]
     ia, isrc, ie, it, isamp = sh.index("Address"), sh.index("Source"), sh.index("Instructions Executed"), sh.index("Thread Instructions Executed"), sh.index("# Samples")
     data = []
