@@ -520,3 +520,45 @@ def test_empty_and_zero_sample_submissions(device):
     rt.clear_image(); rt.raytrace(ubo, 0); device.wait_idle()          # zero dispatches: the cleared image is untouched
     img = rt.read_image()
     assert np.all(img[..., :3] == 0) and np.all(img[..., 3] == 1)
+
+
+@pytest.mark.parametrize("coop,turns", [(0, 1), (32, 0), (32, 1), (8, 3)])
+def test_tail_handover_forced(device, monkeypatch, coop, turns):
+    """Long-ray / tail hand-over (trace_wave.cu: parked rays and paths finished by trace_tail_kernel, one ray per warp) with the
+    thresholds forced so low that nearly every ray -- primary launch included -- takes that path: rays parked in flight after
+    `turns` turns (with their stack and closest hit), paths parked at a ray boundary once the queue is drained.  Image, primary
+    hit ids / t, RNG states must be the oracle's, with and without the material extension, shared and unshared primaries,
+    1 and 6 samples (1 sample: the primary ray itself is walked by the main launch and may be parked at depth 0)."""
+    from raytracergpu_mastersproject_b200 import capi
+    monkeypatch.setenv("RTB_WAVE_COOP", str(coop))
+    monkeypatch.setenv("RTB_WAVE_COOP_TURNS", str(turns))
+    W, H = 80, 56
+    sc = SU.random_scene(23, n_tris=900, n_spheres=120, sort_morton=True)
+    ubo = SU.make_ubo(sc, random_state=77)
+    for spp in (1, 6):
+        _check_against_oracle(device, sc, ubo, W, H, spp, [capi.TRACE_WIDE_NODES, capi.TRACE_WIDE_NODES | capi.TRACE_NO_PRIMARY_SHARING])
+    # extension materials through trace_tail_kernel<true>
+    ref = O.build_bvh(sc["models"], sc["triangles"], sc["spheres"])
+    rr = O.raytrace(ubo, W, H, ref["tris"], ref["sphs"], sc["materials"], ref["nodes"], 5, opt=O.make_options(ext_materials=True))
+    rt = _rt(device, W, H)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.build_bvh(ubo)
+    rt.clear_image(); rt.raytrace(ubo, 5, flags=capi.TRACE_EXT_MATERIALS | capi.TRACE_WIDE_NODES); device.wait_idle()
+    assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"])), "extension materials through the tail kernel differ"
+
+
+def test_tail_handover_off_equals_on(device, monkeypatch):
+    """the hand-over is a scheduling decision: switched off (RTB_WAVE_COOP=0 RTB_WAVE_COOP_TURNS=0) the frame is the same"""
+    from raytracergpu_mastersproject_b200 import capi, make_ubo, scenes
+    sc = scenes.load_scene("meshRoom:110:9")
+    W, H, spp = 160, 90, 8
+    ubo = make_ubo(len(sc["triangles"]), len(sc["spheres"]), len(sc["materials"]), sc["max_depth"], 11, sc["vfov"])
+    rt = _rt(device, W, H)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.build_bvh(ubo)
+    frames = []
+    for coop, turns in ((0, 0), (8, 32), (32, 2)):
+        monkeypatch.setenv("RTB_WAVE_COOP", str(coop)); monkeypatch.setenv("RTB_WAVE_COOP_TURNS", str(turns))
+        rt.clear_image(); rt.raytrace(ubo, spp); device.wait_idle()
+        frames.append(rt.read_image())
+    assert np.array_equal(_bits(frames[0]), _bits(frames[1])) and np.array_equal(_bits(frames[0]), _bits(frames[2]))
