@@ -205,3 +205,49 @@ def test_cuda_logistic_matches_reference_binary(device):
         assert _same(pts.read(np.float32, 2 * n).reshape(n, 2), g["points"][s]), f"logistic.comp dispatch {s}"
     out = img.read(np.uint8, W * H * 4).reshape(H, W, 4)
     assert np.array_equal(out.sum(-1) > 0, g["plotted"])
+
+
+# ------------------------------------------------------------------------------------------------ the generator itself
+_SPV = "/root/reference/RaytracerGPU_MastersProject/shaders/compiled"
+
+
+@pytest.mark.skipif(not os.path.isdir(_SPV), reason="the reference tree only exists in the build container")
+def test_interpreter_regenerates_committed_fixtures():
+    """Build container only: re-run the reference binaries through oracle/spirv_interp.py on the two smallest cases and on the
+    logistic program and compare with the committed fixtures -- the fixtures are reproducible from the reference tree."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_spirv_golden as M
+    for name in ("two", "three"):
+        out = M.generate(name)
+        g = _load(name)
+        for k in ("tris_w", "sphs_w", "enclosing", "morton_unsorted", "morton", "nodes_unfitted", "cinfo_unfitted", "nodes", "cinfo"):
+            assert _same(out[k], g[k]), (name, k)
+        assert np.array_equal(out["images_bvh"].view(np.uint32), g["images_bvh"].view(np.uint32)), name
+    lg = M.run_logistic(M.LOGISTIC)
+    g = np.load(os.path.join(HERE, "golden", "spirv_logistic.npz"))
+    assert _same(lg["points"], g["points"]) and np.array_equal(lg["plotted"], g["plotted"])
+
+
+@pytest.mark.skipif(not os.path.isdir(_SPV), reason="the reference tree only exists in the build container")
+def test_interpreter_reads_the_reference_layouts():
+    """the record layouts the whole repository relies on, read from the Offset / ArrayStride decorations of the reference binary"""
+    from oracle.spirv_interp import DEC_ARRAY_STRIDE, DEC_OFFSET, Module
+    m = Module(os.path.join(_SPV, "raytraceBVH.comp.spv"))
+    b = m.bindings()
+    assert m.local_size == (32, 32, 1) and sorted(b) == [0, 1, 2, 3, 4, 5, 6]
+
+    def element(binding):       # struct { T data[]; } -> (stride, struct type id of T)
+        st = m.types[b[binding][1]]
+        arr = st[1][0]
+        return m.decor[arr][DEC_ARRAY_STRIDE][0], m.types[arr][1]
+
+    def offsets(tid):
+        return [m.mdecor[(tid, i)][DEC_OFFSET][0] for i in range(len(m.types[tid][1]))]
+
+    stride, tri = element(2); assert stride == 64 and offsets(tri) == [0, 16, 32, 48, 52]        # Triangle
+    stride, sph = element(3); assert stride == 32 and offsets(sph) == [0, 16, 20, 24]            # Sphere
+    stride, mat = element(4); assert stride == 32 and offsets(mat) == [0, 16]                    # Material
+    stride, node = element(5); assert stride == 40 and offsets(node) == [0, 24, 28, 32, 36]      # HLBVHNode
+    assert offsets(m.types[node][1][0]) == [0, 4, 8, 12, 16, 20]                                  # AABB: minX maxX minY maxY minZ maxZ
+    assert offsets(b[0][1]) == [0, 16, 32, 48, 52, 56, 60, 64, 68, 72]                            # ParameterUBO (80 bytes)
