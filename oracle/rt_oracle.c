@@ -1,7 +1,7 @@
 /*
  * rt_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).  See rt_oracle.h for the contract.
  *
- * Pinned bit for bit against the reference's own compiled shaders (shaders/compiled/*.spv run by oracle/spirv_interp.py ->
+ * Pinned bit for bit against the reference's own compiled shaders (shaders/compiled/ *.spv run by oracle/spirv_interp.py ->
  * tests/golden/spirv_*.npz, tests/test_spirv_golden.py); driver-defined built-in arithmetic pinned by convention (U1..U14).
  *
  * Every function restates one reference shader and cites it.  The code follows the shader text literally

@@ -5,7 +5,7 @@
  * (paths below are relative to RaytracerGPU_MastersProject/ in the reference tree).
  *
  * HOW IT IS PINNED: the reference ships no tests, golden vectors or fixtures for this path and cannot run on a device
- * in this image (no Vulkan loader/ICD, no glslc) -- but it ships every shader COMPILED (shaders/compiled/*.spv).
+ * in this image (no Vulkan loader/ICD, no glslc) -- but it ships every shader COMPILED (shaders/compiled/ *.spv).
  * oracle/spirv_interp.py executes those binaries on the CPU; tests/golden/make_spirv_golden.py committed their outputs
  * (every buffer after every dispatch, nine scenes) as tests/golden/spirv_*.npz, and tests/test_spirv_golden.py checks
  * that every function below reproduces them BIT FOR BIT, stage by stage.  What the binaries do not define -- the
