@@ -437,16 +437,18 @@ def run_b200(args):
         local_cnt = dict(zip(capi.COUNTER_FIELDS, [int(x) for x in lc.tolist()]))
     alg_bytes = 40 * local_cnt["nodeVisits"] + 40 * local_cnt["triTests"] + 20 * local_cnt["sphTests"] + 20 * local_cnt["matReads"] + 32 * pix_local
     achieved = alg_bytes / (trace_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, limiter = None, None
     tp = os.path.join(ROOT, "profiles", "trace_kernel_dram_bytes.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.config)
+            prof = json.load(open(tp))
+            traffic = prof.get(args.config)
+            limiter = prof.get("_limiter", {}).get(args.config)     # what ncu says bounds the kernel (not HBM): reported, not measured live
         except Exception:  # noqa: BLE001
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": {"wave": "rtb::trace_wave_kernel", "stream": "rtb::trace_stream_kernel"}.get(args.kernel, "rtb::trace_kernel"), "kernel_ms": trace_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "peak_source": peak_src,
+                "peak_source": peak_src, "limiter_from_ncu": limiter,
                 "per_ray": {"node_visits": local_cnt["nodeVisits"] / max(local_cnt["rays"], 1),
                             "tri_tests": local_cnt["triTests"] / max(local_cnt["rays"], 1),
                             "sphere_tests": local_cnt["sphTests"] / max(local_cnt["rays"], 1)}}
