@@ -179,6 +179,60 @@ def run_logistic(cfg):
     return dict(points0=pts, color=color, points=np.stack(states), plotted=(np.array(im.px, np.float32).sum(-1) > 0))
 
 
+def generate_pixels(spec, W, H, n_pixels, spp, random_state, center_box=None, seed=2024, fixed=()):
+    """A host-built scene (raytracergpu_mastersproject_b200/host/Scenes.cpp) through the reference binaries: S1 on the whole scene,
+    S2 (raytraceBVH.comp.spv) on a seeded sample of pixels of the full-size image -- every pixel is independent."""
+    from oracle.spirv_interp import Image
+    from raytracergpu_mastersproject_b200 import scenes
+    sc = scenes.load_scene(spec)
+    ubo = SU.make_ubo(sc, max_depth=sc["max_depth"], random_state=random_state, vfov=sc["vfov"])
+    t0 = time.time()
+    b = run_build(sc, ubo)
+    rng = np.random.default_rng(seed)
+    px = set(fixed)
+    while len(px) < n_pixels:
+        if center_box is not None and rng.random() < 0.7:
+            x0, y0, x1, y1 = center_box
+            px.add((int(rng.integers(x0, x1)), int(rng.integers(y0, y1))))
+        else:
+            px.add((int(rng.integers(0, W)), int(rng.integers(0, H))))
+    px = sorted(px)
+
+    class SparseRow(dict):          # the image as {y: {x: texel}}: only the sampled pixels are ever touched
+        def __missing__(self, k):
+            v = [0.0, 0.0, 0.0, 1.0]
+            self[k] = v
+            return v
+
+    class SparseImage(Image):
+        def __init__(self, w, h):
+            self.w, self.h = w, h
+
+            class Rows(dict):
+                def __missing__(self, k):
+                    r = SparseRow()
+                    self[k] = r
+                    return r
+            self.px = Rows()
+    im = SparseImage(W, H)
+    scratch = bytearray(80)
+    res = {0: bytearray(ubo.tobytes()), 1: im, 2: bytearray(b["tris_w"].tobytes()), 3: bytearray(b["sphs_w"].tobytes()),
+           4: bytearray(sc["materials"].tobytes()), 5: bytearray(b["nodes"].tobytes()), 6: scratch}
+    m = module("raytraceBVH.comp")
+    want = set(px)
+    vals = []
+    for _ in range(spp):
+        m.dispatch((W // 32 + 1, H // 32 + 1, 1), res, only=lambda g: (g[0], g[1]) in want)
+        vals.append(np.array([im.px[y][x] for (x, y) in px], np.float32))
+    print(f"{spec}: {len(sc['triangles'])} triangles, {len(sc['spheres'])} spheres, {len(px)} pixels of {W}x{H} x{spp}: {m.n_executed} SPIR-V "
+          f"instructions traced, {time.time() - t0:.1f} s")
+    out = dict(spec=np.array(spec), models=sc["models"], triangles=sc["triangles"], spheres=sc["spheres"], materials=sc["materials"], ubo=ubo,
+               W=np.int32(W), H=np.int32(H), spp=np.int32(spp), pixels=np.array(px, np.int32), values=np.stack(vals),
+               scratch=np.frombuffer(bytes(scratch), np.float32).copy())
+    out.update(b)
+    return out
+
+
 def generate_c1(n_pixels=1500, spp=2, random_state=12345):
     """BASELINE config C1 on its real scene: the host's complexScene (Scenes.cpp:337-398 with the stand-in models) at the
     reference's 800x800 window, S1 by the reference binaries on all 1 000+ primitives, S2 by raytraceBVH.comp.spv on a seeded
@@ -240,10 +294,21 @@ def generate(name):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["logistic", "c1pixels"])
+    names = sys.argv[1:] or (list(CASES) + ["logistic", "c1pixels", "c2pixels"])
     for name in names:
         if name == "c1pixels":
             np.savez_compressed(os.path.join(HERE, "spirv_c1pixels.npz"), **generate_c1())
+        elif name == "c2pixels":
+            # BASELINE config C2's generator at a size the interpreter can hold (meshRoom:70 = 9 806 primitives instead of 871 206): the
+            # displaced sphere in the simpleScene room at C2's 1920x1080, depth 8 -- incl. rays tangent to the tessellated surface
+            import hashlib
+            out = generate_pixels("meshRoom:70:5", 1920, 1080, 700, 2, 1, center_box=(560, 140, 1360, 940))
+            big = ("models", "triangles", "spheres", "materials", "tris_w", "sphs_w", "morton_unsorted", "morton", "nodes_unfitted",
+                   "cinfo_unfitted", "nodes", "cinfo")       # kept as SHA-256 digests: the scene is rebuilt by the host at test time
+            slim = {k: v for k, v in out.items() if k not in big}
+            slim["digest_names"] = np.array(big)
+            slim["digests"] = np.array([hashlib.sha256(np.ascontiguousarray(out[k]).tobytes()).hexdigest() for k in big])
+            np.savez_compressed(os.path.join(HERE, "spirv_c2pixels.npz"), **slim)
         elif name == "logistic":
             np.savez_compressed(os.path.join(HERE, "spirv_logistic.npz"), **run_logistic(LOGISTIC))
             print("logistic done")

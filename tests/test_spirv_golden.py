@@ -18,7 +18,7 @@ from oracle import oracle as O
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = sorted(os.path.basename(p)[len("spirv_"):-len(".npz")] for p in glob.glob(os.path.join(HERE, "golden", "spirv_*.npz"))
-               if not p.endswith(("spirv_logistic.npz", "spirv_c1pixels.npz")))
+               if not p.endswith(("spirv_logistic.npz", "spirv_c1pixels.npz", "spirv_c2pixels.npz")))
 
 
 def _load(name):
@@ -116,6 +116,40 @@ def test_oracle_c1_matches_reference_binaries():
     assert _same(sc["triangles"], g["triangles"]) and _same(sc["models"], g["models"]) and _same(sc["materials"], g["materials"])
 
 
+def _c2_scene_and_digests():
+    import hashlib
+
+    from raytracergpu_mastersproject_b200 import scenes
+    g = _load("c2pixels")
+    sc = scenes.load_scene(str(g["spec"]))
+    want = dict(zip(g["digest_names"].tolist(), g["digests"].tolist()))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+    for k in ("models", "triangles", "spheres", "materials"):
+        assert sha(sc[k]) == want[k], f"the host's {g['spec']} scene changed: {k}"
+    return g, sc, want, sha
+
+
+def test_oracle_c2_generator_matches_reference_binaries():
+    """BASELINE config C2's scene generator (displaced sphere in the simpleScene room) at 9 806 primitives, C2's 1920x1080 and depth 8:
+    every S1 buffer of the reference binaries (as SHA-256) and 700 sampled pixels of two raytraceBVH.comp dispatches."""
+    g, sc, want, sha = _c2_scene_and_digests()
+    W, H, spp = int(g["W"]), int(g["H"]), int(g["spp"])
+    T, S = len(sc["triangles"]), len(sc["spheres"]); N = T + S
+    tw, sw = O.model_to_world(sc["models"], sc["triangles"], sc["spheres"])
+    assert sha(tw) == want["tris_w"] and sha(sw) == want["sphs_w"]
+    enc = O.enclosing_aabb(tw, sw); assert _same(enc, g["enclosing"])
+    mu = O.morton_codes(tw, sw, enc); assert sha(mu) == want["morton_unsorted"]
+    ms = O.radix_sort(mu); assert sha(ms) == want["morton"]
+    n0, c0 = O.construct_hlbvh(tw, sw, ms); assert sha(n0) == want["nodes_unfitted"] and sha(c0) == want["cinfo_unfitted"]
+    n1, c1 = O.refit_aabbs(n0, c0, N); assert sha(n1) == want["nodes"] and sha(c1) == want["cinfo"]
+    xs, ys = g["pixels"][:, 0], g["pixels"][:, 1]
+    image = None
+    for s in range(spp):
+        image = O.raytrace(g["ubo"], W, H, tw, sw, sc["materials"], n1, 1, image=image, want_hits=False, want_rng=False)["image"]
+        assert np.array_equal(image[ys, xs].view(np.uint32), g["values"][s].view(np.uint32)), f"dispatch {s}"
+    assert (g["values"][-1][:, :3].sum(-1) > 0).sum() >= 5        # some sampled paths reach the light
+
+
 def test_oracle_logistic_matches_reference_binary():
     g = np.load(os.path.join(HERE, "golden", "spirv_logistic.npz"))
     pts = g["points0"].copy()
@@ -184,6 +218,28 @@ def test_cuda_c1_matches_reference_binaries(device):
         rt.raytrace(g["ubo"], 1); device.wait_idle()
         assert np.array_equal(rt.read_image()[ys, xs].view(np.uint32), g["values"][s].view(np.uint32)), f"dispatch {s}"
     for fl in (0, capi.TRACE_WIDE_NODES, capi.TRACE_EXACT_NODES, capi.TRACE_SIMPLE_KERNEL):
+        rt.clear_image(); rt.raytrace(g["ubo"], spp, flags=fl); device.wait_idle()
+        assert np.array_equal(rt.read_image()[ys, xs].view(np.uint32), g["values"][-1].view(np.uint32)), f"flags {fl}"
+
+
+@pytest.mark.gpu
+def test_cuda_c2_generator_matches_reference_binaries(device):
+    from raytracergpu_mastersproject_b200 import Raytracer, capi
+    g, sc, want, sha = _c2_scene_and_digests()
+    W, H, spp = int(g["W"]), int(g["H"]), int(g["spp"])
+    N = len(sc["triangles"]) + len(sc["spheres"])
+    rt = Raytracer(device, W, H)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.build_bvh(g["ubo"])
+    device.wait_idle()
+    assert sha(rt.nodes.read(O.NODE, 2 * N - 1)) == want["nodes"] and sha(rt.morton1.read(O.MORTON, N)) == want["morton"]
+    assert sha(rt.cinfo.read(O.CINFO, 2 * N - 1)) == want["cinfo"] and _same(rt.enclosing.read(O.ENCLOSING, 1), g["enclosing"])
+    xs, ys = g["pixels"][:, 0], g["pixels"][:, 1]
+    rt.clear_image()
+    for s in range(spp):
+        rt.raytrace(g["ubo"], 1); device.wait_idle()
+        assert np.array_equal(rt.read_image()[ys, xs].view(np.uint32), g["values"][s].view(np.uint32)), f"dispatch {s}"
+    for fl in (0, capi.TRACE_REFERENCE_ORDER, capi.TRACE_EXACT_NODES, capi.TRACE_NO_PRIMARY_SHARING):   # 9 806 primitives: the 4-ary walk is the default
         rt.clear_image(); rt.raytrace(g["ubo"], spp, flags=fl); device.wait_idle()
         assert np.array_equal(rt.read_image()[ys, xs].view(np.uint32), g["values"][-1].view(np.uint32)), f"flags {fl}"
 
