@@ -51,6 +51,21 @@ CASES = {
     "two": dict(scene=dict(seed=5, n_tris=1, n_spheres=1, room=False), W=8, H=8, spp=1, depth=2, random_state=1, programs=("bvh",)),
     "three": dict(scene=dict(seed=6, n_tris=2, n_spheres=1, room=False), W=8, H=8, spp=1, depth=2, random_state=2, programs=("bvh",)),
 }
+# edge cases (written as spirv_edge_*.npz): they pin the ORACLE on the corners of the parameter space
+EDGE_CASES = {
+    # N = 1: the root is the only node and a leaf (ConstructHLBVH.comp with zero internal nodes)
+    "edge_one": dict(scene=dict(seed=31, n_tris=0, n_spheres=1, room=False), W=16, H=16, spp=2, depth=3, random_state=3, programs=("bvh", "linear")),
+    # randomState + 1 wraps to 0: every pixel's base seed is 0 (random.glsl:10), only the alpha chain separates the samples
+    "edge_seedwrap": dict(scene=dict(seed=32, n_tris=20, n_spheres=4), W=16, H=12, spp=3, depth=4, random_state=0xFFFFFFFF, programs=("bvh",)),
+    # maxRayTraceDepth 0 (no ray at all: colour stays 0, the alpha chain still advances) and 1 (primary hit only)
+    "edge_depth0": dict(scene=dict(seed=33, n_tris=20, n_spheres=4), W=12, H=12, spp=2, depth=0, random_state=5, programs=("bvh", "linear")),
+    "edge_depth1": dict(scene=dict(seed=33, n_tris=20, n_spheres=4), W=12, H=12, spp=2, depth=1, random_state=5, programs=("bvh", "linear")),
+    # wide field of view, non-square image whose sides are multiples of the 32x32 workgroup (one extra, empty workgroup row / column)
+    "edge_fov90": dict(scene=dict(seed=34, n_tris=24, n_spheres=6), W=64, H=32, spp=1, depth=4, random_state=8, vfov=90.0, programs=("bvh",)),
+    # six dispatches: a long alpha seed chain (raytraceBVH.comp:350,372)
+    "edge_chain6": dict(scene=dict(seed=35, n_tris=16, n_spheres=3), W=10, H=10, spp=6, depth=3, random_state=13, programs=("bvh",)),
+}
+CASES_ALL = dict(CASES, **EDGE_CASES)
 LOGISTIC = dict(points=2048, W=96, H=64, steps=3, seed=11)
 
 
@@ -271,9 +286,9 @@ def generate_c1(n_pixels=1500, spp=2, random_state=12345):
 
 
 def generate(name):
-    c = CASES[name]
+    c = CASES_ALL[name]
     sc = make_scene(c["scene"])
-    ubo = SU.make_ubo(sc, max_depth=c["depth"], random_state=c["random_state"])
+    ubo = SU.make_ubo(sc, max_depth=c["depth"], random_state=c["random_state"], vfov=c.get("vfov", 40.0))
     t0 = time.time()
     out = dict(models=sc["models"], triangles=sc["triangles"], spheres=sc["spheres"], materials=sc["materials"], ubo=ubo,
                W=np.int32(c["W"]), H=np.int32(c["H"]), spp=np.int32(c["spp"]))
@@ -294,7 +309,7 @@ def generate(name):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + ["logistic", "c1pixels", "c2pixels"])
+    names = sys.argv[1:] or (list(CASES_ALL) + ["logistic", "c1pixels", "c2pixels"])
     for name in names:
         if name == "c1pixels":
             np.savez_compressed(os.path.join(HERE, "spirv_c1pixels.npz"), **generate_c1())
