@@ -25,7 +25,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -218,7 +217,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from raytracergpu_mastersproject_b200 import Buffer, Device, capi
+    from raytracergpu_mastersproject_b200 import Device, capi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -12,8 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import (BVH_NODE, CONSTRUCTION_INFO, ENCLOSING_BOX, MATERIAL, MODEL, MORTON_PRIMITIVE, SPHERE, TRIANGLE, UBO,
-                   TraceArgs, check)
+from .capi import UBO, TraceArgs, check
 
 
 class Device:
