@@ -70,9 +70,13 @@ __device__ __forceinline__ void pin_sincos(float x, float& s, float& c) {
 struct __align__(32) f8 { float4 lo, hi; };
 __device__ __forceinline__ f8 ldg256(const void* p) {
     f8 r;
+#ifdef RTB_SIMT_EMU   // tests/emu: the kernel sources compiled for the CPU (SIMT emulation, test infrastructure) -- no PTX there
+    r.lo = ((const float4*)p)[0]; r.hi = ((const float4*)p)[1];
+#else
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
                  : "l"(p));
+#endif
     return r;
 }
 

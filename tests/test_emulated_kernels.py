@@ -1,0 +1,58 @@
+"""CPU tier: the CUDA kernel SOURCES, executed under SIMT emulation, against the oracle and the reference binaries' vectors.
+
+tests/emu/ compiles raytracergpu_mastersproject_b200/csrc/*.cu unmodified (only the `<<<...>>>` launch syntax is rewritten) with g++
+against an emulation of the CUDA runtime in which every thread is a fiber and the fibers of a block meet at the warp collectives
+(__ballot_sync, __shfl_sync, __match_any_sync, ...) and at __syncthreads -- so the kernels' warp-level control flow (phase
+votes, ballot-ranked queue appends, the one-ray-per-warp tail kernel, the radix sort's peer ranking) runs as written.  This test
+then runs a selection of the `-m gpu` parity tests THEMSELVES over that library (RTB_LIB points the harness at it) in a
+subprocess.  It is a check of the kernel code in the tier that has no GPU and a development aid; it is not a product path: the
+emulated library is built into a scratch directory outside the repository, only this test loads it, and the device it reports
+is called "SIMT-EMU".  The GPU tier runs the same tests (and all the others) on the real device.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+# (test file, -k expression): a few seconds each under emulation
+SELECTION = [
+    ("tests/test_gpu_parity.py", "test_s1_stage_by_stage"),
+    ("tests/test_gpu_parity.py", "test_frame_bit_exact and 1-seed1 and not stream and (wave or simple)"),
+    ("tests/test_gpu_parity.py", "test_frame_bit_exact and (seed5 or seed6) and wave-wide-nodes"),
+    ("tests/test_gpu_parity.py", "test_tail_handover_forced and 32-1"),
+    ("tests/test_gpu_parity.py", "test_nearest_first_equal_t_ties or test_tile_sharding_bit_identical or test_resolve_matches_oracle"),
+    ("tests/test_spirv_golden.py", "test_cuda_matches_reference_binaries and (two or three or dups or spheres)"),
+    ("tests/test_spirv_golden.py", "test_cuda_logistic_matches_reference_binary"),
+]
+
+
+@pytest.fixture(scope="module")
+def emulated_library():
+    sys.path.insert(0, os.path.join(HERE, "emu"))
+    import build_emu
+    return build_emu.build(os.path.join(tempfile.gettempdir(), "rtb200_emu"))
+
+
+def test_emulated_library_is_not_the_product(emulated_library):
+    pkg = os.path.join(ROOT, "raytracergpu_mastersproject_b200")
+    assert not os.path.abspath(emulated_library).startswith(os.path.abspath(ROOT) + os.sep), "the emulated build must stay outside the repository"
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h")) or f == "Makefile":
+                text = open(os.path.join(root, f), errors="ignore").read()
+                assert "librtb200_emu" not in text and "build_emu" not in text, f"{f} refers to the emulated build"
+
+
+@pytest.mark.parametrize("path,expr", SELECTION, ids=[s[1][:40].replace(" ", "_") for s in SELECTION])
+def test_gpu_parity_tests_pass_over_the_emulated_kernels(emulated_library, path, expr):
+    env = dict(os.environ, RTB_LIB=emulated_library)
+    r = subprocess.run([sys.executable, "-m", "pytest", path, "-x", "-q", "-m", "gpu", "-k", expr, "-p", "no:cacheprovider"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    tail = (r.stdout + r.stderr)[-1500:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "SIMT-EMU" not in r.stderr, tail
