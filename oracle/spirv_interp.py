@@ -156,6 +156,7 @@ class Module:
         self.glsl_ext = None
         self.sincos = sincos or (lambda x: (f32(_libm.sinf(x)), f32(_libm.cosf(x))))
         self.n_executed = 0
+        self.calls = {}                 # function id -> number of OpFunctionCall executions (work counters of the reference binary)
         cur_fn, cur_block = None, None
         i = 5
         while i < len(w):
@@ -314,6 +315,10 @@ class Module:
                 self.write(mt, val[m], buf, off + d[DEC_OFFSET][0], d.get(DEC_MATRIX_STRIDE, [None])[0])
         else:
             raise ValueError("write of " + k)
+
+    def call_count(self, name):
+        """executions of OpFunctionCall whose callee's debug name starts with `name(`"""
+        return sum(n for fid, n in self.calls.items() if self.names.get(fid, "").startswith(name + "("))
 
     def bindings(self):
         """{binding: (variable id, pointee type id, storage class, name)} of the module's descriptor-backed variables"""
@@ -537,6 +542,7 @@ class Module:
                 elif op == 254:                                 # OpReturnValue
                     return v[ins[1]]
                 elif op == 57:                                  # OpFunctionCall
+                    self.calls[ins[3]] = self.calls.get(ins[3], 0) + 1
                     v[ins[2]] = yield from self.call(ins[3], [v[x] for x in ins[4:]], v)
                 elif op == 224:                                 # OpControlBarrier
                     yield ("barrier",)

@@ -156,7 +156,11 @@ def run_trace(shader, ubo, W, H, spp, tris_w, sphs_w, mats, nodes):
         # threads outside the image return before touching memory (raytraceBVH.comp:346-347): skipped, not interpreted
         m.dispatch((W // 32 + 1, H // 32 + 1, 1), res, only=lambda g: g[0] < W and g[1] < H)
         per_dispatch.append(np.array(im.px, np.float32))
-    return np.stack(per_dispatch), m.n_executed
+    # the reference binary's own work counts (OpFunctionCall executions): rays = hitBVH / sceneHit calls, node visits = AABBhitCheck
+    # calls, triangle / sphere tests, material reads = emitted() calls -- the quantities bench.py's roofline bytes are built from
+    counts = np.array([m.call_count("sceneHit"), m.call_count("AABBhitCheck"), m.call_count("triangleHit"), m.call_count("sphereHit"),
+                       m.call_count("emitted")], np.uint64)
+    return np.stack(per_dispatch), m.n_executed, counts
 
 
 def run_resolve(image, rays_per_pixel):
@@ -296,10 +300,10 @@ def generate(name):
     out.update(b)
     n_ins = 0
     if "bvh" in c["programs"]:
-        out["images_bvh"], k = run_trace("raytraceBVH.comp", ubo, c["W"], c["H"], c["spp"], b["tris_w"], b["sphs_w"], sc["materials"], b["nodes"])
+        out["images_bvh"], k, out["counts_bvh"] = run_trace("raytraceBVH.comp", ubo, c["W"], c["H"], c["spp"], b["tris_w"], b["sphs_w"], sc["materials"], b["nodes"])
         n_ins += k
     if "linear" in c["programs"]:
-        out["images_linear"], k = run_trace("raytrace.comp", ubo, c["W"], c["H"], c["spp"], b["tris_w"], b["sphs_w"], sc["materials"], None)
+        out["images_linear"], k, out["counts_linear"] = run_trace("raytrace.comp", ubo, c["W"], c["H"], c["spp"], b["tris_w"], b["sphs_w"], sc["materials"], None)
         n_ins += k
     if "resolve" in c["programs"]:
         out["resolved"] = run_resolve(out["images_bvh"][-1], c["spp"])

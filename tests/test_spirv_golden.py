@@ -83,6 +83,23 @@ def test_oracle_trace_matches_reference_binaries(name):
         assert np.array_equal(O.resolve_rgba8(g["images_bvh"][-1], spp), want), "fragment resolve"
 
 
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_oracle_work_counters_match_reference_binaries(name):
+    """The quantities bench.py's roofline bytes are built from (rays, node visits V, triangle / sphere tests Tt / St,
+    material reads H) are the reference binary's own: counted as executions of sceneHit / AABBhitCheck / triangleHit / sphereHit /
+    emitted in the interpreted raytraceBVH.comp.spv (raytrace.comp.spv for the non-BVH program, which has no box tests)."""
+    g = _load(name)
+    W, H, spp = int(g["W"]), int(g["H"]), int(g["spp"])
+    c = O.raytrace(g["ubo"], W, H, g["tris_w"], g["sphs_w"], g["materials"], g["nodes"], spp, want_hits=False, want_rng=False)["counters"]
+    assert [c["rays"], c["nodeVisits"], c["triTests"], c["sphTests"], c["matReads"]] == g["counts_bvh"].tolist()
+    assert c["samples"] == W * H * spp
+    if "counts_linear" in g.files:
+        c = O.raytrace(g["ubo"], W, H, g["tris_w"], g["sphs_w"], g["materials"], None, spp, opt=O.make_options(linear_scan=True),
+                       want_hits=False, want_rng=False)["counters"]
+        want = g["counts_linear"].tolist()
+        assert [c["rays"], c["triTests"], c["sphTests"], c["matReads"]] == [want[0], want[2], want[3], want[4]] and want[1] == 0
+
+
 def test_golden_traces_are_not_trivial():
     """the fixtures exercise what they claim: hits, misses, multi-bounce paths, both primitive types, every material type"""
     g = _load("room")
@@ -198,6 +215,12 @@ def test_cuda_matches_reference_binaries(device, name):
     for fl in variants:
         rt.clear_image(); rt.raytrace(g["ubo"], spp, flags=fl); device.wait_idle()
         assert np.array_equal(rt.read_image().view(np.uint32), g["images_bvh"][-1].view(np.uint32)), f"flags {fl}"
+    # the instrumented launch counts the reference binary's work (roofline bytes)
+    rt.clear_image(); rt.counters.zero()
+    rt.raytrace(g["ubo"], spp, flags=capi.TRACE_COUNT); device.wait_idle()
+    c = rt.read_counters()
+    assert [c["rays"], c["nodeVisits"], c["triTests"], c["sphTests"], c["matReads"]] == g["counts_bvh"].tolist(), "work counters"
+    assert np.array_equal(rt.read_image().view(np.uint32), g["images_bvh"][-1].view(np.uint32))
     if "resolved" in g.files:
         want = np.floor(np.clip(g["resolved"], 0.0, 1.0).astype(np.float32) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
         assert np.array_equal(rt.resolve_rgba8(spp), want)
