@@ -19,8 +19,7 @@ from oracle import oracle as O
 HERE = os.path.dirname(os.path.abspath(__file__))
 ALL_CASES = sorted(os.path.basename(p)[len("spirv_"):-len(".npz")] for p in glob.glob(os.path.join(HERE, "golden", "spirv_*.npz"))
                    if not p.endswith(("spirv_logistic.npz", "spirv_c1pixels.npz", "spirv_c2pixels.npz")))
-# the edge_* fixtures pin the oracle on corners of the parameter space (N = 1, depth 0 / 1, wrapped seed, ...); the CUDA path is
-# checked against the oracle on the same corners in tests/test_gpu_parity.py, so the GPU tests below use the main fixtures only
+# the edge_* fixtures cover corners of the parameter space (N = 1, depth 0 / 1, wrapped seed, ...)
 CASES = [c for c in ALL_CASES if not c.startswith("edge_")]
 
 
@@ -187,7 +186,7 @@ def test_oracle_logistic_matches_reference_binary():
 
 # ------------------------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_cuda_matches_reference_binaries(device, name):
     from raytracergpu_mastersproject_b200 import Raytracer, capi
     g = _load(name)
