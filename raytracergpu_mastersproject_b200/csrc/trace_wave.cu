@@ -456,6 +456,9 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
                     best = mn;
                 }
                 __syncwarp();
+#ifdef RTB_TAIL_TEST_FALLBACK   // test builds only (tests/test_emulated_kernels.py): every third ray takes the exact fallback below
+                if ((item + depth) % 3u == 0u) fit = false;
+#endif
                 if (!fit || __any_sync(FULL, poison)) {
                     needExact = true;
                 } else {

@@ -90,7 +90,7 @@ int launch_trace_stream(cudaStream_t, TraceParams, bool, bool, int, uint32_t) { 
 '''
 
 
-def build(out_dir=None):
+def build(out_dir=None, defines=()):
     out_dir = out_dir or os.path.join(tempfile.gettempdir(), "rtb200_emu")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "librtb200_emu.so")
@@ -98,7 +98,7 @@ def build(out_dir=None):
     if os.path.exists(so) and all(os.path.getmtime(s) <= os.path.getmtime(so) for s in srcs):
         return so
     flags = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-frounding-math", "-fno-strict-aliasing", "-w", "-Wno-psabi",
-             "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include")]
+             "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include")] + ["-D" + d for d in defines]
     objs, procs = [], []
     for u in UNITS:
         cpp = os.path.join(out_dir, u.replace(".cu", "_emu.cpp"))

@@ -48,6 +48,18 @@ def test_emulated_library_is_not_the_product(emulated_library):
                 assert "librtb200_emu" not in text and "build_emu" not in text, f"{f} refers to the emulated build"
 
 
+def test_tail_kernel_exact_fallback_over_the_emulated_kernels():
+    """trace_tail_kernel sends a ray to hit_bvh() -- the reference's own walk on the exact records -- when its pending set
+    overflows or a NaN hit turns up; neither happens on ordinary scenes.  A test build (-DRTB_TAIL_TEST_FALLBACK) forces every
+    third ray down that path; with the hand-over thresholds forced low as well, the frames must still be the oracle's."""
+    sys.path.insert(0, os.path.join(HERE, "emu"))
+    import build_emu
+    lib = build_emu.build(os.path.join(tempfile.gettempdir(), "rtb200_emu_fallback"), defines=("RTB_TAIL_TEST_FALLBACK",))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-x", "-q", "-m", "gpu", "-k", "test_tail_handover_forced and 8-3",
+                        "-p", "no:cacheprovider"], cwd=ROOT, env=dict(os.environ, RTB_LIB=lib), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and " passed" in r.stdout, (r.stdout + r.stderr)[-1500:]
+
+
 @pytest.mark.parametrize("path,expr", SELECTION, ids=[s[1][:40].replace(" ", "_") for s in SELECTION])
 def test_gpu_parity_tests_pass_over_the_emulated_kernels(emulated_library, path, expr):
     env = dict(os.environ, RTB_LIB=emulated_library)
