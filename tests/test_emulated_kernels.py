@@ -10,11 +10,14 @@ emulated library is built into a scratch directory outside the repository, only 
 is called "SIMT-EMU".  The GPU tier runs the same tests (and all the others) on the real device.
 """
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
 
 import pytest
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="the emulated build needs g++")
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
