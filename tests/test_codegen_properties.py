@@ -1,0 +1,72 @@
+"""CPU tier: properties of the sm_100a code the product build produced (cuobjdump on librtb200.so; nothing is executed).
+
+The trace kernels' performance rests on a few code-generation facts that a source change can silently lose -- 7 resident CTAs per
+SM need <= 72 registers and <= ~32 KB of static shared memory per CTA, the hot traverse step must not spill, and the node /
+leaf / triangle records must be fetched with 256-bit loads.  DESIGN.md section 4 quotes these numbers from ncu; this test pins them in
+the tier that has no GPU."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "raytracergpu_mastersproject_b200", "librtb200.so")
+MAIN = "_ZN3rtb17trace_wave_kernelILb0ELb0ELb0ELi3EEEvNS_11TraceParamsE"          # nearest-first 4-ary walk, production variant
+MAIN_SORTED = "_ZN3rtb17trace_wave_kernelILb0ELb0ELb0ELi4EEEvNS_11TraceParamsE"   # same, farthest-first stacking (sphere scenes)
+TAIL = "_ZN3rtb17trace_tail_kernelILb0EEEvNS_11TraceParamsE"
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="needs the CUDA toolkit's cuobjdump")
+
+
+@pytest.fixture(scope="module")
+def usage():
+    from raytracergpu_mastersproject_b200 import capi
+    capi.build()
+    out = subprocess.run(["cuobjdump", "-res-usage", SO], capture_output=True, text=True, check=True).stdout
+    res, name = {}, None
+    for line in out.splitlines():
+        m = re.match(r"\s*Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        elif name and "REG:" in line:
+            res[name] = {k: int(v) for k, v in re.findall(r"(REG|STACK|SHARED|LOCAL):(\d+)", line)}
+            name = None
+    return res
+
+
+def test_built_for_sm_100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", SO], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_trace_kernels_fit_seven_ctas_per_sm(usage):
+    for k in (MAIN, MAIN_SORTED):
+        u = usage[k]
+        assert u["REG"] <= 72, (k, u)                         # 65536 / (72 * 128) = 7.1 CTAs of 128 threads
+        assert u["SHARED"] <= 31 * 1024, (k, u)               # 7 * (SHARED + 1 KB reserved) <= 227 KB
+    assert usage[TAIL]["REG"] <= 80 and usage[TAIL]["SHARED"] <= 16 * 1024, usage[TAIL]      # 6 CTAs per SM
+
+
+def _sass(kernel):
+    return subprocess.run(["cuobjdump", "-sass", "-fun", kernel, SO], capture_output=True, text=True, check=True).stdout
+
+
+def test_hot_loop_has_wide_loads_and_no_spills():
+    sass = _sass(MAIN)
+    ins = [l for l in sass.splitlines() if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l)]
+    assert len(ins) > 1000
+    wide = [l for l in ins if re.search(r"LDG\.E\.(ENL2\.)?256", l)]
+    assert len(wide) >= 8, "the 64-byte records must be fetched with 256-bit loads (2 per record)"
+    # register spills would show as local-memory traffic at fixed frame offsets; the only local memory allowed is the stack
+    # spill area of the traversal stack (indexed, deeper than 32 levels): it is addressed through a register, never [R1+imm]
+    spills = [l for l in ins if re.search(r"\b(STL|LDL)(\.\w+)*\s", l) and re.search(r"\[R1(\+0x[0-9a-f]+)?\]", l)]
+    assert not spills, spills[:5]
+    assert re.search(r"I2F(P)?\.", sass), "byte planes are decoded with integer-to-float conversions"
+
+
+def test_tail_kernel_uses_warp_collectives():
+    sass = _sass(TAIL)
+    assert "VOTE" in sass and "SHFL" in sass and re.search(r"LDG\.E\.(ENL2\.)?256", sass)
