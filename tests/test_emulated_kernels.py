@@ -31,6 +31,8 @@ SELECTION = [
     ("tests/test_gpu_parity.py", "test_nearest_first_equal_t_ties or test_tile_sharding_bit_identical or test_resolve_matches_oracle"),
     ("tests/test_spirv_golden.py", "test_cuda_matches_reference_binaries and (two or three or dups or spheres or edge)"),
     ("tests/test_spirv_golden.py", "test_cuda_logistic_matches_reference_binary"),
+    # the C++20 host binary (reference main.cpp shape) over the emulated library: its PPM frame == the oracle's resolved frame
+    ("tests/test_gpu_host_main.py", "complexScene or non_bvh or reports_errors"),
 ]
 
 
@@ -65,7 +67,14 @@ def test_tail_kernel_exact_fallback_over_the_emulated_kernels():
 
 @pytest.mark.parametrize("path,expr", SELECTION, ids=[s[1][:40].replace(" ", "_") for s in SELECTION])
 def test_gpu_parity_tests_pass_over_the_emulated_kernels(emulated_library, path, expr):
-    env = dict(os.environ, RTB_LIB=emulated_library)
+    # rtb200_main / librtb200_host.so name librtb200.so in their NEEDED entries: a directory with that name pointing at the emulated
+    # build, searched before their RUNPATH, binds them to it for this subprocess only
+    ld = os.path.join(os.path.dirname(emulated_library), "ld")
+    os.makedirs(ld, exist_ok=True)
+    link = os.path.join(ld, "librtb200.so")
+    if not os.path.islink(link):
+        os.symlink(emulated_library, link)
+    env = dict(os.environ, RTB_LIB=emulated_library, LD_LIBRARY_PATH=ld + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([sys.executable, "-m", "pytest", path, "-x", "-q", "-m", "gpu", "-k", expr, "-p", "no:cacheprovider"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-1500:]
