@@ -97,7 +97,7 @@ def build(out_dir=None, defines=()):
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in os.listdir(HERE)] + [os.path.join(ROOT, "include", "rtb200.h")]
     if os.path.exists(so) and all(os.path.getmtime(s) <= os.path.getmtime(so) for s in srcs):
         return so
-    flags = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-frounding-math", "-fno-strict-aliasing", "-w", "-Wno-psabi",
+    flags = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-frounding-math", "-fno-strict-aliasing", "-w", "-Wno-psabi", "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0",
              "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include")] + ["-D" + d for d in defines]
     objs, procs = [], []
     for u in UNITS:

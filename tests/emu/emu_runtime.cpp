@@ -1,5 +1,6 @@
 // tests/emu/emu_runtime.cpp -- the fiber scheduler behind tests/emu/cuda_runtime.h (SIMT emulation, TEST INFRASTRUCTURE ONLY).
 #include <cuda_runtime.h>
+#include <setjmp.h>
 #include <sys/mman.h>
 #include <time.h>
 #include <ucontext.h>
@@ -19,11 +20,16 @@ constexpr size_t STACK_BYTES = 512 << 10;
 struct Fiber {
     ucontext_t ctx;
     char* stack = nullptr;
-    bool done = false;
+    bool done = false, started = false;
+    jmp_buf jb;                             // switches after the first entry use _setjmp / _longjmp: no signal-mask system call
+    int waitKind = 0;                       // 0 runnable | 1 waits for its warp's collective | 2 waits at the block barrier
+    unsigned waitGen = 0;
     ThreadInfo info;
 };
 struct Warp {
     unsigned arrived = 0, exited = 0, gen = 0;
+    unsigned pendingMask = 0;               // the collective the arrived lanes wait for (completed by the last arrival or by an exit)
+    CollectiveFn pendingFn = nullptr;
     unsigned long long vals[32], out[32];
     unsigned aux[32];
 };
@@ -36,10 +42,11 @@ struct Block {
 Block* g_block = nullptr;
 Fiber* g_cur = nullptr;
 ucontext_t g_sched;
+jmp_buf g_schedJb;
 const std::function<void()>* g_body = nullptr;
 ThreadInfo g_hostInfo;
 
-void yield() { swapcontext(&g_cur->ctx, &g_sched); }
+void yield() { if (!_setjmp(g_cur->jb)) _longjmp(g_schedJb, 1); }
 
 void release_barrier_if_complete(Block& b) {
     if (b.syncArrived > 0 && b.syncArrived >= b.live) { b.syncArrived = 0; b.syncGen++; b.events++; }
@@ -59,9 +66,11 @@ void fiber_main() {
     f.done = true;
     b.live--;
     b.events++;
-    b.warps[f.info.warp].exited |= 1u << f.info.lane;       // an exited lane never blocks the others (as on the hardware)
+    Warp& w = b.warps[f.info.warp];
+    w.exited |= 1u << f.info.lane;                           // an exited lane never blocks the others (as on the hardware)
+    if (w.arrived && w.pendingFn) complete_if_ready(w, w.pendingMask, w.pendingFn);
     release_barrier_if_complete(b);
-    swapcontext(&f.ctx, &g_sched);
+    _longjmp(g_schedJb, 1);
 }
 }  // namespace
 
@@ -77,14 +86,17 @@ unsigned long long collective(unsigned mask, unsigned long long mine, unsigned a
         return out(lane, v, a, bit);
     }
     w.vals[lane] = mine; w.aux[lane] = aux; w.arrived |= bit;
+    w.pendingMask = mask; w.pendingFn = out;
     g_block->events++;
     const unsigned gen = w.gen;
-    // the last lane to arrive evaluates the collective for everybody; lanes that left the kernel count as arrived
+    // the last lane to arrive evaluates the collective for everybody; lanes that left the kernel count as arrived (an exit
+    // re-evaluates the pending collective, see fiber_main), so a waiting lane is simply skipped by the scheduler until gen moves
     complete_if_ready(w, mask, out);
     while (w.gen == gen) {
+        f.waitKind = 1; f.waitGen = gen;
         yield();
-        if (w.gen == gen) complete_if_ready(w, mask, out);   // a lane of the mask may have exited meanwhile
     }
+    f.waitKind = 0;
     return w.out[lane];
 }
 
@@ -94,7 +106,11 @@ void syncthreads() {
     b.syncArrived++;
     b.events++;
     release_barrier_if_complete(b);
-    while (b.syncGen == gen) yield();
+    while (b.syncGen == gen) {
+        g_cur->waitKind = 2; g_cur->waitGen = gen;
+        yield();
+    }
+    g_cur->waitKind = 0;
 }
 
 void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
@@ -113,12 +129,12 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
     g_body = &body;
     for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
         b.live = nThreads; b.syncArrived = 0; b.events = 0;
-        for (auto& w : b.warps) { w.arrived = 0; w.exited = 0; }
+        for (auto& w : b.warps) { w.arrived = 0; w.exited = 0; w.pendingMask = 0; w.pendingFn = nullptr; }
         // lanes beyond the block size do not exist: they count as exited
         if (nThreads % 32) b.warps.back().exited = ~0u << (nThreads % 32);
         for (unsigned t = 0; t < nThreads; t++) {
             Fiber& f = b.fibers[t];
-            f.done = false;
+            f.done = false; f.started = false; f.waitKind = 0;
             f.info.tIdx = uint3{ t % block.x, (t / block.x) % block.y, t / (block.x * block.y) };
             f.info.bIdx = uint3{ bx, by, bz };
             f.info.bDim = block; f.info.gDim = grid;
@@ -133,8 +149,14 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
             for (unsigned t = 0; t < nThreads; t++) {
                 Fiber& f = b.fibers[t];
                 if (f.done) continue;
+                if (f.waitKind == 1 && b.warps[f.info.warp].gen == f.waitGen) continue;      // still waiting: no context switch
+                if (f.waitKind == 2 && b.syncGen == f.waitGen) continue;
                 g_cur = &f;
-                swapcontext(&g_sched, &f.ctx);
+                if (!_setjmp(g_schedJb)) {
+                    if (f.started) _longjmp(f.jb, 1);
+                    f.started = true;
+                    swapcontext(&g_sched, &f.ctx);               // first entry: onto the fiber's own stack
+                }
             }
             g_cur = nullptr;
             if (b.live > 0 && b.events == before) {

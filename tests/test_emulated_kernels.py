@@ -22,15 +22,13 @@ pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="the emulate
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
-# (test file, -k expression): a few seconds each under emulation
+# (test files, -k expression): nearly the whole `-m gpu` suite; left out are the streaming A/B kernel (needs a grid-wide barrier), the
+# tests at sizes the emulation is too slow for (full-size configs, multi-pass, mid-size meshes, 5-sample frames of every seed,
+# the 800x800 / 1920x1080 pixel-sampled fixtures) and one test that loops over the streaming kernel internally
 SELECTION = [
-    ("tests/test_gpu_parity.py", "test_s1_stage_by_stage"),
-    ("tests/test_gpu_parity.py", "test_frame_bit_exact and 1-seed1 and not stream and (wave or simple)"),
-    ("tests/test_gpu_parity.py", "test_frame_bit_exact and (seed5 or seed6) and wave-wide-nodes"),
-    ("tests/test_gpu_parity.py", "test_tail_handover_forced and 32-0"),
-    ("tests/test_gpu_parity.py", "test_nearest_first_equal_t_ties or test_tile_sharding_bit_identical or test_resolve_matches_oracle"),
-    ("tests/test_spirv_golden.py", "test_cuda_matches_reference_binaries and (two or three or dups or spheres or edge)"),
-    ("tests/test_spirv_golden.py", "test_cuda_logistic_matches_reference_binary"),
+    ("tests/test_gpu_parity.py", "not stream and not multi_pass and not mid_size and not degenerate_and_extreme and not (test_frame_bit_exact and 5-seed)"),
+    ("tests/test_spirv_golden.py tests/test_golden.py tests/test_gpu_logistic.py",
+     "test_cuda_matches_reference_binaries or test_cuda_logistic or test_logistic_steps or (test_cuda_reproduces_golden and not complexScene)"),
     # the C++20 host binary (reference main.cpp shape) over the emulated library: its PPM frame == the oracle's resolved frame
     ("tests/test_gpu_host_main.py", "complexScene or non_bvh or reports_errors"),
 ]
@@ -65,7 +63,7 @@ def test_tail_kernel_exact_fallback_over_the_emulated_kernels():
     assert r.returncode == 0 and " passed" in r.stdout, (r.stdout + r.stderr)[-1500:]
 
 
-@pytest.mark.parametrize("path,expr", SELECTION, ids=[s[1][:40].replace(" ", "_") for s in SELECTION])
+@pytest.mark.parametrize("path,expr", SELECTION, ids=["parity", "fixtures", "cpp_host"])
 def test_gpu_parity_tests_pass_over_the_emulated_kernels(emulated_library, path, expr):
     # rtb200_main / librtb200_host.so name librtb200.so in their NEEDED entries: a directory with that name pointing at the emulated
     # build, searched before their RUNPATH, binds them to it for this subprocess only
@@ -75,7 +73,7 @@ def test_gpu_parity_tests_pass_over_the_emulated_kernels(emulated_library, path,
     if not os.path.islink(link):
         os.symlink(emulated_library, link)
     env = dict(os.environ, RTB_LIB=emulated_library, LD_LIBRARY_PATH=ld + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
-    r = subprocess.run([sys.executable, "-m", "pytest", path, "-x", "-q", "-m", "gpu", "-k", expr, "-p", "no:cacheprovider"],
+    r = subprocess.run([sys.executable, "-m", "pytest", *path.split(), "-x", "-q", "-m", "gpu", "-k", expr, "-p", "no:cacheprovider"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-1500:]
     assert r.returncode == 0, tail
