@@ -1,7 +1,7 @@
 """Builds the SIMT-emulated library (TEST INFRASTRUCTURE ONLY, see tests/emu/cuda_runtime.h): the kernel sources of
 raytracergpu_mastersproject_b200/csrc/*.cu, unmodified except for the `kernel<<<grid, block, smem, stream>>>(args)` launch syntax
 (rewritten to emu::launch), compiled with g++ against the emulation header.  Output: <out_dir>/librtb200_emu.so with the C-ABI of
-include/rtb200.h.  The streaming A/B kernel (cooperative-groups grid barrier) is not emulated.
+include/rtb200.h.  The emulated device has one multiprocessor, so the streaming A/B kernel's cooperative launch is a single block.
 
     python tests/emu/build_emu.py [out_dir]        (default: $TMPDIR/rtb200_emu -- outside the repository on purpose)
 """
@@ -14,7 +14,7 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "raytracergpu_mastersproject_b200", "csrc")
-UNITS = ["capi.cu", "bvh_build.cu", "radix_sort.cu", "trace.cu", "trace_wave.cu"]
+UNITS = ["capi.cu", "bvh_build.cu", "radix_sort.cu", "trace.cu", "trace_wave.cu", "trace_stream.cu"]
 
 
 def _match_back(s, end):
@@ -52,7 +52,12 @@ def _split_top(s):
     return out
 
 
+COOP = re.compile(r"cudaLaunchCooperativeKernel\(\(const void\*\)(.+?), (dim3\(.+?\)), (dim3\(.+?\)), args, 0, st\);")
+
+
 def rewrite_launches(src):
+    # the cooperative launch of the streaming kernel (its single argument is the TraceParams `p` the args array points at)
+    src = COOP.sub(lambda m: f"emu::launch({m.group(2)}, {m.group(3)}, [=]() {{ ({m.group(1)})(p); }});", src)
     out, pos = "", 0
     while True:
         a = src.find("<<<", pos)
@@ -80,14 +85,6 @@ def rewrite_launches(src):
         pos = e + 1
 
 
-STUBS = r'''
-#include <cuda_runtime.h>
-#include "common.cuh"
-#include "kernels.h"
-namespace rtb {   // the streaming A/B kernel needs a grid-wide barrier (cooperative groups): not emulated
-int launch_trace_stream(cudaStream_t, TraceParams, bool, bool, int, uint32_t) { fprintf(stderr, "emu: RTB_TRACE_STREAM_KERNEL is not emulated (nothing rendered)\n"); return 0; }
-}
-'''
 
 
 def build(out_dir=None, defines=()):
@@ -106,9 +103,7 @@ def build(out_dir=None, defines=()):
         open(cpp, "w").write('#include <cuda_runtime.h>\n#line 1 "%s"\n' % os.path.join(CSRC, u) + rewrite_launches(text))
         objs.append(cpp.replace(".cpp", ".o"))
         procs.append(subprocess.Popen(flags + ["-c", cpp, "-o", objs[-1]]))
-    stub = os.path.join(out_dir, "stubs_emu.cpp")
-    open(stub, "w").write(STUBS)
-    for src in (stub, os.path.join(HERE, "emu_runtime.cpp")):
+    for src in (os.path.join(HERE, "emu_runtime.cpp"),):
         objs.append(os.path.join(out_dir, os.path.basename(src).replace(".cpp", ".o")))
         procs.append(subprocess.Popen(flags + ["-c", src, "-o", objs[-1]]))
     for p in procs:

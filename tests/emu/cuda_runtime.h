@@ -5,7 +5,7 @@
 // to emu::launch by the build script).  Every CUDA thread becomes a fiber (ucontext); the fibers of one thread block run
 // interleaved on one OS thread and meet at the warp collectives (__ballot_sync, __shfl_sync, ...) and at __syncthreads, so
 // the kernels' warp-level control flow -- the thing a plain host port would not exercise -- is executed as written.
-// Thread blocks run one after the other.  The result is a library with the C-ABI of librtb200.so that executes the same
+// Thread blocks run one after the other (the emulated device has one multiprocessor, so a cooperative launch is one block).  The result is a library with the C-ABI of librtb200.so that executes the same
 // kernel code on the CPU, used ONLY by tests/test_emulated_kernels.py (the CPU tier's check of the kernel sources against
 // the oracle) and as a development aid when no GPU is at hand.  It is built into a scratch directory, is never loaded by the
 // product (raytracergpu_mastersproject_b200/capi.py loads librtb200.so, which has no CPU path), never travels to the GPU box,
@@ -67,7 +67,7 @@ static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     memset(p, 0, sizeof(*p));
     snprintf(p->name, sizeof(p->name), "SIMT-EMU (CPU emulation of the sm_100a kernels, test infrastructure)");
-    p->major = 10; p->minor = 0; p->multiProcessorCount = 2;
+    p->major = 10; p->minor = 0; p->multiProcessorCount = 1;      // one SM: a cooperative launch is one block (cooperative_groups.h)
     return cudaSuccess;
 }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }

@@ -22,11 +22,10 @@ pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="the emulate
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
-# (test files, -k expression): nearly the whole `-m gpu` suite; left out are the streaming A/B kernel (needs a grid-wide barrier), the
-# tests at sizes the emulation is too slow for (full-size configs, multi-pass, mid-size meshes, 5-sample frames of every seed,
-# the 800x800 / 1920x1080 pixel-sampled fixtures) and one test that loops over the streaming kernel internally
+# (test files, -k expression): nearly the whole `-m gpu` suite; left out are only the tests at sizes the emulation is too slow for
+# (full-size configs, multi-pass, mid-size meshes, 5-sample frames of every seed, the 800x800 / 1920x1080 pixel-sampled fixtures)
 SELECTION = [
-    ("tests/test_gpu_parity.py", "not stream and not multi_pass and not mid_size and not degenerate_and_extreme and not (test_frame_bit_exact and 5-seed)"),
+    ("tests/test_gpu_parity.py", "not multi_pass and not mid_size and not (test_frame_bit_exact and 5-seed)"),
     ("tests/test_spirv_golden.py tests/test_golden.py tests/test_gpu_logistic.py",
      "test_cuda_matches_reference_binaries or test_cuda_logistic or test_logistic_steps or (test_cuda_reproduces_golden and not complexScene)"),
     # the C++20 host binary (reference main.cpp shape) over the emulated library: its PPM frame == the oracle's resolved frame

@@ -209,8 +209,6 @@ def test_cuda_matches_reference_binaries(device, name):
     # fused submission, every traversal variant
     variants = [0, capi.TRACE_WIDE_NODES, capi.TRACE_WIDE_NODES | capi.TRACE_REFERENCE_ORDER, capi.TRACE_EXACT_NODES,
                 capi.TRACE_COMPRESSED_NODES, capi.TRACE_SIMPLE_KERNEL, capi.TRACE_STREAM_KERNEL, capi.TRACE_NO_PRIMARY_SHARING]
-    if "SIMT-EMU" in device.name():      # tests/test_emulated_kernels.py: the streaming A/B kernel (grid-wide barrier) is not emulated
-        variants.remove(capi.TRACE_STREAM_KERNEL)
     for fl in variants:
         rt.clear_image(); rt.raytrace(g["ubo"], spp, flags=fl); device.wait_idle()
         assert np.array_equal(rt.read_image().view(np.uint32), g["images_bvh"][-1].view(np.uint32)), f"flags {fl}"
