@@ -8,6 +8,7 @@ bench.py can drive the identical C-ABI entry points from Python.  No compute hap
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -23,6 +24,11 @@ class Device:
         self._lib = capi.lib()
         check(self._lib.rtb_ctx_create(index, C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.index = index
+        # RTB_LIB can point this harness at another build of the library (A/B builds).  The test suite's SIMT-emulated build of
+        # the kernel sources (tests/emu, CPU tier only) identifies itself by its device name; it is refused anywhere else.
+        if self.name().startswith("SIMT-EMU") and os.environ.get("RTB_TEST_EMULATION") != "1":
+            self.close()
+            raise capi.RtbError("an emulated (CPU) build of librtb200 was loaded outside tests/test_emulated_kernels.py: the product has no CPU path")
 
     @property
     def handle(self):

@@ -58,8 +58,15 @@ def test_tail_kernel_exact_fallback_over_the_emulated_kernels():
     import build_emu
     lib = build_emu.build(os.path.join(tempfile.gettempdir(), "rtb200_emu_fallback"), defines=("RTB_TAIL_TEST_FALLBACK",))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-x", "-q", "-m", "gpu", "-k", "test_tail_handover_forced and 8-3",
-                        "-p", "no:cacheprovider"], cwd=ROOT, env=dict(os.environ, RTB_LIB=lib), capture_output=True, text=True, timeout=900)
+                        "-p", "no:cacheprovider"], cwd=ROOT, env=dict(os.environ, RTB_LIB=lib, RTB_TEST_EMULATION="1"), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and " passed" in r.stdout, (r.stdout + r.stderr)[-1500:]
+
+
+def test_emulated_library_is_refused_outside_this_test(emulated_library):
+    code = "from raytracergpu_mastersproject_b200 import Device; Device(0)"
+    env = {k: v for k, v in os.environ.items() if k != "RTB_TEST_EMULATION"}
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(env, RTB_LIB=emulated_library), capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CPU path" in r.stderr
 
 
 @pytest.mark.parametrize("path,expr", SELECTION, ids=["parity", "fixtures", "cpp_host"])
@@ -71,7 +78,7 @@ def test_gpu_parity_tests_pass_over_the_emulated_kernels(emulated_library, path,
     link = os.path.join(ld, "librtb200.so")
     if not os.path.islink(link):
         os.symlink(emulated_library, link)
-    env = dict(os.environ, RTB_LIB=emulated_library, LD_LIBRARY_PATH=ld + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    env = dict(os.environ, RTB_LIB=emulated_library, RTB_TEST_EMULATION="1", LD_LIBRARY_PATH=ld + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([sys.executable, "-m", "pytest", *path.split(), "-x", "-q", "-m", "gpu", "-k", expr, "-p", "no:cacheprovider"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-1500:]
