@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RTB_VERSION 100
+#define RTB_VERSION 200
 
 /* ---- record layouts ------------------------------------------------------------------------------- */
 typedef struct { float m[16]; } rtb_model;                         /* mat4 column-major, 64 B (definitions.glsl:6-8) */
@@ -83,6 +83,11 @@ enum {
      * before tMin) are dropped; equal-t ties are resolved as the reference's visiting order would.  This flag keeps the
      * reference's visiting order with no t-interval, like the shader. */
     RTB_TRACE_REFERENCE_ORDER = 1u << 11,
+    /* Instrumented variant of the PRODUCTION walk: the same kernels, records, visiting order, hand-over and primary-hit
+     * sharing as an un-flagged call (same results), additionally filling `walkCounters` with what those kernels really
+     * fetch -- the figures bench.py's roofline is computed from.  (RTB_TRACE_COUNT, by contrast, walks the exact records in
+     * the reference's order and counts the REFERENCE's work.) */
+    RTB_TRACE_WALK_COUNT = 1u << 12,
     RTB_TRACE_CULLED = 1u << 5          /* extension, default off: also skip subtrees outside the box of the ray segment
                                            [tMin, closest] (+ margin).  NOT the reference's traversal (it has no t-interval);
                                            fewer node visits, results empirically identical (see trace_wave.cu) */
@@ -92,6 +97,22 @@ enum {
  * whose box was tested (reference-equivalent count), triTests / sphTests = leaf primitive tests,
  * matReads = hits that read a material, samples = (pixel, sample) pairs. */
 typedef struct { uint64_t rays, nodeVisits, triTests, sphTests, matReads, samples; } rtb_counters;
+
+/* What the production trace kernels fetch (RTB_TRACE_WALK_COUNT), u64 each, accumulated into:
+ *   rays            rays actually walked (a pixel's shared primary ray counts once)
+ *   recordFetches   64-byte traversal records fetched (4-ary records; exact child pairs for small scenes / fallback rays)
+ *   leafBoxFetches  32-byte exact leaf boxes fetched (candidate re-check)
+ *   triTests        64-byte packed triangle records fetched and tested;  sphTests: 16-byte sphere + 4-byte material index
+ *   matReads        16-byte material records read by the shading step
+ *   items           (pixel, sample) work items pulled: 8 B pixel index / xy + 4 B seed (+ 48 B shared primary hit)
+ *   paths           finished paths: one 12-byte colour store into the sample slot
+ *   parked          paths / rays handed over to the tail kernel: 240 B written by the main launch and read back by the tail launch
+ *   laneSteps, warpSteps   traverse-phase turns per lane / per warp (their ratio = lanes active per T step)
+ *   tailRays        rays finished one-ray-per-warp by the tail kernel;  tailTurns: its warp turns */
+typedef struct {
+    uint64_t rays, recordFetches, leafBoxFetches, triTests, sphTests, matReads, items, paths, parked, laneSteps, warpSteps,
+             tailRays, tailTurns, _reserved[3];
+} rtb_walk_counters;
 
 /* What one S2 submission renders (the raysPerPixel dispatch loop of RaytracerBVH.cpp:1025-1050).
  * The image buffer is RGBA32F, `localRows` x imageWidth, row-major, local row j holding global image row
@@ -113,6 +134,7 @@ typedef struct {
     void* hitT;         /* optional device f32[localRows*W] */
     void* rngOut;       /* optional device u32[localRows*W]: rngState after the last rendered sample */
     void* counters;     /* device rtb_counters*, required with RTB_TRACE_COUNT (accumulated into) */
+    void* walkCounters; /* device rtb_walk_counters*, required with RTB_TRACE_WALK_COUNT (accumulated into) */
 } rtb_trace_args;
 
 typedef struct rtb_ctx rtb_ctx;

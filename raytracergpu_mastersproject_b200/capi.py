@@ -13,7 +13,8 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_SO = os.environ.get("RTB_LIB") or os.path.join(_PKG, "librtb200.so")   # RTB_LIB: A/B builds of the same library
+_DEFAULT_SO = os.path.join(_PKG, "librtb200.so")
+_SO = _DEFAULT_SO
 _HEADER = os.path.join(os.path.dirname(_PKG), "include", "rtb200.h")
 
 MODEL = np.dtype([("m", "<f4", (16,))])
@@ -38,15 +39,30 @@ TRACE_COUNT, TRACE_EXT_MATERIALS, TRACE_ENCLOSING_INF, TRACE_SIMPLE_KERNEL, TRAC
 TRACE_STREAM_KERNEL, TRACE_COMPRESSED_NODES, TRACE_WIDE_NODES, TRACE_EXACT_NODES = 64, 128, 256, 512
 TRACE_NO_PRIMARY_SHARING = 1024
 TRACE_REFERENCE_ORDER = 2048
+TRACE_WALK_COUNT = 4096
 
 COUNTER_FIELDS = ("rays", "nodeVisits", "triTests", "sphTests", "matReads", "samples")
+# rtb_walk_counters (16 x u64): what the production kernels fetch (RTB_TRACE_WALK_COUNT)
+WALK_COUNTER_FIELDS = ("rays", "recordFetches", "leafBoxFetches", "triTests", "sphTests", "matReads", "items", "paths", "parked",
+                       "laneSteps", "warpSteps", "tailRays", "tailTurns", "_r0", "_r1", "_r2")
+
+
+def walk_bytes(w: dict, primary_sharing: bool) -> dict:
+    """Bytes the production trace kernels fetch / store for the counted work (DESIGN.md "roofline"): every figure is the size
+    of the record the kernel loads, as laid out in HBM."""
+    loads = (64 * w["recordFetches"] + 32 * w["leafBoxFetches"] + 64 * w["triTests"] + 20 * w["sphTests"] + 16 * w["matReads"]
+             + (12 + (48 if primary_sharing else 0)) * w["items"] + 240 * w["parked"])
+    stores = 12 * w["paths"] + 240 * w["parked"]
+    return {"load_bytes": int(loads), "store_bytes": int(stores), "record_bytes": int(64 * w["recordFetches"]),
+            "leaf_box_bytes": int(32 * w["leafBoxFetches"]), "primitive_bytes": int(64 * w["triTests"] + 20 * w["sphTests"])}
 
 
 class TraceArgs(C.Structure):
     _fields_ = [("imageWidth", C.c_uint32), ("imageHeight", C.c_uint32), ("localRows", C.c_uint32),
                 ("bandRows", C.c_uint32), ("bandFirst", C.c_uint32), ("bandStep", C.c_uint32),
                 ("sampleSkip", C.c_uint32), ("sampleCount", C.c_uint32), ("flags", C.c_uint32), ("_pad", C.c_uint32),
-                ("hitPrim", C.c_void_p), ("hitT", C.c_void_p), ("rngOut", C.c_void_p), ("counters", C.c_void_p)]
+                ("hitPrim", C.c_void_p), ("hitT", C.c_void_p), ("rngOut", C.c_void_p), ("counters", C.c_void_p),
+                ("walkCounters", C.c_void_p)]
 
 
 EXPORTS = [
@@ -84,11 +100,13 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_SO):
+    if _SO == _DEFAULT_SO:
         try:
-            build()
+            build()      # mtime-gated: a no-op unless csrc/ is newer than the library (a stale .so must never be tested silently)
         except Exception as e:  # noqa: BLE001
-            raise RtbError(f"librtb200.so is missing and could not be built ({e}); there is no CPU fallback") from e
+            if not os.path.exists(_SO):
+                raise RtbError(f"librtb200.so is missing and could not be built ({e}); there is no CPU fallback") from e
+            raise RtbError(f"librtb200.so is older than its sources and could not be rebuilt ({e})") from e
     L = C.CDLL(_SO)
     vp, u32, sz = C.c_void_p, C.c_uint32, C.c_size_t
     L.rtb_last_error.restype = C.c_char_p; L.rtb_last_error.argtypes = []

@@ -49,9 +49,20 @@ struct rtb_ctx {
     Scratch cnodes, leafBox, wide;    // compressed 32-byte / wide 64-byte traversal records + exact leaf boxes
     Scratch activePix, activeXY, sampleBuf, primaryHits;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
     Scratch poolSlot, poolColor, poolAtt, poolOrg, poolDir, poolNrm, poolList, poolCnt;   // streaming kernel: path pool
+    bool traced = false;              // a trace was submitted since the error flag was last read
     bool bound = false, boundNodes = false, cnodesReady = false, wideReady = false, leafBoxReady = false;
     const void* boundNodesPtr = nullptr;
     uint32_t bT = 0, bS = 0, bM = 0, bN = 0;
+    // tuning knobs (none of them changes a result), read from the environment ONCE, at rtb_ctx_create
+    struct Knobs {
+        uint32_t tMin = 0;            // RTB_WAVE_TMIN: lanes needed to stay in the traverse phase (0 = kernel default)
+        int sortedPush = -1;          // RTB_WAVE_SORTED_PUSH: -1 = by scene (sphere-majority scenes stack waiting entries farthest-first)
+        uint32_t qGate = 4;           // RTB_WAVE_QGATE
+        uint32_t coopMax = 8;         // RTB_WAVE_COOP: tail hand-over threshold (live lanes per warp)
+        uint32_t coopTurns = 32;      // RTB_WAVE_COOP_TURNS: long-ray hand-over threshold (turns)
+        size_t sampleBufBytes = 4ull << 30;   // RTB_WAVE_SAMPLE_BUF_MB: per-(sample, pixel) slot budget
+        size_t streamPool = 0;        // RTB_STREAM_POOL (A/B streaming kernel)
+    } knobs;
 };
 
 namespace {
@@ -165,6 +176,13 @@ int rtb_ctx_create(int device, void* stream, rtb_ctx** out) {
     }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    if (const char* e = getenv("RTB_WAVE_TMIN")) c->knobs.tMin = (uint32_t)atoi(e);
+    if (const char* e = getenv("RTB_WAVE_SORTED_PUSH")) c->knobs.sortedPush = atoi(e);
+    if (const char* e = getenv("RTB_WAVE_QGATE")) c->knobs.qGate = (uint32_t)atoi(e);
+    if (const char* e = getenv("RTB_WAVE_COOP")) c->knobs.coopMax = (uint32_t)atoi(e);
+    if (const char* e = getenv("RTB_WAVE_COOP_TURNS")) c->knobs.coopTurns = (uint32_t)atoi(e);
+    if (const char* e = getenv("RTB_WAVE_SAMPLE_BUF_MB")) c->knobs.sampleBufBytes = (size_t)atoll(e) << 20;
+    if (const char* e = getenv("RTB_STREAM_POOL")) c->knobs.streamPool = (size_t)atoll(e);
     *out = c;
     return 0;
 }
@@ -185,19 +203,26 @@ int rtb_ctx_destroy(rtb_ctx* c) {
     return 0;
 }
 
-int rtb_sync(rtb_ctx* c) {
-    REQUIRE(c, "rtb_sync: null context");
-    Activate act(c);
+// Every entry point that synchronises (rtb_sync, rtb_download, rtb_timer_stop_ms) ends here: wait for the stream, then surface
+// (and clear) the device-side error flag, so a frame rendered with an overflowed traversal stack is never returned as good.
+static int sync_and_check(rtb_ctx* c) {
     CK(cudaStreamSynchronize(c->stream));
-    if (c->errFlag.p) {
+    if (c->errFlag.p && c->traced) {
         unsigned int f = 0;
         CK(cudaMemcpy(&f, c->errFlag.p, sizeof(f), cudaMemcpyDeviceToHost));
+        c->traced = false;
         if (f) {
             cudaMemset(c->errFlag.p, 0, sizeof(f));
-            return fail("rtb_raytrace: traversal stack overflow (tree deeper than 64 levels)");
+            return fail("rtb_raytrace: traversal stack overflow (tree deeper than the traversal stack)");
         }
     }
     return 0;
+}
+
+int rtb_sync(rtb_ctx* c) {
+    REQUIRE(c, "rtb_sync: null context");
+    Activate act(c);
+    return sync_and_check(c);
 }
 
 int rtb_device_name(rtb_ctx* c, char* buf, size_t len) {
@@ -214,12 +239,15 @@ int rtb_alloc(rtb_ctx* c, size_t bytes, void** dptr) {
     CK(cudaMalloc(dptr, bytes ? bytes : 16));
     return 0;
 }
-int rtb_free(rtb_ctx* c, void* dptr) {
-    REQUIRE(c, "rtb_free: null context");
+int rtb_free(rtb_ctx* c, void* dptr) {     // c may be NULL (a Buffer outliving its Device): cudaFree synchronises the device itself
     if (!dptr) return 0;
-    Activate act(c);
-    CK(cudaStreamSynchronize(c->stream));
-    CK(cudaFree(dptr));
+    if (c) {
+        Activate act(c);
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaFree(dptr));
+    } else {
+        CK(cudaFree(dptr));
+    }
     return 0;
 }
 int rtb_upload(rtb_ctx* c, void* dst, const void* host, size_t bytes) {
@@ -232,8 +260,7 @@ int rtb_download(rtb_ctx* c, void* host, const void* src, size_t bytes) {
     REQUIRE(c && (bytes == 0 || (src && host)), "rtb_download: bad argument");
     Activate act(c);
     if (bytes) CK(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return sync_and_check(c);
 }
 int rtb_memset(rtb_ctx* c, void* dst, int byte, size_t bytes) {
     REQUIRE(c && (bytes == 0 || dst), "rtb_memset: bad argument");
@@ -258,7 +285,7 @@ int rtb_timer_stop_ms(rtb_ctx* c, float* ms) {
     REQUIRE(c && ms, "rtb_timer_stop_ms: bad argument");
     Activate act(c);
     CK(cudaEventRecord(c->ev1, c->stream));
-    CK(cudaEventSynchronize(c->ev1));
+    if (sync_and_check(c)) return 1;
     CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
     return 0;
 }
@@ -380,6 +407,11 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     REQUIRE(ubo->numTriangles == c->bT && ubo->numSpheres == c->bS, "rtb_raytrace: UBO primitive counts differ from the bound set");
     REQUIRE(a->imageWidth && a->imageHeight && a->bandRows && a->bandStep, "rtb_raytrace: bad image / band description");
     REQUIRE(!(a->flags & RTB_TRACE_COUNT) || a->counters, "rtb_raytrace: RTB_TRACE_COUNT needs a counters buffer");
+    REQUIRE(!(a->flags & RTB_TRACE_WALK_COUNT) || a->walkCounters, "rtb_raytrace: RTB_TRACE_WALK_COUNT needs a walkCounters buffer");
+    REQUIRE(!((a->flags & RTB_TRACE_WALK_COUNT) && (a->flags & (RTB_TRACE_COUNT | RTB_TRACE_LINEAR_SCAN | RTB_TRACE_SIMPLE_KERNEL | RTB_TRACE_STREAM_KERNEL | RTB_TRACE_CULLED))),
+            "rtb_raytrace: RTB_TRACE_WALK_COUNT instruments the production walk only (no COUNT / LINEAR_SCAN / SIMPLE / STREAM / CULLED)");
+    // the wave kernels pack a pixel as x | y << 16 (activeXY)
+    REQUIRE(a->imageWidth <= 65536u && a->imageHeight <= 65535u, "rtb_raytrace: image larger than 65536 x 65535");
     if (a->sampleCount == 0 || a->localRows == 0) return 0;
     Activate act(c);
     TraceParams p;
@@ -401,15 +433,15 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     p.sampleSkip = a->sampleSkip; p.sampleCount = a->sampleCount;
     p.maxDepth = ubo->maxRayTraceDepth; p.randomState = ubo->randomState;
     p.hitPrim = (uint32_t*)a->hitPrim; p.hitT = (float*)a->hitT; p.rngOut = (uint32_t*)a->rngOut;
-    p.counters = (unsigned long long*)a->counters;
     p.workCounter = (unsigned int*)c->workCounter.p;
     p.errFlag = (unsigned int*)c->errFlag.p;
-    { const char* e = getenv("RTB_WAVE_TMIN"); p.tMin = e ? (uint32_t)atoi(e) : 0u; }
-    { const char* e = getenv("RTB_WAVE_SORTED_PUSH"); p.sortedPush = e ? (uint32_t)atoi(e) : (c->bS > c->bT ? 1u : 0u); }   // measured: +16 % C3, -2..7 % C2/C4/C5
-    { const char* e = getenv("RTB_WAVE_QGATE"); p.qGate = e ? (uint32_t)atoi(e) : 4u; }   // tuning knob, results unaffected
-    { const char* e = getenv("RTB_WAVE_COOP"); p.coopMax = e ? (uint32_t)atoi(e) : 8u; }  // tail hand-over threshold (live lanes per warp); results unaffected
-    { const char* e = getenv("RTB_WAVE_COOP_TURNS"); p.coopTurns = e ? (uint32_t)atoi(e) : 32u; }  // long-ray hand-over threshold (turns); results unaffected
-    const bool count = (a->flags & RTB_TRACE_COUNT) != 0, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;
+    p.tMin = c->knobs.tMin;
+    p.sortedPush = c->knobs.sortedPush >= 0 ? (uint32_t)c->knobs.sortedPush : (c->bS > c->bT ? 1u : 0u);   // measured: +16 % C3, -2..7 % C2/C4/C5
+    p.qGate = c->knobs.qGate; p.coopMax = c->knobs.coopMax; p.coopTurns = c->knobs.coopTurns;
+    const bool walk = (a->flags & RTB_TRACE_WALK_COUNT) != 0;
+    const bool count = (a->flags & RTB_TRACE_COUNT) != 0 || walk, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;
+    p.counters = walk ? nullptr : (unsigned long long*)a->counters;
+    p.walkCounters = walk ? (unsigned long long*)a->walkCounters : nullptr;
     int launches = 1;
     const bool linear = (a->flags & RTB_TRACE_LINEAR_SCAN) != 0;
     if (linear || (a->flags & RTB_TRACE_SIMPLE_KERNEL)) {
@@ -417,8 +449,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     } else {
         // per-(sample, pixel) colour slots: as many samples per pass as fit the scratch budget (default 4 GiB)
         const size_t pixels = (size_t)a->imageWidth * a->localRows;
-        size_t budget = 4ull << 30;
-        if (const char* e = getenv("RTB_WAVE_SAMPLE_BUF_MB")) budget = (size_t)atoll(e) << 20;
+        const size_t budget = c->knobs.sampleBufBytes;
         size_t perPass = budget / (pixels * sizeof(float4));
         if (perPass < 1) perPass = 1;
         if (perPass > a->sampleCount) perPass = a->sampleCount;
@@ -434,7 +465,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
         if ((a->flags & RTB_TRACE_STREAM_KERNEL) && !cull) {
             // pool of in-flight paths: ~18 paths per resident lane keeps the per-iteration tails short
             size_t cap = (size_t)c->smCount * 128 * 7 * 18;
-            if (const char* e = getenv("RTB_STREAM_POOL")) cap = (size_t)atoll(e);
+            if (c->knobs.streamPool) cap = c->knobs.streamPool;
             if (cap > pixels * perPass) cap = pixels * perPass;
             if (cap < 1024) cap = 1024;
             if (ensure(c, c->poolSlot, cap * 4) || ensure(c, c->poolColor, cap * 16) || ensure(c, c->poolAtt, cap * 16) ||
@@ -445,7 +476,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
             p.pool.rayList = (uint32_t*)c->poolList.p; p.pool.cnt = (unsigned int*)c->poolCnt.p; p.pool.capacity = (uint32_t)cap;
             launches = launch_trace_stream(c->stream, p, count, ext, c->smCount, (uint32_t)perPass);
         } else {
-            const bool derived = c->boundNodes && c->bN > 1 && !count;
+            const bool derived = c->boundNodes && c->bN > 1 && (!count || walk);
             int nodesMode = !derived ? 0 : (a->flags & RTB_TRACE_EXACT_NODES) ? 0 : (a->flags & RTB_TRACE_WIDE_NODES) ? 2
                                 : (a->flags & RTB_TRACE_COMPRESSED_NODES) ? 1 : (c->bN >= 8192 ? 2 : 0);
             int extra = 0;
@@ -478,7 +509,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
             if (nodesMode == 2) p.sc.wide = (const uint4*)c->wide.p;
             if (nodesMode == 2 && c->unorderedOk && !cull && !(a->flags & RTB_TRACE_REFERENCE_ORDER)) nodesMode = 3;
             p.primaryHits = nullptr; p.primaryMode = 0;
-            if (!count && a->sampleCount > 1 && !(a->flags & RTB_TRACE_NO_PRIMARY_SHARING)) {
+            if ((!count || walk) && a->sampleCount > 1 && !(a->flags & RTB_TRACE_NO_PRIMARY_SHARING)) {
                 if (ensure(c, c->primaryHits, pixels * 3 * sizeof(float4))) return 1;
                 p.primaryHits = (float4*)c->primaryHits.p;
             }
@@ -491,6 +522,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
             launches = extra + launch_trace_wave(c->stream, p, count, ext, cull, nodesMode, c->smCount, (uint32_t)perPass);
         }
     }
+    c->traced = true;
     return check_launch(c, launches, "trace kernel");
 }
 

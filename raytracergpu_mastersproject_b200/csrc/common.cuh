@@ -136,7 +136,8 @@ struct TraceParams {
     uint32_t W, H, localRows, bandRows, bandFirst, bandStep;
     uint32_t sampleSkip, sampleCount, maxDepth, randomState;
     uint32_t* hitPrim; float* hitT; uint32_t* rngOut;
-    unsigned long long* counters;      // rtb_counters
+    unsigned long long* counters;      // rtb_counters (reference-equivalent work), or null
+    unsigned long long* walkCounters;  // rtb_walk_counters (what the kernels fetch), or null
     unsigned int* workCounter;         // persistent-thread tile counter
     unsigned int* errFlag;             // bit0: traversal stack overflow
     uint32_t tilesX, tilesY;

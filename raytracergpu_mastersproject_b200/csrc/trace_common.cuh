@@ -17,7 +17,37 @@ struct Hit {
     int back;           // backFaceInt
 };
 
-struct Tally { unsigned long long rays, visits, tri, sph, mat; };
+// rays .. mat: the reference-equivalent work counters (rtb_counters); rec .. tailTurns: what the kernels really fetch
+// (rtb_walk_counters, RTB_TRACE_WALK_COUNT).  Only the COUNT instantiations touch any of it.
+struct Tally {
+    unsigned long long rays, visits, tri, sph, mat;
+    unsigned long long rec, lbox, items, paths, parked, lsteps, wsteps, tailRays, tailTurns;
+};
+constexpr int WALK_COUNTER_WORDS = 13;
+// warp-reduce the per-lane tallies and add them to the rtb_counters / rtb_walk_counters buffers (either may be null)
+__device__ __forceinline__ void flush_tally(const Tally& tl, unsigned long long* counters, unsigned long long* walk, const unsigned lane) {
+    const unsigned long long a[5] = { tl.rays, tl.visits, tl.tri, tl.sph, tl.mat };
+    const unsigned long long b[WALK_COUNTER_WORDS] = { tl.rays, tl.rec, tl.lbox, tl.tri, tl.sph, tl.mat, tl.items, tl.paths, tl.parked,
+                                                       tl.lsteps, tl.wsteps, tl.tailRays, tl.tailTurns };
+    if (counters) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            unsigned long long s = a[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+            if (lane == 0 && s) atomicAdd(counters + i, s);
+        }
+    }
+    if (walk) {
+#pragma unroll
+        for (int i = 0; i < WALK_COUNTER_WORDS; i++) {
+            unsigned long long s = b[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+            if (lane == 0 && s) atomicAdd(walk + i, s);
+        }
+    }
+}
 
 // AABBhitCheck, raytraceBVH.comp:184-193 : exact IEEE divisions, GLSL min/max, no t-interval
 __device__ __forceinline__ bool box_hit(const f3 o, const f3 d, const float lox, const float loy, const float loz, const float hix,

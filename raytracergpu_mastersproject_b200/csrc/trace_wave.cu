@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
                         e[7 + j] = make_float4(__uint_as_float(sm.stack[4 * j][tid]), __uint_as_float(sm.stack[4 * j + 1][tid]),
                                                __uint_as_float(sm.stack[4 * j + 2][tid]), __uint_as_float(sm.stack[4 * j + 3][tid]));
                     rayActive = false; travDone = true; sp = 0; cur = 0xFFFFFFFFu;      // the lane is free for the next item
+                    if (COUNT) tl.parked++;
                 }
             }
         }
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
                     e->x = color.x; e->y = color.y; e->z = color.z;       // .w keeps the sample's incoming alpha
                     if (p.rngOut && p.lastPass && smp + 1 == p.sampleCount) p.rngOut[pix] = rng;
                     needItem = true;
+                    if (COUNT) tl.paths++;
                 }
             }
             if (needItem) {                                               // lane-granular persistent threads: next (pixel, sample)
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
                 else { g = (uint32_t)(i / groupItems); r = (uint32_t)(i % groupItems); }
                 const uint32_t slot = g * 32u + (r & 31u);
                 if (slot >= activeCount) continue;                        // padding of the last group
+                if (COUNT) tl.items++;
                 smp = r >> 5;
                 pix = p.activePix[slot];
                 slotIndex = (size_t)smp * p.slotCapacity + slot;
@@ -241,6 +244,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
                     e[3] = make_float4(att.x, att.y, att.z, __uint_as_float(smp));
                     e[4] = make_float4(__uint_as_float((uint32_t)slotIndex), __uint_as_float((uint32_t)((unsigned long long)slotIndex >> 32)), 0.f, 0.f);
                     rayActive = false;
+                    if (COUNT) tl.parked++;
                     continue;                                             // pulls from the drained queue -> dead
                 }
             }
@@ -278,6 +282,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
 #ifdef RTB_TAIL_PROBE
             if (can) prSteps++;
 #endif
+            if (COUNT) { if (can) { tl.lsteps++; if (cur != 0xFFFFFFFFu) tl.rec++; } if (lane == 0) tl.wsteps++; }
             if (can) {
                 // CN: 32-byte compressed records; rays with a zero / denormal direction component (reference yields inf / NaN)
                 // keep to the exact 64-byte records
@@ -300,6 +305,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
                 qHead = (qHead + 1) & (QCAP - 1);
                 qCount--;
                 const float before = closest;
+                if (COUNT && CN && !exactOnly) tl.lbox++;
                 if (NODES >= 3 && !exactOnly) {
                     bool poison = false;
                     if (leaf_box_passes(sc, g, o, d, rinv, false)) leaf_test_unordered<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl, poison);
@@ -320,16 +326,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
     if (pw < 8192) g_probeLane[pw * 32 + lane] = prMax;
 #endif
     if (err) atomicOr(p.errFlag, err);
-    if (COUNT) {
-        unsigned long long v[5] = { tl.rays, tl.visits, tl.tri, tl.sph, tl.mat };
-#pragma unroll
-        for (int i = 0; i < 5; i++) {
-            unsigned long long s = v[i];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL, s, off);
-            if (lane == 0 && s) atomicAdd(p.counters + i, s);
-        }
-    }
+    if (COUNT) flush_tally(tl, p.counters, p.walkCounters, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -347,7 +344,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
 // evaluated redundantly by every lane (uniform state, no divergence).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t COOP_CAP = 512;
-template <bool EXT>
+template <bool EXT, bool COUNT>
 __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TraceParams p) {
     __shared__ uint32_t coopStack[WAVE_THREADS / 32][COOP_CAP];
     const unsigned FULL = 0xFFFFFFFFu;
@@ -396,15 +393,21 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
                         rec.mat = __float_as_uint(q6.x); rec.prim = __float_as_uint(q6.y); rec.back = (int)__float_as_uint(q6.z);
                     }
                     resume = 0;
-                } else if (lane == 0) stk[0] = 0u;
+                } else {
+                    if (lane == 0) stk[0] = 0u;
+                    if (COUNT && lane == 0) tl.rays++;                    // a resumed ray was counted by the launch that started it
+                }
+                if (COUNT && lane == 0) tl.tailRays++;
                 __syncwarp();
                 while (n > 0) {
+                    if (COUNT && lane == 0) tl.tailTurns++;
                     const uint32_t take = n < 32u ? n : 32u;
                     const uint32_t my = lane < take ? stk[n - 1u - lane] : 0xFFFFFFFFu;
                     n -= take;
                     __syncwarp();
                     uint32_t intMask = 0, id0 = 0, id1 = 0, id2 = 0, id3 = 0;
                     if (my != 0xFFFFFFFFu) {
+                        if (COUNT) tl.rec++;
                         const uint4* rp = sc.wide + 4ull * my;
                         const f8 h0 = ldg256(rp), h1 = ldg256(rp + 2);
                         const uint32_t w3 = __float_as_uint(h0.lo.w);
@@ -441,7 +444,8 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
                         for (int k = 0; k < 4; k++) {
                             if (!((enqMask >> k) & 1u)) continue;
                             const uint32_t g = (k == 0 ? id0 : k == 1 ? id1 : k == 2 ? id2 : id3) - leafOffset;
-                            if (leaf_box_passes(sc, g, o, d, rinv, false)) leaf_test_unordered<false>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl, poison);
+                            if (COUNT) tl.lbox++;
+                            if (leaf_box_passes(sc, g, o, d, rinv, false)) leaf_test_unordered<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl, poison);
                         }
                     }
                     if (n + 128u > COOP_CAP) { fit = false; break; }      // warp-uniform
@@ -477,7 +481,11 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
                     rec.mat = __shfl_sync(FULL, rec.mat, win); rec.prim = __shfl_sync(FULL, rec.prim, win); rec.back = __shfl_sync(FULL, rec.back, win);
                 }
             }
-            if (needExact) hit = hit_bvh<false>(sc, o, d, T_MIN_RAY, T_MAX_RAY, rec, tl, err);   // the reference's walk, every lane alike
+            if (needExact) {                                              // the reference's walk, every lane alike (rare: NaN hits, axis-parallel rays)
+                Tally scratch = { 0, 0, 0, 0, 0 };
+                hit = hit_bvh<COUNT>(sc, o, d, T_MIN_RAY, T_MAX_RAY, rec, scratch, err);
+                if (COUNT && lane == 0) { tl.rec += (scratch.visits - 1) / 2; tl.tri += scratch.tri; tl.sph += scratch.sph; }
+            }
             if (p.primaryMode == 1u) {                                    // primary-hit launch: keep the hit record, no shading
                 if (lane == 0) {
                     float4* h = p.primaryHits + 3ull * pix;
@@ -497,6 +505,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
                 color = color + F3(0.f, 0.f, 0.f) * att;
             } else {
                 const float4 m = __ldg(sc.mats + rec.mat);
+                if (COUNT && lane == 0) tl.mat++;
                 const uint32_t type = __float_as_uint(m.w);
                 const f3 albedo = xyz(m);
                 const f3 emitted = (type == RTB_LIGHT) ? albedo : F3(0.f, 0.f, 0.f);
@@ -516,6 +525,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
                 if (depth >= p.maxDepth) pathEnd = true;
             }
             if (pathEnd) {
+                if (COUNT && lane == 0) tl.paths++;
                 if (lane == 0) {
                     float4* out = p.sampleBuf + slotIndex;
                     out->x = color.x; out->y = color.y; out->z = color.z;   // .w keeps the sample's incoming alpha
@@ -526,6 +536,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
         }
     }
     if (err) atomicOr(p.errFlag, err);
+    if (COUNT) flush_tally(tl, nullptr, p.walkCounters, lane);
 }
 
 template <bool COUNT, bool EXT, bool CULL, int NODES>
@@ -540,10 +551,12 @@ static void launch_wave_variant(cudaStream_t st, const TraceParams& p, int smCou
 static void dispatch_wave(cudaStream_t st, const TraceParams& p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint64_t need) {
     const int v = (count ? 4 : 0) | (ext ? 2 : 0) | (cull ? 1 : 0);
     if (nodesMode == 3 && p.sortedPush) {
-        if (ext) launch_wave_variant<false, true, false, 4>(st, p, smCount, need);
+        if (count) { if (ext) launch_wave_variant<true, true, false, 4>(st, p, smCount, need); else launch_wave_variant<true, false, false, 4>(st, p, smCount, need); }
+        else if (ext) launch_wave_variant<false, true, false, 4>(st, p, smCount, need);
         else launch_wave_variant<false, false, false, 4>(st, p, smCount, need);
     } else if (nodesMode == 3) {
-        if (ext) launch_wave_variant<false, true, false, 3>(st, p, smCount, need);
+        if (count) { if (ext) launch_wave_variant<true, true, false, 3>(st, p, smCount, need); else launch_wave_variant<true, false, false, 3>(st, p, smCount, need); }
+        else if (ext) launch_wave_variant<false, true, false, 3>(st, p, smCount, need);
         else launch_wave_variant<false, false, false, 3>(st, p, smCount, need);
     } else if (nodesMode == 2) {
         switch (v) {
@@ -575,7 +588,9 @@ static void dispatch_wave(cudaStream_t st, const TraceParams& p, bool count, boo
 
 // One S2 submission = ceil(sampleCount / samplesPerPass) passes of { pre-pass, [primary hits,] trace, accumulate }.  Returns #launches.
 int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint32_t samplesPerPass) {
-    if (count || p.sc.N < 2) nodesMode = 0;                // the instrumented variant counts the reference's visits: exact records
+    const bool walk = p.walkCounters != nullptr;           // RTB_TRACE_WALK_COUNT: the production walk, counting what it fetches
+    if ((count && !walk) || p.sc.N < 2) nodesMode = 0;     // RTB_TRACE_COUNT counts the reference's visits: exact records, reference order
+    if (walk && nodesMode != 3) nodesMode = 0;             // (the walk counters are built into the two production variants)
     if (nodesMode == 1 && !p.sc.cnodes) nodesMode = 0;
     if (nodesMode >= 2 && !p.sc.wide) nodesMode = 0;
     if (nodesMode == 3 && cull) nodesMode = 2;             // the segment-box extension belongs to the reference-order walk
@@ -583,7 +598,7 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool
     // Primary-hit sharing: the reference's getRay has no jitter (raytraceBVH.comp:329-342), so the samples of a pixel all start
     // with the same primary ray and hitBVH returns the same record for each of them.  It is traced once per pixel per submission
     // (nothing survives the call); the instrumented variant keeps tracing it per sample because it counts the reference's work.
-    const bool share = !count && p.primaryHits != nullptr && p.sampleCount > 1;
+    const bool share = (!count || walk) && p.primaryHits != nullptr && p.sampleCount > 1;
     const uint32_t pixels = p.W * p.localRows;
     const uint32_t totalSamples = p.sampleCount, skip0 = p.sampleSkip;
     int launches = 0;
@@ -598,11 +613,12 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool
         const bool tail = nodesMode == 3 && (p.coopMax != 0u || p.coopTurns != 0u);
         auto launch_tail = [&]() {                                          // finish the parked paths / rays, one ray per warp
             int nb = 0;
-            if (ext) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_tail_kernel<true>, WAVE_THREADS, 0);
-            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_tail_kernel<false>, WAVE_THREADS, 0);
+            if (ext) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_tail_kernel<true, false>, WAVE_THREADS, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_tail_kernel<false, false>, WAVE_THREADS, 0);
             const unsigned grid = (unsigned)smCount * (unsigned)(nb > 0 ? nb : 1);
-            if (ext) trace_tail_kernel<true><<<grid, WAVE_THREADS, 0, st>>>(p);
-            else trace_tail_kernel<false><<<grid, WAVE_THREADS, 0, st>>>(p);
+            if (walk) { if (ext) trace_tail_kernel<true, true><<<grid, WAVE_THREADS, 0, st>>>(p); else trace_tail_kernel<false, true><<<grid, WAVE_THREADS, 0, st>>>(p); }
+            else if (ext) trace_tail_kernel<true, false><<<grid, WAVE_THREADS, 0, st>>>(p);
+            else trace_tail_kernel<false, false><<<grid, WAVE_THREADS, 0, st>>>(p);
             launches++;
         };
         if (share && first == 0) {                                          // one primary ray per active pixel -> primaryHits

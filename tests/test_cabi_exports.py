@@ -26,7 +26,7 @@ def test_header_symbols_exported():
 def test_version_and_loud_failure_without_gpu():
     import torch
     from raytracergpu_mastersproject_b200 import Device, RtbError, capi
-    assert capi.lib().rtb_version() == 100
+    assert capi.lib().rtb_version() == 200
     if not torch.cuda.is_available():
         try:
             Device(0)
@@ -42,4 +42,4 @@ def test_record_sizes_match_reference_layouts():
              capi.BVH_NODE.itemsize, capi.MORTON_PRIMITIVE.itemsize, capi.CONSTRUCTION_INFO.itemsize,
              capi.ENCLOSING_BOX.itemsize, capi.UBO.itemsize]
     assert sizes == [64, 64, 32, 32, 40, 12, 8, 32, 80]
-    assert ctypes.sizeof(capi.TraceArgs) == 72
+    assert ctypes.sizeof(capi.TraceArgs) == 80

@@ -4,7 +4,7 @@ tests/emu/ compiles raytracergpu_mastersproject_b200/csrc/*.cu unmodified (only 
 against an emulation of the CUDA runtime in which every thread is a fiber and the fibers of a block meet at the warp collectives
 (__ballot_sync, __shfl_sync, __match_any_sync, ...) and at __syncthreads -- so the kernels' warp-level control flow (phase
 votes, ballot-ranked queue appends, the one-ray-per-warp tail kernel, the radix sort's peer ranking) runs as written.  This test
-then runs a selection of the `-m gpu` parity tests THEMSELVES over that library (RTB_LIB points the harness at it) in a
+then runs a selection of the `-m gpu` parity tests THEMSELVES over that library (tests/conftest.py points the ctypes binding at it) in a
 subprocess.  It is a check of the kernel code in the tier that has no GPU and a development aid; it is not a product path: the
 emulated library is built into a scratch directory outside the repository, only this test loads it, and the device it reports
 is called "SIMT-EMU".  The GPU tier runs the same tests (and all the others) on the real device.
@@ -58,15 +58,23 @@ def test_tail_kernel_exact_fallback_over_the_emulated_kernels():
     import build_emu
     lib = build_emu.build(os.path.join(tempfile.gettempdir(), "rtb200_emu_fallback"), defines=("RTB_TAIL_TEST_FALLBACK",))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-x", "-q", "-m", "gpu", "-k", "test_tail_handover_forced and 8-3",
-                        "-p", "no:cacheprovider"], cwd=ROOT, env=dict(os.environ, RTB_LIB=lib, RTB_TEST_EMULATION="1"), capture_output=True, text=True, timeout=900)
+                        "-p", "no:cacheprovider"], cwd=ROOT, env=dict(os.environ, RTB_EMU_LIB=lib, RTB_TEST_EMULATION="1"), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and " passed" in r.stdout, (r.stdout + r.stderr)[-1500:]
 
 
-def test_emulated_library_is_refused_outside_this_test(emulated_library):
-    code = "from raytracergpu_mastersproject_b200 import Device; Device(0)"
-    env = {k: v for k, v in os.environ.items() if k != "RTB_TEST_EMULATION"}
-    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(env, RTB_LIB=emulated_library), capture_output=True, text=True, timeout=120)
-    assert r.returncode != 0 and "no CPU path" in r.stderr
+def test_package_has_no_hook_for_the_emulated_library(emulated_library):
+    """Outside pytest's conftest the package loads only its own in-tree librtb200.so, whatever the environment says: on this
+    GPU-less tier that ends in 'no CUDA device', never in an emulated frame."""
+    code = ("from raytracergpu_mastersproject_b200 import Device, capi; assert capi.library_path().endswith('raytracergpu_mastersproject_b200/librtb200.so');"
+            "Device(0)")
+    env = dict(os.environ, RTB_LIB=emulated_library, RTB_EMU_LIB=emulated_library, RTB_TEST_EMULATION="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=120)
+    import torch
+    if not torch.cuda.is_available():
+        assert r.returncode != 0 and "no CUDA device" in r.stderr, r.stderr[-800:]
+    for f in ("capi.py", "renderer.py", "scenes.py", "sharding.py", "__init__.py"):
+        text = open(os.path.join(ROOT, "raytracergpu_mastersproject_b200", f)).read()
+        assert "RTB_LIB" not in text and "RTB_EMU_LIB" not in text and "EMULATION" not in text, f
 
 
 @pytest.mark.parametrize("path,expr", SELECTION, ids=["parity", "fixtures", "cpp_host"])
@@ -78,7 +86,7 @@ def test_gpu_parity_tests_pass_over_the_emulated_kernels(emulated_library, path,
     link = os.path.join(ld, "librtb200.so")
     if not os.path.islink(link):
         os.symlink(emulated_library, link)
-    env = dict(os.environ, RTB_LIB=emulated_library, RTB_TEST_EMULATION="1", LD_LIBRARY_PATH=ld + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    env = dict(os.environ, RTB_EMU_LIB=emulated_library, RTB_TEST_EMULATION="1", LD_LIBRARY_PATH=ld + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([sys.executable, "-m", "pytest", *path.split(), "-x", "-q", "-m", "gpu", "-k", expr, "-p", "no:cacheprovider"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-1500:]

@@ -142,7 +142,7 @@ def test_frame_bit_exact(device, cfg, spp, kernel):
         assert np.array_equal(rg.read(np.uint32).reshape(H, W), rr["rng"])
 
 
-def test_multi_pass_bit_identical(device, monkeypatch):
+def test_multi_pass_bit_identical(device, make_device):
     """A submission whose per-sample slots exceed the scratch budget runs in several passes (C4 / C5 do at full size):
     same image, hit ids and RNG states as one pass; the shared primary hits of pass 1 serve the later passes."""
     from raytracergpu_mastersproject_b200 import Buffer, capi
@@ -155,7 +155,11 @@ def test_multi_pass_bit_identical(device, monkeypatch):
     hp = Buffer(device, 4, W * H); rg = Buffer(device, 4, W * H)
     rt.clear_image(); rt.raytrace(ubo, spp, hit_prim=hp, rng_out=rg); device.wait_idle()
     one = rt.read_image(); hp1 = hp.read(np.uint32); rg1 = rg.read(np.uint32)
-    monkeypatch.setenv("RTB_WAVE_SAMPLE_BUF_MB", "1")            # 128 * 96 * 16 B = 192 KiB per sample -> passes of 5 spp
+    device = make_device(RTB_WAVE_SAMPLE_BUF_MB=1)               # 128 * 96 * 16 B = 192 KiB per sample -> passes of 5 spp
+    rt = _rt(device, W, H)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.build_bvh(ubo)
+    hp = Buffer(device, 4, W * H); rg = Buffer(device, 4, W * H)
     for flags in (0, capi.TRACE_NO_PRIMARY_SHARING, capi.TRACE_EXACT_NODES, capi.TRACE_REFERENCE_ORDER):
         hp.zero(); rg.zero()
         rt.clear_image(); rt.raytrace(ubo, spp, flags=flags, hit_prim=hp, rng_out=rg); device.wait_idle()
@@ -523,15 +527,14 @@ def test_empty_and_zero_sample_submissions(device):
 
 
 @pytest.mark.parametrize("coop,turns", [(0, 1), (32, 0), (32, 1), (8, 3)])
-def test_tail_handover_forced(device, monkeypatch, coop, turns):
+def test_tail_handover_forced(make_device, coop, turns):
     """Long-ray / tail hand-over (trace_wave.cu: parked rays and paths finished by trace_tail_kernel, one ray per warp) with the
     thresholds forced so low that nearly every ray -- primary launch included -- takes that path: rays parked in flight after
     `turns` turns (with their stack and closest hit), paths parked at a ray boundary once the queue is drained.  Image, primary
     hit ids / t, RNG states must be the oracle's, with and without the material extension, shared and unshared primaries,
     1 and 6 samples (1 sample: the primary ray itself is walked by the main launch and may be parked at depth 0)."""
     from raytracergpu_mastersproject_b200 import capi
-    monkeypatch.setenv("RTB_WAVE_COOP", str(coop))
-    monkeypatch.setenv("RTB_WAVE_COOP_TURNS", str(turns))
+    device = make_device(RTB_WAVE_COOP=coop, RTB_WAVE_COOP_TURNS=turns)
     W, H = 80, 56
     sc = SU.random_scene(23, n_tris=900, n_spheres=120, sort_morton=True)
     ubo = SU.make_ubo(sc, random_state=77)
@@ -547,18 +550,58 @@ def test_tail_handover_forced(device, monkeypatch, coop, turns):
     assert np.array_equal(_bits(rt.read_image()), _bits(rr["image"])), "extension materials through the tail kernel differ"
 
 
-def test_tail_handover_off_equals_on(device, monkeypatch):
+def test_tail_handover_off_equals_on(make_device):
     """the hand-over is a scheduling decision: switched off (RTB_WAVE_COOP=0 RTB_WAVE_COOP_TURNS=0) the frame is the same"""
     from raytracergpu_mastersproject_b200 import capi, make_ubo, scenes
     sc = scenes.load_scene("meshRoom:110:9")
     W, H, spp = 160, 90, 8
     ubo = make_ubo(len(sc["triangles"]), len(sc["spheres"]), len(sc["materials"]), sc["max_depth"], 11, sc["vfov"])
+    frames = []
+    for coop, turns in ((0, 0), (8, 32), (32, 2)):
+        device = make_device(RTB_WAVE_COOP=coop, RTB_WAVE_COOP_TURNS=turns)
+        rt = _rt(device, W, H)
+        rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+        rt.build_bvh(ubo)
+        rt.clear_image(); rt.raytrace(ubo, spp); device.wait_idle()
+        frames.append(rt.read_image())
+        del rt
+    assert np.array_equal(_bits(frames[0]), _bits(frames[1])) and np.array_equal(_bits(frames[0]), _bits(frames[2]))
+
+
+@pytest.mark.parametrize("spec,spp,ext", [("meshRoom:70:5", 6, False), ("heightField:90:70:6:40", 4, True), ("sphereField:9000:7", 3, False)])
+def test_walk_counters_of_the_production_kernels(device, spec, spp, ext):
+    """RTB_TRACE_WALK_COUNT: the production walk (4-ary records, nearest-first, hand-over, shared primary hits) instrumented with
+    what it fetches.  Same frame as the un-instrumented call; the counters obey the identities the walk implies and relate to the
+    reference-equivalent counters (RTB_TRACE_COUNT) as primary-hit sharing says they must."""
+    from raytracergpu_mastersproject_b200 import Buffer, capi, make_ubo, scenes
+    sc = scenes.load_scene(spec)
+    W, H = 160, 96
+    ubo = make_ubo(len(sc["triangles"]), len(sc["spheres"]), len(sc["materials"]), sc["max_depth"], 5, sc["vfov"])
     rt = _rt(device, W, H)
     rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
     rt.build_bvh(ubo)
-    frames = []
-    for coop, turns in ((0, 0), (8, 32), (32, 2)):
-        monkeypatch.setenv("RTB_WAVE_COOP", str(coop)); monkeypatch.setenv("RTB_WAVE_COOP_TURNS", str(turns))
-        rt.clear_image(); rt.raytrace(ubo, spp); device.wait_idle()
-        frames.append(rt.read_image())
-    assert np.array_equal(_bits(frames[0]), _bits(frames[1])) and np.array_equal(_bits(frames[0]), _bits(frames[2]))
+    e = capi.TRACE_EXT_MATERIALS if ext else 0
+    rt.clear_image(); rt.raytrace(ubo, spp, flags=e); device.wait_idle()
+    plain = rt.read_image()
+    wc = Buffer(device, 8, 16); wc.zero()
+    rt.clear_image(); rt.raytrace(ubo, spp, flags=e | capi.TRACE_WALK_COUNT, walk_counters=wc); device.wait_idle()
+    assert np.array_equal(_bits(rt.read_image()), _bits(plain)), "the instrumented production walk renders a different frame"
+    w = dict(zip(capi.WALK_COUNTER_FIELDS, (int(x) for x in wc.read(np.uint64, 16))))
+    rt.clear_image(); rt.counters.zero(); rt.raytrace(ubo, spp, flags=e | capi.TRACE_COUNT); device.wait_idle()
+    assert np.array_equal(_bits(rt.read_image()), _bits(plain))
+    ref = rt.read_counters()
+    # active pixels = pixels whose primary ray enters the root box = items of the primary launch
+    active = w["items"] // (spp + 1)
+    assert w["items"] == active * (spp + 1), "items = one primary-hit item + spp sample items per active pixel"
+    assert w["paths"] == active * spp, "every (pixel, sample) item ends in exactly one colour store"
+    # rays walked = the reference's rays minus the (spp - 1) repeats of every active pixel's primary ray and minus the rays of
+    # root-missing pixels (finished by the pre-pass without a walk)
+    missed = W * H - active
+    assert w["rays"] == ref["rays"] - active * (spp - 1) - missed * spp
+    assert w["matReads"] == ref["matReads"], "every sample still shades its own primary hit"
+    assert 0 < w["triTests"] + w["sphTests"] <= ref["triTests"] + ref["sphTests"], "t-culling can only drop primitive tests"
+    assert w["leafBoxFetches"] >= w["triTests"] + w["sphTests"], "a primitive is tested only after its exact leaf box passed"
+    assert w["recordFetches"] > 0 and w["laneSteps"] + 32 * w["tailTurns"] >= w["recordFetches"] and w["warpSteps"] * 32 >= w["laneSteps"]
+    assert w["tailRays"] >= w["parked"] or w["parked"] == 0, "every parked path / ray is finished by the tail kernel"
+    b = capi.walk_bytes(w, primary_sharing=True)
+    assert b["load_bytes"] > b["record_bytes"] > 0
