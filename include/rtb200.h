@@ -108,10 +108,12 @@ typedef struct { uint64_t rays, nodeVisits, triTests, sphTests, matReads, sample
  *   paths           finished paths: one 12-byte colour store into the sample slot
  *   parked          paths / rays handed over to the tail kernel: 240 B written by the main launch and read back by the tail launch
  *   laneSteps, warpSteps   traverse-phase turns per lane / per warp (their ratio = lanes active per T step)
- *   tailRays        rays finished one-ray-per-warp by the tail kernel;  tailTurns: its warp turns */
+ *   tailRays        rays finished one-ray-per-warp by the tail kernel;  tailTurns: its warp turns
+ *   uniqueRecordFetches  recordFetches of the main launch with the lanes of a warp step that expand the SAME record counted once
+ *                   (what reaches L1 as distinct sectors: compare with ncu's l1tex__t_sectors_pipe_lsu_mem_global_op_ld) */
 typedef struct {
     uint64_t rays, recordFetches, leafBoxFetches, triTests, sphTests, matReads, items, paths, parked, laneSteps, warpSteps,
-             tailRays, tailTurns, _reserved[3];
+             tailRays, tailTurns, uniqueRecordFetches, _reserved[2];
 } rtb_walk_counters;
 
 /* What one S2 submission renders (the raysPerPixel dispatch loop of RaytracerBVH.cpp:1025-1050).
@@ -203,7 +205,45 @@ int rtb_resolve_rgba8(rtb_ctx* ctx, const void* image, uint32_t width, uint32_t 
  * imageStore(int(r / 4 * width), int((1 - x') * height)) = pixelColor. */
 int rtb_logistic_step(rtb_ctx* ctx, void* points /* float2[count] */, uint32_t count, void* imageRgba8, uint32_t width,
                       uint32_t height, const float* pixelColor /* [4] */);
-/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+/* ---- multi-GPU (no reference counterpart: the reference renders on the first device only, VulkanWrapper/Device.cpp:115-138) ----
+ * One context per GPU -- one process per GPU (torchrun, MPI, ...) or one host thread per GPU of one process.  The scene is
+ * replicated and every rank builds the same BVH; a frame is partitioned either by interleaved 8-row bands (rtb_trace_args
+ * bandFirst = rank, bandStep = nRanks: bit-identical to one GPU) or by sample range (sampleSkip / sampleCount: fp32 sum order
+ * differs, tolerance).  The calls below are the ONE exchange at the end of a frame.  They run over NCCL (NVLink / NVSwitch),
+ * bound at run time (libnccl.so.2; RTB_NCCL_LIBRARY overrides the name), are enqueued on the context's stream like every
+ * kernel entry point, and must be called by all ranks of the communicator. */
+#define RTB_COMM_ID_BYTES 128
+/* ncclGetUniqueId: one rank creates the id, the host distributes it to the others by any means (file, MPI, torch.distributed) */
+int rtb_comm_unique_id(void* id128);
+int rtb_comm_init_rank(rtb_ctx* ctx, int nRanks, int rank, const void* id128);
+int rtb_comm_destroy(rtb_ctx* ctx);                           /* also done by rtb_ctx_destroy */
+int rtb_comm_info(rtb_ctx* ctx, int* rank, int* nRanks);      /* (0, 1) without a communicator */
+/* In-place all-gather of a device buffer of nRanks * bytesPerRank bytes whose slice [rank * bytesPerRank, +bytesPerRank) this
+ * rank has filled: each rank uploads 1/n of the scene arrays over its own PCIe link and the rest arrives over NVLink
+ * (replaces n full RaytraceScene::updateScene uploads, RaytraceScene.cpp:78-113). */
+int rtb_comm_all_gather(rtb_ctx* ctx, void* buffer, size_t bytesPerRank);
+int rtb_comm_broadcast(rtb_ctx* ctx, void* buffer, size_t bytes, int root);
+/* Tile mode.  localImage: this rank's RGBA32F bands as rendered with bandRows / bandFirst = rank / bandStep = nRanks
+ * (localRows = ceil(ceil(height / bandRows) / nRanks) * bandRows rows of `width` pixels).  On return (stream order) EVERY rank
+ * holds the assembled frame: frameRgba32f (height x width RGBA32F, may be NULL) and / or frameRgba8 (the fragment-shader
+ * resolve, SingleTriangleFullScreen.frag:13-21, fused into the re-assembly; may be NULL).  With frameRgba32f == NULL the bands
+ * are resolved before the exchange and only 4 bytes per pixel cross NVLink. */
+int rtb_gather_tiles(rtb_ctx* ctx, const void* localImage, uint32_t width, uint32_t height, uint32_t bandRows,
+                     void* frameRgba32f, uint32_t raysPerPixel, void* frameRgba8);
+/* Sample-range mode.  image: this rank's full-frame partial sums (rendered from a cleared image with its own sampleSkip /
+ * sampleCount); it is overwritten.  On `root` it ends up holding the sum of the rgb planes over all ranks and the LAST rank's
+ * alpha (= the end of the per-pixel seed chain); frameRgba8 (root only, may be NULL) receives the resolved frame. */
+int rtb_reduce_samples(rtb_ctx* ctx, void* image, uint32_t width, uint32_t height, int root, uint32_t raysPerPixel, void* frameRgba8);
+
+/* Measurement aid: rate (GB/s) at which this GPU delivers divergent 64-byte record fetches -- every lane of a persistent grid of
+ * the trace kernels' shape fetching records at random indices of a scratch buffer of `footprintBytes` -- i.e. the node-fetch
+ * roofline at a scene's record footprint (bench.py reports the trace kernels' fetch rate against it).  Synchronises. */
+int rtb_probe_gather(rtb_ctx* ctx, size_t footprintBytes, float* gbPerSecond);
+/* rtb_download without the wait: the copy is complete after the next rtb_sync (or any later synchronising call) of this context.
+ * `host` should be pinned (rtb_host_alloc) for the copy to overlap other streams. */
+int rtb_download_async(rtb_ctx* ctx, void* host, const void* src, size_t bytes);
+
+/* number of kernels / collectives this context has launched so far (bench.py's gpu_launches) */
 int rtb_launch_count(rtb_ctx* ctx, uint64_t* count);
 
 #ifdef __cplusplus

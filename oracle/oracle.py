@@ -14,7 +14,22 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+def _cpu_tag() -> str:
+    """The oracle is built -march=native: one build per distinct CPU feature set, so that a library built in
+    the build container is never executed on a GPU box with another CPU (it is rebuilt there; gcc is in the image)."""
+    import hashlib
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                return hashlib.sha1(" ".join(sorted(line.split(":", 1)[1].split())).encode()).hexdigest()[:10]
+    except OSError:
+        pass
+    return "generic"
+
+
+_SO = os.path.join(_HERE, "_build", f"liboracle-{_cpu_tag()}.so")
 
 # record layouts (shaders/include/definitions.glsl:6-77, VulkanWrapper/SceneTypes.hpp:32-123)
 MODEL = np.dtype([("m", "<f4", (16,))])
@@ -51,7 +66,7 @@ def build(force: bool = False) -> str:
     src = [os.path.join(_HERE, f) for f in ("rt_oracle.c", "rt_oracle.h", "Makefile")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
     if force or stale:
-        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+        subprocess.run(["make", "-C", _HERE, "-s", "OUT=" + os.path.relpath(_SO, _HERE)], check=True)
     return _SO
 
 
@@ -134,6 +149,15 @@ def delta(sorted_morton, i, j):
 
 
 def max_threads(): return int(lib().orc_max_threads())
+
+
+def host_threads() -> int:
+    """All host cores this process may run on -- NOT omp_get_max_threads(), which launchers cap (torchrun exports OMP_NUM_THREADS=1).
+    Pass it as make_options(threads=...) to time the oracle on the whole host."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 # ---------------------------------------------------------------- S1

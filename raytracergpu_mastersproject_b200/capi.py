@@ -44,7 +44,7 @@ TRACE_WALK_COUNT = 4096
 COUNTER_FIELDS = ("rays", "nodeVisits", "triTests", "sphTests", "matReads", "samples")
 # rtb_walk_counters (16 x u64): what the production kernels fetch (RTB_TRACE_WALK_COUNT)
 WALK_COUNTER_FIELDS = ("rays", "recordFetches", "leafBoxFetches", "triTests", "sphTests", "matReads", "items", "paths", "parked",
-                       "laneSteps", "warpSteps", "tailRays", "tailTurns", "_r0", "_r1", "_r2")
+                       "laneSteps", "warpSteps", "tailRays", "tailTurns", "uniqueRecordFetches", "_r1", "_r2")
 
 
 def walk_bytes(w: dict, primary_sharing: bool) -> dict:
@@ -72,6 +72,8 @@ EXPORTS = [
     "rtb_enclosing_aabb", "rtb_morton_codes", "rtb_sort_morton", "rtb_build_hlbvh", "rtb_refit_aabbs",
     "rtb_build_bvh", "rtb_clear_image", "rtb_bind_trace_buffers", "rtb_raytrace", "rtb_resolve_rgba8",
     "rtb_launch_count", "rtb_logistic_step",
+    "rtb_comm_unique_id", "rtb_comm_init_rank", "rtb_comm_destroy", "rtb_comm_info", "rtb_comm_all_gather", "rtb_comm_broadcast",
+    "rtb_gather_tiles", "rtb_reduce_samples", "rtb_probe_gather", "rtb_download_async",
 ]
 
 
@@ -140,6 +142,16 @@ def lib():
         "rtb_resolve_rgba8": [vp, vp, u32, u32, u32, vp],
         "rtb_launch_count": [vp, C.POINTER(C.c_uint64)],
         "rtb_logistic_step": [vp, vp, u32, vp, u32, u32, vp],
+        "rtb_probe_gather": [vp, sz, C.POINTER(C.c_float)],
+        "rtb_download_async": [vp, vp, vp, sz],
+        "rtb_comm_unique_id": [vp],
+        "rtb_comm_init_rank": [vp, C.c_int, C.c_int, vp],
+        "rtb_comm_destroy": [vp],
+        "rtb_comm_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        "rtb_comm_all_gather": [vp, vp, sz],
+        "rtb_comm_broadcast": [vp, vp, sz, C.c_int],
+        "rtb_gather_tiles": [vp, vp, u32, u32, u32, vp, u32, vp],
+        "rtb_reduce_samples": [vp, vp, u32, u32, C.c_int, u32, vp],
     }
     for name, args in sigs.items():
         fn = getattr(L, name)

@@ -437,9 +437,15 @@ __global__ void __launch_bounds__(256) eta_climb_kernel(const uint32_t* __restri
 //   0-2 origin.xyz | 3: Ex, Ey, Ez, meta (bits 0-3 leaf flags, bits 4-7 present flags) | 4-9: one word per plane
 //   (lo.x lo.y lo.z hi.x hi.y hi.z), byte e = entry e, so the kernel picks a ray's near / far planes of all four entries
 //   with one select per word | 10-13: entry node indices (a leaf is leafOffset + primitive id) | 14-15 unused
-__global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* wide, const float* __restrict__ etaNode) {
+// The records are grown by the hit-point slack only if the ROOT's slack (= the scene's largest) is finite; otherwise they stay
+// tight and *cullAllowed = 0 tells the trace kernels to walk them without t-culling (decided on the device: no read-back).
+__global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* wide, const float* __restrict__ etaNode,
+                                                        unsigned int* cullAllowed) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < 2 || i >= n - 1) return;
+    bool slackOk = false;
+    if (etaNode) { const float etaRoot = etaNode[0]; slackOk = etaRoot >= 0.0f && etaRoot < 3.0e38f; }
+    if (i == 0 && cullAllowed) *cullAllowed = slackOk ? 1u : 0u;
     const uint32_t leafOffset = n - 1;
     // The entries are a cut through X's subtree, kept in visiting order (right before left, raytraceBVH.comp:241-244): start from
     // X's two children and keep replacing the internal entry with the largest surface area by its own two children while a slot
@@ -465,7 +471,7 @@ __global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restri
     for (int k = 0; k < 3; k++) { org[k] = __int_as_float(0x7f800000); top[k] = __int_as_float(0xff800000); }
     for (int e = 0; e < cnt; e++) {
         const float* b = reinterpret_cast<const float*>(nodes + 10ull * entry[e]);
-        const float eta = etaNode ? etaNode[entry[e]] : 0.0f;                          // largest hit-point slack in the entry's subtree
+        const float eta = slackOk ? etaNode[entry[e]] : 0.0f;                          // largest hit-point slack in the entry's subtree
         for (int k = 0; k < 3; k++) {
             lo[e][k] = __fsub_rd(b[2 * k], eta); hi[e][k] = __fadd_ru(b[2 * k + 1], eta);
             org[k] = fminf(org[k], lo[e][k]); top[k] = fmaxf(top[k], hi[e][k]);
@@ -587,9 +593,9 @@ void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pai
 void launch_pack_cnodes(cudaStream_t st, const void* nodes, uint32_t n, void* cnodes, void* leafBox) {
     pack_cnodes_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)cnodes, (float4*)leafBox);
 }
-void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode) {
+void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode, unsigned int* cullAllowed) {
     if (n < 2) return;
-    pack_wide_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)wide, etaNode);
+    pack_wide_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)wide, etaNode, cullAllowed);
 }
 // etaNode[2n-1] <- per-node hit-point slack; parent[2n-1], arrivals[n-1] are scratch.  Returns #launches.
 int launch_eta(cudaStream_t st, const void* nodes, uint32_t n, const void* ptris, uint32_t T, const void* psphs, uint32_t S,

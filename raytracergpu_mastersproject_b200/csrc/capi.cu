@@ -9,88 +9,18 @@
 #include <string>
 
 #include "common.cuh"
+#include "ctx.h"
 #include "kernels.h"
 
 using namespace rtb;
 
-namespace {
-
-thread_local std::string g_lastError;
-
-int fail(const char* what, cudaError_t e = cudaSuccess) {
-    g_lastError = what;
-    if (e != cudaSuccess) { g_lastError += ": "; g_lastError += cudaGetErrorString(e); }
-    return 1;
-}
-#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(#call, _e); } while (0)
-#define REQUIRE(cond, msg) do { if (!(cond)) return fail(msg); } while (0)
-
-struct Scratch {
-    void* p = nullptr;
-    size_t cap = 0;
-};
-
-}  // namespace
-
-struct rtb_ctx {
-    int device = 0;
-    int smCount = 0;
-    cudaStream_t stream = nullptr;
-    bool ownStream = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    uint64_t launches = 0;
-    char name[256] = { 0 };
-    // build scratch (grow-only)
-    Scratch sortKeys[2], sortVals[2], sortCounts, encRed, enclosing, cinfo, nodes;
-    // the bound raytrace set: traversal records derived from the reference-layout arrays
-    Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag, parkBuf;
-    Scratch etaNode, etaParent, etaArrivals;   // per-node hit-point slack (launch_eta) and its scratch
-    bool unorderedOk = false;         // eta small enough for the nearest-first, t-culled traversal
-    Scratch cnodes, leafBox, wide;    // compressed 32-byte / wide 64-byte traversal records + exact leaf boxes
-    Scratch activePix, activeXY, sampleBuf, primaryHits;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots
-    Scratch poolSlot, poolColor, poolAtt, poolOrg, poolDir, poolNrm, poolList, poolCnt;   // streaming kernel: path pool
-    bool traced = false;              // a trace was submitted since the error flag was last read
-    bool bound = false, boundNodes = false, cnodesReady = false, wideReady = false, leafBoxReady = false;
-    const void* boundNodesPtr = nullptr;
-    uint32_t bT = 0, bS = 0, bM = 0, bN = 0;
-    // tuning knobs (none of them changes a result), read from the environment ONCE, at rtb_ctx_create
-    struct Knobs {
-        uint32_t tMin = 0;            // RTB_WAVE_TMIN: lanes needed to stay in the traverse phase (0 = kernel default)
-        int sortedPush = -1;          // RTB_WAVE_SORTED_PUSH: -1 = by scene (sphere-majority scenes stack waiting entries farthest-first)
-        uint32_t qGate = 4;           // RTB_WAVE_QGATE
-        uint32_t coopMax = 8;         // RTB_WAVE_COOP: tail hand-over threshold (live lanes per warp)
-        uint32_t coopTurns = 32;      // RTB_WAVE_COOP_TURNS: long-ray hand-over threshold (turns)
-        size_t sampleBufBytes = 4ull << 30;   // RTB_WAVE_SAMPLE_BUF_MB: per-(sample, pixel) slot budget
-        size_t streamPool = 0;        // RTB_STREAM_POOL (A/B streaming kernel)
-    } knobs;
-};
+namespace rtb {
+std::string& last_error() { thread_local std::string e; return e; }
+}  // namespace rtb
 
 namespace {
 
-int ensure(rtb_ctx* c, Scratch& s, size_t bytes) {
-    if (bytes == 0) bytes = 16;
-    if (s.cap >= bytes) return 0;
-    if (s.p) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(s.p)); s.p = nullptr; s.cap = 0; }
-    const size_t want = bytes + bytes / 8;      // a little slack so small growth does not reallocate
-    CK(cudaMalloc(&s.p, want));
-    CK(cudaMemsetAsync(s.p, 0, want, c->stream));
-    s.cap = want;
-    return 0;
-}
-void release(Scratch& s) { if (s.p) cudaFree(s.p); s.p = nullptr; s.cap = 0; }
-
-int check_launch(rtb_ctx* c, int n, const char* what) {
-    c->launches += (uint64_t)n;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(what, e);
-    return 0;
-}
-
-struct Activate {   // make the context's device current for the duration of a call
-    int prev = -1;
-    explicit Activate(const rtb_ctx* c) { cudaGetDevice(&prev); if (prev != c->device) cudaSetDevice(c->device); else prev = -1; }
-    ~Activate() { if (prev >= 0) cudaSetDevice(prev); }
-};
+constexpr uint32_t WIDE_MIN_PRIMITIVES = 8192;   // below: the exact child pairs (deriving the 4-ary records costs more than it saves)
 
 // Camera globals of raytraceBVH.comp:50-81, evaluated once on the host in binary32 with the shader's operation
 // order (compiled with -ffp-contract=off); tan() is libm's tanf.
@@ -140,11 +70,38 @@ int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tr
     return 0;
 }
 
+// Derived traversal records (DESIGN.md "data layout"): exact leaf boxes + the 32-byte (mode 1) or 4-ary 64-byte (mode 2) records,
+// once per bound node array.  Returns the number of launches, -1 on failure.
+int derive_records(rtb_ctx* c, int nodesMode) {
+    int extra = 0;
+    if (nodesMode && (!c->leafBoxReady || (nodesMode == 1 && !c->cnodesReady))) {   // exact leaf boxes (+ the 32-byte records)
+        if (nodesMode == 1 && ensure(c, c->cnodes, 32ull * (c->bN - 1))) return -1;
+        if (ensure(c, c->leafBox, 32ull * c->bN)) return -1;
+        launch_pack_cnodes(c->stream, c->boundNodesPtr, c->bN, nodesMode == 1 ? c->cnodes.p : nullptr, c->leafBox.p);
+        c->leafBoxReady = true; if (nodesMode == 1) c->cnodesReady = true;
+        extra++;
+    }
+    if (nodesMode == 2 && !c->wideReady) {
+        // Hit-point slack (bvh_build.cu eta_leaf_kernel): a point the reference's primitive tests accept, for a
+        // ray that starts inside the scene's box, lies within eta of the primitive, so inside every record box grown by
+        // the largest eta of its subtree.  If any primitive's slack is not finite (zero-area triangle) the records stay
+        // tight and the walk drops nothing by t; pack_wide_kernel decides that on the device (walkFlag), no read-back.
+        const size_t nn = 2ull * c->bN - 1;
+        if (ensure(c, c->wide, 64ull * (c->bN - 1)) || ensure(c, c->etaNode, 4 * nn) || ensure(c, c->etaParent, 4 * nn) ||
+            ensure(c, c->etaArrivals, 4ull * c->bN) || ensure(c, c->walkFlag, 16)) return -1;
+        extra += launch_eta(c->stream, c->boundNodesPtr, c->bN, c->ptris.p, c->bT, c->psphs.p, c->bS, c->rootBox.p,
+                            (float*)c->etaNode.p, (uint32_t*)c->etaParent.p, (unsigned int*)c->etaArrivals.p);
+        launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wide.p, (const float*)c->etaNode.p, (unsigned int*)c->walkFlag.p);
+        c->wideReady = true; extra++;
+    }
+    return extra;
+}
+
 }  // namespace
 
 extern "C" {
 
-const char* rtb_last_error(void) { return g_lastError.c_str(); }
+const char* rtb_last_error(void) { return rtb::last_error().c_str(); }
 int rtb_version(void) { return RTB_VERSION; }
 
 int rtb_device_count(int* count) {
@@ -189,11 +146,12 @@ int rtb_ctx_create(int device, void* stream, rtb_ctx** out) {
 
 int rtb_ctx_destroy(rtb_ctx* c) {
     if (!c) return 0;
+    if (c->comm) rtb_comm_destroy(c);
     Activate act(c);
     cudaStreamSynchronize(c->stream);
     for (Scratch* s : { &c->sortKeys[0], &c->sortKeys[1], &c->sortVals[0], &c->sortVals[1], &c->sortCounts, &c->encRed, &c->enclosing,
                         &c->cinfo, &c->nodes, &c->pairs, &c->ptris, &c->psphs, &c->psphMat, &c->pmats, &c->rootBox, &c->workCounter,
-                        &c->errFlag, &c->etaNode, &c->etaParent, &c->etaArrivals, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->activeXY, &c->sampleBuf, &c->primaryHits, &c->poolSlot, &c->poolColor,
+                        &c->errFlag, &c->walkFlag, &c->gatherBuf, &c->bandRgba8, &c->etaNode, &c->etaParent, &c->etaArrivals, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->activeXY, &c->sampleBuf, &c->primaryHits, &c->poolSlot, &c->poolColor,
                         &c->poolAtt, &c->poolOrg, &c->poolDir, &c->poolNrm, &c->poolList, &c->poolCnt, &c->parkBuf })
         release(*s);
     cudaEventDestroy(c->ev0);
@@ -261,6 +219,12 @@ int rtb_download(rtb_ctx* c, void* host, const void* src, size_t bytes) {
     Activate act(c);
     if (bytes) CK(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     return sync_and_check(c);
+}
+int rtb_download_async(rtb_ctx* c, void* host, const void* src, size_t bytes) {
+    REQUIRE(c && (bytes == 0 || (src && host)), "rtb_download_async: bad argument");
+    Activate act(c);
+    if (bytes) CK(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
 }
 int rtb_memset(rtb_ctx* c, void* dst, int byte, size_t bytes) {
     REQUIRE(c && (bytes == 0 || dst), "rtb_memset: bad argument");
@@ -382,7 +346,13 @@ int rtb_build_bvh(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void* tria
     if (ensure(c, c->rootBox, sizeof(float4) * 2)) return 1;
     launch_refit(c->stream, nodes, cinfo, N, N > 1 ? c->pairs.p : nullptr, c->rootBox.p); launches++;            // K6 (+ pair records)
     if (check_launch(c, launches, "BVH build kernels")) return 1;
-    return bind_internal(c, T, S, ubo->numMaterials, triangles, spheres, materials, nodes, /*pairsDone=*/N > 1);
+    if (bind_internal(c, T, S, ubo->numMaterials, triangles, spheres, materials, nodes, /*pairsDone=*/N > 1)) return 1;
+    if (N >= WIDE_MIN_PRIMITIVES) {      // the records the default walk of a scene of this size fetches belong to the build (S1), not to the first trace
+        const int extra = derive_records(c, 2);
+        if (extra < 0) return 1;
+        return check_launch(c, extra, "traversal record kernels");
+    }
+    return 0;
 }
 
 // ---- S2 --------------------------------------------------------------------------------------------------------
@@ -462,6 +432,11 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
         p.sampleBuf = (float4*)c->sampleBuf.p;
         p.slotCapacity = (uint32_t)pixels;
         const bool cull = (a->flags & RTB_TRACE_CULLED) != 0;
+#ifndef RTB_AB_KERNELS
+        REQUIRE(!(a->flags & (RTB_TRACE_STREAM_KERNEL | RTB_TRACE_COMPRESSED_NODES)),
+                "rtb_raytrace: the streaming kernel and the 32-byte compressed records are A/B variants (measured, not adopted): rebuild with make AB=1");
+        {
+#else
         if ((a->flags & RTB_TRACE_STREAM_KERNEL) && !cull) {
             // pool of in-flight paths: ~18 paths per resident lane keeps the per-iteration tails short
             size_t cap = (size_t)c->smCount * 128 * 7 * 18;
@@ -476,38 +451,16 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
             p.pool.rayList = (uint32_t*)c->poolList.p; p.pool.cnt = (unsigned int*)c->poolCnt.p; p.pool.capacity = (uint32_t)cap;
             launches = launch_trace_stream(c->stream, p, count, ext, c->smCount, (uint32_t)perPass);
         } else {
+#endif
             const bool derived = c->boundNodes && c->bN > 1 && (!count || walk);
             int nodesMode = !derived ? 0 : (a->flags & RTB_TRACE_EXACT_NODES) ? 0 : (a->flags & RTB_TRACE_WIDE_NODES) ? 2
-                                : (a->flags & RTB_TRACE_COMPRESSED_NODES) ? 1 : (c->bN >= 8192 ? 2 : 0);
-            int extra = 0;
-            if (nodesMode && (!c->leafBoxReady || (nodesMode == 1 && !c->cnodesReady))) {   // exact leaf boxes (+ the 32-byte records)
-                if (nodesMode == 1 && ensure(c, c->cnodes, 32ull * (c->bN - 1))) return 1;
-                if (ensure(c, c->leafBox, 32ull * c->bN)) return 1;
-                launch_pack_cnodes(c->stream, c->boundNodesPtr, c->bN, nodesMode == 1 ? c->cnodes.p : nullptr, c->leafBox.p);
-                c->leafBoxReady = true; if (nodesMode == 1) c->cnodesReady = true;
-                extra++;
-            }
-            if (nodesMode == 2 && !c->wideReady) {
-                // Hit-point slack (bvh_build.cu eta_leaf_kernel): a point the reference's primitive tests accept, for a
-                // ray that starts inside the scene's box, lies within eta of the primitive, so inside every record box grown by
-                // the largest eta of its subtree.  If any
-                // primitive's slack is not finite (zero-area triangle) the records stay tight and only the reference-order walk
-                // is used.  One 4-byte readback per build.
-                const size_t nn = 2ull * c->bN - 1;
-                if (ensure(c, c->wide, 64ull * (c->bN - 1)) || ensure(c, c->etaNode, 4 * nn) || ensure(c, c->etaParent, 4 * nn) ||
-                    ensure(c, c->etaArrivals, 4ull * c->bN)) return 1;
-                extra += launch_eta(c->stream, c->boundNodesPtr, c->bN, c->ptris.p, c->bT, c->psphs.p, c->bS, c->rootBox.p,
-                                    (float*)c->etaNode.p, (uint32_t*)c->etaParent.p, (unsigned int*)c->etaArrivals.p);
-                float etaRoot = 0.f;
-                CK(cudaMemcpyAsync(&etaRoot, c->etaNode.p, 4, cudaMemcpyDeviceToHost, c->stream));
-                CK(cudaStreamSynchronize(c->stream));
-                c->unorderedOk = etaRoot >= 0.f && etaRoot < 3.0e38f;
-                launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wide.p, c->unorderedOk ? (const float*)c->etaNode.p : nullptr);
-                c->wideReady = true; extra++;
-            }
+                                : (a->flags & RTB_TRACE_COMPRESSED_NODES) ? 1 : (c->bN >= WIDE_MIN_PRIMITIVES ? 2 : 0);
+            int extra = derive_records(c, nodesMode);
+            if (extra < 0) return 1;
             if (nodesMode) { p.sc.cnodes = nodesMode == 1 ? (const uint4*)c->cnodes.p : nullptr; p.sc.leafBox = (const float4*)c->leafBox.p; }
             if (nodesMode == 2) p.sc.wide = (const uint4*)c->wide.p;
-            if (nodesMode == 2 && c->unorderedOk && !cull && !(a->flags & RTB_TRACE_REFERENCE_ORDER)) nodesMode = 3;
+            if (nodesMode == 2 && !cull && !(a->flags & RTB_TRACE_REFERENCE_ORDER)) nodesMode = 3;
+            p.cullAllowed = (const unsigned int*)c->walkFlag.p;
             p.primaryHits = nullptr; p.primaryMode = 0;
             if ((!count || walk) && a->sampleCount > 1 && !(a->flags & RTB_TRACE_NO_PRIMARY_SHARING)) {
                 if (ensure(c, c->primaryHits, pixels * 3 * sizeof(float4))) return 1;

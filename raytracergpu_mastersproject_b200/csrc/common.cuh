@@ -140,6 +140,7 @@ struct TraceParams {
     unsigned long long* walkCounters;  // rtb_walk_counters (what the kernels fetch), or null
     unsigned int* workCounter;         // persistent-thread tile counter
     unsigned int* errFlag;             // bit0: traversal stack overflow
+    const unsigned int* cullAllowed;   // nearest-first walk: 1 = the records were grown by the hit-point slack, t-culling is sound (pack_wide_kernel)
     uint32_t tilesX, tilesY;
     uint32_t sortedPush;               // nearest-first kernel: pick the variant that stacks waiting entries farthest-first
     uint32_t qGate;                    // nearest-first kernel: a lane keeps stepping while its FIFO holds <= qGate candidates

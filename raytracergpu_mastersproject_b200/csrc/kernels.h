@@ -22,7 +22,7 @@ void launch_hlbvh(cudaStream_t st, const void* tris, uint32_t T, const void* sph
 void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox);   // pairs != NULL: also emit traversal records
 void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pairs, void* rootBox);
 void launch_pack_cnodes(cudaStream_t st, const void* nodes, uint32_t n, void* cnodes, void* leafBox);
-void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode);
+void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode, unsigned int* cullAllowed);
 int launch_eta(cudaStream_t st, const void* nodes, uint32_t n, const void* ptris, uint32_t T, const void* psphs, uint32_t S,
                const void* rootBox, float* etaNode, uint32_t* parent, unsigned int* arrivals);
 void launch_pack_prims(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* mats, uint32_t M,

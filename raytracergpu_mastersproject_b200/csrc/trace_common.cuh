@@ -21,14 +21,14 @@ struct Hit {
 // (rtb_walk_counters, RTB_TRACE_WALK_COUNT).  Only the COUNT instantiations touch any of it.
 struct Tally {
     unsigned long long rays, visits, tri, sph, mat;
-    unsigned long long rec, lbox, items, paths, parked, lsteps, wsteps, tailRays, tailTurns;
+    unsigned long long rec, lbox, items, paths, parked, lsteps, wsteps, tailRays, tailTurns, recUnique;
 };
-constexpr int WALK_COUNTER_WORDS = 13;
+constexpr int WALK_COUNTER_WORDS = 14;
 // warp-reduce the per-lane tallies and add them to the rtb_counters / rtb_walk_counters buffers (either may be null)
 __device__ __forceinline__ void flush_tally(const Tally& tl, unsigned long long* counters, unsigned long long* walk, const unsigned lane) {
     const unsigned long long a[5] = { tl.rays, tl.visits, tl.tri, tl.sph, tl.mat };
     const unsigned long long b[WALK_COUNTER_WORDS] = { tl.rays, tl.rec, tl.lbox, tl.tri, tl.sph, tl.mat, tl.items, tl.paths, tl.parked,
-                                                       tl.lsteps, tl.wsteps, tl.tailRays, tl.tailTurns };
+                                                       tl.lsteps, tl.wsteps, tl.tailRays, tl.tailTurns, tl.recUnique };
     if (counters) {
 #pragma unroll
         for (int i = 0; i < 5; i++) {

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
     constexpr bool CN = NODES != 0;                       // conservative internal boxes: leaves are re-checked exactly
     constexpr uint32_t Q_ROOM = NODES >= 2 ? 4u : 2u;     // free FIFO entries a turn may need
     const uint32_t qGate = NODES >= 3 ? min(p.qGate, QCAP - Q_ROOM) : QCAP - Q_ROOM;   // a lane steps while its FIFO holds <= qGate candidates
+    const bool cullAllowed = NODES >= 3 ? (*p.cullAllowed != 0u) : false;   // records grown by a finite hit-point slack (pack_wide_kernel)
 
     // ---- per-lane state -------------------------------------------------------------------------------------------
     bool dead = false, rayActive = false, travDone = true, exactOnly = false, hit = false, cullOk = false;
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
             if (NODES >= 3) {   // the slack the records were grown by covers rays that start inside the scene's box (+ 0.1 %): others are not culled
                 const float grow = 1.0e-3f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
-                cullOk = o.x >= lo.x - grow && o.x <= hi.x + grow && o.y >= lo.y - grow && o.y <= hi.y + grow && o.z >= lo.z - grow && o.z <= hi.z + grow;
+                cullOk = cullAllowed && o.x >= lo.x - grow && o.x <= hi.x + grow && o.y >= lo.y - grow && o.y <= hi.y + grow && o.z >= lo.z - grow && o.z <= hi.z + grow;
             }
             if (box_test(o, d, rinv, exactOnly, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) {
                 if (sc.N == 1) enqueue(0u);                                                // the root is the only leaf
@@ -282,13 +283,25 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
 #ifdef RTB_TAIL_PROBE
             if (can) prSteps++;
 #endif
-            if (COUNT) { if (can) { tl.lsteps++; if (cur != 0xFFFFFFFFu) tl.rec++; } if (lane == 0) tl.wsteps++; }
+            if (COUNT) {
+                if (can) {
+                    tl.lsteps++;
+                    if (cur != 0xFFFFFFFFu) {      // lanes of a warp that expand the SAME record share one fetch (L1 coalesces them): count it once
+                        tl.rec++;
+                        const unsigned same = __match_any_sync(__activemask(), cur);
+                        if ((unsigned)(__ffs(same) - 1) == lane) tl.recUnique++;
+                    }
+                }
+                if (lane == 0) tl.wsteps++;
+            }
             if (can) {
                 // CN: 32-byte compressed records; rays with a zero / denormal direction component (reference yields inf / NaN)
                 // keep to the exact 64-byte records
                 if (NODES >= 3 && !exactOnly) wave_step_u<NODES == 4>(sc, sm, tid, o, rinv, cullOk ? closest : __int_as_float(0x7f800000), cullOk ? T_MIN_RAY : __int_as_float(0xff800000), cur, sp, qCount, travDone, lstack, err, leafOffset);
                 else if (NODES == 2 && !exactOnly) wave_step_w<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
+#ifdef RTB_AB_KERNELS
                 else if (NODES == 1 && !exactOnly) wave_step_c<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
+#endif
                 else wave_step<COUNT, CULL>(sc, sm, tid, leafOffset, o, d, rinv, exactOnly, cur, sp, qHead, qCount, travDone, lstack, tl, err, segLo, segHi);
             }
         }
@@ -375,9 +388,10 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
             const f3 rinv = F3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
             bool needExact = !(fabsf(rinv.x) < 3.0e38f && fabsf(rinv.y) < 3.0e38f && fabsf(rinv.z) < 3.0e38f);
             const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
+            if (COUNT && lane == 0) { tl.tailRays++; if (!(resume & 1u)) tl.rays++; }   // a resumed ray was counted by the launch that started it
             if (!needExact && ((resume & 1u) || box_test(o, d, rinv, false, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z))) {
                 const float grow = 1.0e-3f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
-                const bool cullOk = o.x >= lo.x - grow && o.x <= hi.x + grow && o.y >= lo.y - grow && o.y <= hi.y + grow && o.z >= lo.z - grow && o.z <= hi.z + grow;
+                const bool cullOk = *p.cullAllowed != 0u && o.x >= lo.x - grow && o.x <= hi.x + grow && o.y >= lo.y - grow && o.y <= hi.y + grow && o.z >= lo.z - grow && o.z <= hi.z + grow;
                 float closest = T_MAX_RAY, best = T_MAX_RAY;              // lane-local closest hit; warp-wide culling bound
                 bool poison = false, fit = true;
                 uint32_t n = 1;
@@ -393,11 +407,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
                         rec.mat = __float_as_uint(q6.x); rec.prim = __float_as_uint(q6.y); rec.back = (int)__float_as_uint(q6.z);
                     }
                     resume = 0;
-                } else {
-                    if (lane == 0) stk[0] = 0u;
-                    if (COUNT && lane == 0) tl.rays++;                    // a resumed ray was counted by the launch that started it
-                }
-                if (COUNT && lane == 0) tl.tailRays++;
+                } else if (lane == 0) stk[0] = 0u;
                 __syncwarp();
                 while (n > 0) {
                     if (COUNT && lane == 0) tl.tailTurns++;
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
                     __syncwarp();
                     uint32_t intMask = 0, id0 = 0, id1 = 0, id2 = 0, id3 = 0;
                     if (my != 0xFFFFFFFFu) {
-                        if (COUNT) tl.rec++;
+                        if (COUNT) { tl.rec++; tl.recUnique++; }      // the lanes of a tail warp expand distinct entries of one ray
                         const uint4* rp = sc.wide + 4ull * my;
                         const f8 h0 = ldg256(rp), h1 = ldg256(rp + 2);
                         const uint32_t w3 = __float_as_uint(h0.lo.w);
@@ -565,6 +575,7 @@ static void dispatch_wave(cudaStream_t st, const TraceParams& p, bool count, boo
         case 2: launch_wave_variant<false, true, false, 2>(st, p, smCount, need); break;
         default: launch_wave_variant<false, true, true, 2>(st, p, smCount, need); break;
         }
+#ifdef RTB_AB_KERNELS
     } else if (nodesMode == 1) {
         switch (v) {
         case 0: launch_wave_variant<false, false, false, 1>(st, p, smCount, need); break;
@@ -572,6 +583,7 @@ static void dispatch_wave(cudaStream_t st, const TraceParams& p, bool count, boo
         case 2: launch_wave_variant<false, true, false, 1>(st, p, smCount, need); break;
         default: launch_wave_variant<false, true, true, 1>(st, p, smCount, need); break;
         }
+#endif
     } else {
         switch (v) {
         case 0: launch_wave_variant<false, false, false, 0>(st, p, smCount, need); break;
@@ -591,7 +603,11 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool
     const bool walk = p.walkCounters != nullptr;           // RTB_TRACE_WALK_COUNT: the production walk, counting what it fetches
     if ((count && !walk) || p.sc.N < 2) nodesMode = 0;     // RTB_TRACE_COUNT counts the reference's visits: exact records, reference order
     if (walk && nodesMode != 3) nodesMode = 0;             // (the walk counters are built into the two production variants)
+#ifdef RTB_AB_KERNELS
     if (nodesMode == 1 && !p.sc.cnodes) nodesMode = 0;
+#else
+    if (nodesMode == 1) nodesMode = 0;
+#endif
     if (nodesMode >= 2 && !p.sc.wide) nodesMode = 0;
     if (nodesMode == 3 && cull) nodesMode = 2;             // the segment-box extension belongs to the reference-order walk
     if (p.tMin == 0) p.tMin = nodesMode >= 2 ? 20 : T_MIN_DEFAULT;   // swept on C2 (RTB_WAVE_TMIN)

@@ -217,6 +217,7 @@ __device__ __forceinline__ void wave_step(const TraceScene& sc, WaveSmem<THREADS
     if (doPop && !popLeaf) cur = e;
 }
 
+#ifdef RTB_AB_KERNELS   // measured and not adopted: compiled only into A/B builds (make EXTRA=-DRTB_AB_KERNELS AB=1)
 // Traverse-phase turn over the 32-byte COMPRESSED record (one 256-bit load).  Child planes are conservative (outward
 // rounded) 8-bit offsets from the node origin; slab parameters are evaluated as t = q * (scale / dir) + (origin - o) / dir
 // with one FFMA per plane.  A child is skipped only when it is a definite miss even after granting every rounding error
@@ -292,6 +293,7 @@ __device__ __forceinline__ void wave_step_c(const TraceScene& sc, WaveSmem<THREA
     if (doPop && !popLeaf) cur = e;
 }
 
+#endif   // RTB_AB_KERNELS
 
 // Traverse-phase turn over the 64-byte WIDE record (two 256-bit loads): up to four grandchild entries of binary node `cur` in
 // the reference's visiting order, boxes conservative (8-bit, outward rounded) exactly as in wave_step_c, so one turn covers

@@ -34,5 +34,7 @@ namespace Config {
 		constexpr const u32 RandomState = 12345; // deterministic stand-in for the clock-seeded mt19937 (D9); 0 = clock
 		constexpr const int DeviceIndex = 0;
 		constexpr const char* OutputImage = "frame.ppm";
+		constexpr const char* OutputPng = "frame.png";     // the same frame as PNG (utils/Png.hpp)
+		constexpr const u32 BandRows = 8;                  // multi-GPU tile mode: rows per interleaved band (rtb_trace_args)
 	};
 };

@@ -1,4 +1,5 @@
 #include "LogisticMap.hpp"
+#include "utils/Png.hpp"
 
 #include <fstream>
 #include <iostream>
@@ -48,6 +49,7 @@ auto LogisticMap::mainLoop() -> void {                                   // Logi
 	std::ofstream f(Config::Headless::OutputImage, std::ios::binary);
 	f << "P6\n" << width << " " << height << "\n255\n";
 	for (size_t i = 0; i < size_t(width) * height; i++) f.write(reinterpret_cast<const char*>(&lastFrame[4 * i]), 3);
+	png::writeRGB(Config::Headless::OutputPng, lastFrame.data(), width, height);
 	std::cout << "LogisticMap: " << frames << " iterations of " << SAMPLE_COUNT << " points\n";
 }
 

@@ -1,4 +1,5 @@
 #include "Raytracer.hpp"
+#include "utils/Png.hpp"
 
 #include <chrono>
 #include <cstdio>
@@ -77,6 +78,7 @@ auto Raytracer::mainLoop() -> void {                                     // Rayt
 		std::ofstream f(Config::Headless::OutputImage, std::ios::binary);
 		f << "P6\n" << width << " " << height << "\n255\n";
 		for (size_t i = 0; i < size_t(width) * height; i++) f.write(reinterpret_cast<const char*>(&lastFrame[4 * i]), 3);
+		png::writeRGB(Config::Headless::OutputPng, lastFrame.data(), width, height);
 	}
 }
 

@@ -6,6 +6,7 @@
 #include <iostream>
 
 #include "Scenes.hpp"
+#include "utils/Png.hpp"
 
 namespace RaytracerBVHRenderer {
 
@@ -23,11 +24,17 @@ f32 msSince(std::chrono::high_resolution_clock::time_point t0) {
 
 Raytracer::Raytracer() : Raytracer(Config::Headless::Width, Config::Headless::Height, "complexScene") {}
 
-Raytracer::Raytracer(u32 w, u32 h, const std::string& sceneName, int deviceIndex)
-	: device(deviceIndex), width(w), height(h),
+Raytracer::Raytracer(u32 w, u32 h, const std::string& sceneName, int deviceIndex, MultiGpu m)
+	: device(deviceIndex), width(w), height(h), multi(m), localRows(h),
 	  gen(Config::Headless::RandomState ? Config::Headless::RandomState
 	                                    : static_cast<u32>(std::chrono::system_clock::now().time_since_epoch().count())) {
-	std::cout << "physical device: " << device.name() << "\n";           // Device.cpp:137
+	if (multi.rank == 0) std::cout << "physical device: " << device.name() << "\n";           // Device.cpp:137
+	if (multi.ranks > 1) {
+		if (!Config::Headless::RandomState) throw std::runtime_error("multi-GPU rendering needs a fixed Config::Headless::RandomState (every rank must draw the same seeds)");
+		Device::check(rtb_comm_init_rank(device.context(), multi.ranks, multi.rank, multi.commId), "failed to create the communicator");
+		const u32 band = Config::Headless::BandRows, bands = (height + band - 1) / band;
+		localRows = ((bands + u32(multi.ranks) - 1) / u32(multi.ranks)) * band;
+	}
 	createScene(sceneName);
 }
 
@@ -44,13 +51,13 @@ auto Raytracer::createScene(const std::string& sceneName) -> void {
 	mortonPrimitiveBuffer2 = std::make_unique<Buffer>(device, sizeof(SceneTypes::GPU::MortonPrimitive), n);
 	HLBVHNodesBuffer = std::make_unique<Buffer>(device, sizeof(SceneTypes::GPU::BVHNode), 2 * n - 1);
 	HLBVHConstructionInfoBuffer = std::make_unique<Buffer>(device, sizeof(rtb_construction_info), 2 * n - 1);
-	computeImage = std::make_unique<Buffer>(device, 4 * sizeof(f32), width * height);   // R32G32B32A32_SFLOAT
+	computeImage = std::make_unique<Buffer>(device, 4 * sizeof(f32), width * localRows);   // R32G32B32A32_SFLOAT (this rank's bands)
 	presentImage = std::make_unique<Buffer>(device, 4, width * height);                 // B8G8R8A8_UNORM stand-in (RGBA8)
 }
 
 // one frame (reference: doIteration, RaytracerBVH.hpp:206-496)
 auto Raytracer::doIteration(f32) -> void {
-	std::cout << "iteration: " << iteration << "\n";
+	if (multi.rank == 0) std::cout << "iteration: " << iteration << "\n";
 	rtb_ctx* q = device.computeQueue();
 	auto t0 = std::chrono::high_resolution_clock::now();
 	scene->updateScene();                                                 // re-flatten + re-upload model-space arrays
@@ -75,7 +82,7 @@ auto Raytracer::doIteration(f32) -> void {
 
 	// S1: clear + K1..K6 (recordComputeS1CommandBuffer, RaytracerBVH.cpp:734-997), then the fence wait
 	t0 = std::chrono::high_resolution_clock::now();
-	Device::check(rtb_clear_image(q, computeImage->getBuffer(), width, height), "failed to clear the accumulation image");
+	Device::check(rtb_clear_image(q, computeImage->getBuffer(), width, localRows), "failed to clear the accumulation image");
 	Device::check(rtb_build_bvh(q, &ubo, scene->getModelBuffer()->getBuffer(), scene->getTriangleBuffer()->getBuffer(),
 	                            scene->getSphereBuffer()->getBuffer(), scene->getMaterialBuffer()->getBuffer(),
 	                            enclosingAABBBuffer->getBuffer(), mortonPrimitiveBuffer1->getBuffer(), mortonPrimitiveBuffer2->getBuffer(),
@@ -87,8 +94,9 @@ auto Raytracer::doIteration(f32) -> void {
 	// S2: raysPerPixel samples (recordComputeS2CommandBuffer, RaytracerBVH.cpp:998-1050), then the fence wait
 	t0 = std::chrono::high_resolution_clock::now();
 	rtb_trace_args args{};
-	args.imageWidth = width; args.imageHeight = height; args.localRows = height;
+	args.imageWidth = width; args.imageHeight = height; args.localRows = localRows;
 	args.bandRows = height; args.bandFirst = 0; args.bandStep = 1;
+	if (multi.ranks > 1) { args.bandRows = Config::Headless::BandRows; args.bandFirst = u32(multi.rank); args.bandStep = u32(multi.ranks); }
 	args.sampleSkip = 0; args.sampleCount = scene->getRaysPerPixel();
 	Device::check(rtb_raytrace(q, &ubo, computeImage->getBuffer(), &args), "failed to submit compute command buffer!");
 	device.waitIdle();
@@ -96,13 +104,17 @@ auto Raytracer::doIteration(f32) -> void {
 
 	// "present": the fullscreen fragment pass (SingleTriangleFullScreen.frag:13-21) into an RGBA8 host image
 	t0 = std::chrono::high_resolution_clock::now();
-	Device::check(rtb_resolve_rgba8(q, computeImage->getBuffer(), width, height, scene->getRaysPerPixel(), presentImage->getBuffer()),
-	              "failed to submit draw command buffer!");
+	if (multi.ranks > 1)      // the bands of all ranks, resolved and re-assembled on every rank (NCCL over NVLink, in-stream)
+		Device::check(rtb_gather_tiles(q, computeImage->getBuffer(), width, height, Config::Headless::BandRows, nullptr, scene->getRaysPerPixel(),
+		                               presentImage->getBuffer()), "failed to gather the frame");
+	else
+		Device::check(rtb_resolve_rgba8(q, computeImage->getBuffer(), width, height, scene->getRaysPerPixel(), presentImage->getBuffer()),
+		              "failed to submit draw command buffer!");
 	lastFrame.resize(size_t(4) * width * height);
 	presentImage->readFromBuffer(lastFrame.data(), lastFrame.size());
 	lastTimings.resolveMs = msSince(t0);
 
-	std::printf("TIMINGS:\n\tupdateSceneTime: %.0fus, Total BVH Build Time: %.0fus, Total Raytracing Time: %.0fus, resolve: %.0fus\n",
+	if (multi.rank == 0) std::printf("TIMINGS:\n\tupdateSceneTime: %.0fus, Total BVH Build Time: %.0fus, Total Raytracing Time: %.0fus, resolve: %.0fus\n",
 	            1e3 * lastTimings.updateSceneMs, 1e3 * (lastTimings.updateSceneMs + lastTimings.buildMs), 1e3 * lastTimings.traceMs,
 	            1e3 * lastTimings.resolveMs);
 }
@@ -116,8 +128,9 @@ auto Raytracer::mainLoop() -> void {
 		auto newTime = std::chrono::high_resolution_clock::now();
 		auto frameTime = std::chrono::duration_cast<std::chrono::microseconds>(newTime - currentTime);
 		currentTime = newTime;
-		std::cout << "Frame Time(us): " << frameTime.count() << " RaysPerPixel: " << scene->getRaysPerPixel()
-		          << " Depth: " << scene->getMaxRaytraceDepth() << std::endl;
+		if (multi.rank == 0)
+			std::cout << "Frame Time(us): " << frameTime.count() << " RaysPerPixel: " << scene->getRaysPerPixel()
+			          << " Depth: " << scene->getMaxRaytraceDepth() << std::endl;
 		doIteration(f32(frameTime.count()));
 		if constexpr (Config::RunRayPerPixelIncreasingDemo) {               // the rays-per-pixel sweep -> runtimes.csv
 			namespace D = Config::RayPerPixelIncreasingDemoConfig;
@@ -131,7 +144,11 @@ auto Raytracer::mainLoop() -> void {
 		iteration++;
 	}
 	device.waitIdle();
-	if (!lastFrame.empty()) writePPM(Config::Headless::OutputImage, lastFrame, width, height);
+	if (!lastFrame.empty() && multi.rank == 0) {
+		writePPM(Config::Headless::OutputImage, lastFrame, width, height);
+		png::writeRGB(Config::Headless::OutputPng, lastFrame.data(), width, height);
+	}
+	if (multi.rank != 0) return;
 	if constexpr (Config::RunRayPerPixelIncreasingDemo) {
 		std::ofstream out("runtimes.csv", std::ios::out | std::ios::trunc);
 		for (size_t i = 0; i < times.size(); i++) {

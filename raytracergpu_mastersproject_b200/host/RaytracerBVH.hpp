@@ -40,9 +40,16 @@ namespace RaytracerBVHRenderer {
 
 	struct FrameTimings { f32 updateSceneMs = 0, buildMs = 0, traceMs = 0, resolveMs = 0; };
 
+	// additive: this renderer is rank `rank` of `ranks` renderers (one per GPU, one host thread or process each) that share a
+	// frame by interleaved bands of Config::Headless::BandRows rows; commId = the 128 bytes of rtb_comm_unique_id().
+	// The reference renders on the first device only (VulkanWrapper/Device.cpp:115-138).
+	struct MultiGpu { int rank = 0; int ranks = 1; const void* commId = nullptr; };
+
 	class Raytracer {
 		Device device;
 		u32 width, height;
+		MultiGpu multi;
+		u32 localRows;                            // rows of the accumulation image this rank renders (= height on one GPU)
 
 		std::unique_ptr<RaytraceScene> scene;
 		std::unique_ptr<Buffer> enclosingAABBBuffer, mortonPrimitiveBuffer1, mortonPrimitiveBuffer2;
@@ -61,7 +68,8 @@ namespace RaytracerBVHRenderer {
 
 	public:
 		Raytracer();                                                      // 800 x 800, complexScene (RaytracerBVH.cpp:8,511)
-		Raytracer(u32 width, u32 height, const std::string& sceneName, int deviceIndex = Config::Headless::DeviceIndex);   // additive
+		Raytracer(u32 width, u32 height, const std::string& sceneName, int deviceIndex = Config::Headless::DeviceIndex,
+		          MultiGpu multi = {});                                   // additive
 		~Raytracer();
 		auto mainLoop() -> void;
 

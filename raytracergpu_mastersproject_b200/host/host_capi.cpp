@@ -5,6 +5,7 @@
 #include <string>
 
 #include "Scenes.hpp"
+#include "utils/Png.hpp"
 #include "VulkanWrapper/RTModel.hpp"
 #include "VulkanWrapper/RaytraceScene.hpp"
 
@@ -54,6 +55,11 @@ long rtbh_load_obj(const char* path, float* out, long maxTriangles) {
 		if (out) for (long i = 0; i < long(tris.size()) && i < maxTriangles; i++) std::memcpy(out + 9 * i, &tris[size_t(i)], 36);
 		return long(tris.size());
 	} catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// the headless hosts' PNG writer (utils/Png.hpp), for the CPU test of the encoder
+int rtbh_write_png(const char* path, const unsigned char* rgba, unsigned width, unsigned height) {
+	try { png::writeRGB(path, rgba, width, height); return 0; } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 
 }  // extern "C"

@@ -54,6 +54,34 @@ class Device:
         check(self._lib.rtb_timer_stop_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
+    # -- multi-GPU: one Device per rank; the exchange at the end of a frame (include/rtb200.h "multi-GPU")
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(capi.lib().rtb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
+        check(self._lib.rtb_comm_init_rank(self._h, n_ranks, rank, C.c_char_p(unique_id)))
+
+    def comm_info(self) -> tuple[int, int]:
+        r, n = C.c_int(), C.c_int()
+        check(self._lib.rtb_comm_info(self._h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    def comm_all_gather(self, ptr: int, bytes_per_rank: int):
+        check(self._lib.rtb_comm_all_gather(self._h, C.c_void_p(ptr), bytes_per_rank))
+
+    def gather_tiles(self, local_image_ptr: int, width: int, height: int, band_rows: int, frame_f32_ptr: int | None,
+                     rays_per_pixel: int, frame_rgba8_ptr: int | None):
+        check(self._lib.rtb_gather_tiles(self._h, C.c_void_p(local_image_ptr), width, height, band_rows,
+                                         C.c_void_p(frame_f32_ptr) if frame_f32_ptr else None, rays_per_pixel,
+                                         C.c_void_p(frame_rgba8_ptr) if frame_rgba8_ptr else None))
+
+    def reduce_samples(self, image_ptr: int, width: int, height: int, root: int, rays_per_pixel: int, frame_rgba8_ptr: int | None):
+        check(self._lib.rtb_reduce_samples(self._h, C.c_void_p(image_ptr), width, height, root, rays_per_pixel,
+                                           C.c_void_p(frame_rgba8_ptr) if frame_rgba8_ptr else None))
+
     def close(self):
         if self._h:
             self._lib.rtb_ctx_destroy(self._h)

@@ -54,6 +54,7 @@ def lib():
         L.rtbh_transform_mat4.restype = None; L.rtbh_transform_mat4.argtypes = [C.c_void_p] * 4
         L.rtbh_load_obj.restype = C.c_long; L.rtbh_load_obj.argtypes = [C.c_char_p, C.c_void_p, C.c_long]
         L.rtbh_set_model_dir.restype = None; L.rtbh_set_model_dir.argtypes = [C.c_char_p]
+        L.rtbh_write_png.restype = C.c_int; L.rtbh_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_uint, C.c_uint]
         L.rtbh_set_model_dir(os.path.join(_HOST, "models").encode())
         _lib = L
     return _lib
@@ -85,6 +86,36 @@ def transform_mat4(translation, scale, rotation) -> np.ndarray:
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     lib().rtbh_transform_mat4(p(t), p(s), p(r), p(out))
     return out
+
+
+def write_png(path: str, rgba: np.ndarray):
+    """RGBA8 [H, W, 4] -> PNG through the C++ hosts' own encoder (host/utils/Png.hpp)"""
+    a = np.ascontiguousarray(rgba, np.uint8)
+    if lib().rtbh_write_png(path.encode(), a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0]) != 0:
+        raise capi.RtbError(lib().rtbh_last_error().decode())
+
+
+def read_png_rgb(path: str) -> np.ndarray:
+    """Decoder for the test suite (stdlib zlib): checks the signature, every chunk CRC, the zlib Adler-32, un-filters (type 0
+    only, as the encoder writes) -> uint8 [H, W, 3]"""
+    import struct
+    import zlib
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n", "not a PNG"
+    pos, idat, w = 8, b"", None
+    while pos < len(data):
+        n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        assert zlib.crc32(typ + body) == struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0], f"bad CRC in {typ}"
+        if typ == b"IHDR":
+            w, h, depth, ctype, comp, flt, inter = struct.unpack(">IIBBBBB", body)
+            assert (depth, ctype, comp, flt, inter) == (8, 2, 0, 0, 0)
+        elif typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3 * w)
+    assert np.all(raw[:, 0] == 0), "only filter type 0 is written"
+    return raw[:, 1:].reshape(h, w, 3).copy()
 
 
 def load_obj(path: str) -> np.ndarray:

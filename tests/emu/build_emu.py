@@ -14,7 +14,7 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "raytracergpu_mastersproject_b200", "csrc")
-UNITS = ["capi.cu", "bvh_build.cu", "radix_sort.cu", "trace.cu", "trace_wave.cu", "trace_stream.cu"]
+UNITS = ["capi.cu", "comm.cu", "probe.cu", "bvh_build.cu", "radix_sort.cu", "trace.cu", "trace_wave.cu"]
 
 
 def _match_back(s, end):
@@ -109,7 +109,7 @@ def build(out_dir=None, defines=()):
     for p in procs:
         if p.wait() != 0:
             raise RuntimeError("emu build failed")
-    subprocess.run(["g++", "-shared", "-o", so] + objs, check=True)
+    subprocess.run(["g++", "-shared", "-o", so] + objs + ["-ldl"], check=True)
     return so
 
 

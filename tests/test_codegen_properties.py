@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "raytracergpu_mastersproject_b200", "librtb200.so")
 MAIN = "_ZN3rtb17trace_wave_kernelILb0ELb0ELb0ELi3EEEvNS_11TraceParamsE"          # nearest-first 4-ary walk, production variant
 MAIN_SORTED = "_ZN3rtb17trace_wave_kernelILb0ELb0ELb0ELi4EEEvNS_11TraceParamsE"   # same, farthest-first stacking (sphere scenes)
-TAIL = "_ZN3rtb17trace_tail_kernelILb0EEEvNS_11TraceParamsE"
+TAIL = "_ZN3rtb17trace_tail_kernelILb0ELb0EEEvNS_11TraceParamsE"
 
 pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="needs the CUDA toolkit's cuobjdump")
 

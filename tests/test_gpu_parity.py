@@ -95,7 +95,7 @@ def test_s1_stage_by_stage(device, cfg):
 
 @pytest.mark.parametrize("cfg", SCENES, ids=lambda c: f"seed{c['seed']}")
 @pytest.mark.parametrize("spp", [1, 5])
-@pytest.mark.parametrize("kernel", ["wave", "wave-exact-nodes", "wave-compressed-nodes", "wave-wide-nodes", "wave-wide-reference-order", "simple", "stream"])
+@pytest.mark.parametrize("kernel", ["wave", "wave-exact-nodes", "wave-wide-nodes", "wave-wide-reference-order", "simple"])
 def test_frame_bit_exact(device, cfg, spp, kernel):
     """Whole frame (S1 fused + S2): node array, hit ids, RNG states, counters and the fp32 image, all bit-exact.
     Both trace kernels: the production warp-coherent one and the straightforward one kept for A/B measurements."""
@@ -339,7 +339,7 @@ def test_error_behaviour(device):
 # edge cases
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("depth", [0, 1, 2])
-@pytest.mark.parametrize("kernel", ["wave", "simple", "stream"])
+@pytest.mark.parametrize("kernel", ["wave", "simple"])
 def test_shallow_depths(device, depth, kernel):
     """maxRayTraceDepth 0 (the bounce loop never runs: no rays, colour 0, the alpha chain still advances), 1 and 2."""
     from raytracergpu_mastersproject_b200 import capi
@@ -390,7 +390,7 @@ def test_degenerate_and_extreme_geometry_nan_parity(device):
     ubo = SU.make_ubo(sc, random_state=17)
     ref = O.build_bvh(sc["models"], t, sc["spheres"])
     rr = O.raytrace(ubo, W, H, ref["tris"], ref["sphs"], sc["materials"], ref["nodes"], spp)
-    for fl in (0, capi.TRACE_SIMPLE_KERNEL, capi.TRACE_STREAM_KERNEL):
+    for fl in (0, capi.TRACE_SIMPLE_KERNEL):
         rt = _rt(device, W, H)
         rt.update_scene(sc["models"], t, sc["spheres"], sc["materials"])
         rt.build_bvh(ubo)
@@ -605,3 +605,18 @@ def test_walk_counters_of_the_production_kernels(device, spec, spp, ext):
     assert w["tailRays"] >= w["parked"] or w["parked"] == 0, "every parked path / ray is finished by the tail kernel"
     b = capi.walk_bytes(w, primary_sharing=True)
     assert b["load_bytes"] > b["record_bytes"] > 0
+
+
+def test_ab_variants_are_not_in_the_product_build(device):
+    """The streaming kernel and the 32-byte compressed records were measured and not adopted: the default build does not
+    carry them and says so instead of silently running something else."""
+    from raytracergpu_mastersproject_b200 import RtbError, capi
+    sc = SU.random_scene(1, n_tris=50, n_spheres=5)
+    ubo = SU.make_ubo(sc)
+    rt = _rt(device, 16, 16)
+    rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+    rt.build_bvh(ubo)
+    rt.clear_image()
+    for fl in (capi.TRACE_STREAM_KERNEL, capi.TRACE_COMPRESSED_NODES):
+        with pytest.raises(RtbError, match="A/B variants"):
+            rt.raytrace(ubo, 1, flags=fl)

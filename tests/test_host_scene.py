@@ -75,21 +75,69 @@ def test_unknown_scene_raises():
 
 
 def test_obj_loader(tmp_path):
-    p = tmp_path / "t.obj"
-    p.write_text("# quad as one polygon + a negative-index triangle, with vt / vn\n"
-                 "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvn 0 0 1\n"
-                 "f 1/1/1 2/1/1 3/1/1 4/1/1\n"
-                 "f -4//1 -3//1 -1//1\n")
-    tris = scenes.load_obj(str(p))
-    assert tris.shape == (3, 3, 3)                          # fan triangulation: (1,2,3) (1,3,4) + 1
-    assert tris[0].tolist() == [[0, 0, 0], [1, 0, 0], [1, 1, 0]]
-    assert tris[1].tolist() == [[0, 0, 0], [1, 1, 0], [0, 1, 0]]
-    assert tris[2].tolist() == [[0, 0, 0], [1, 0, 0], [0, 1, 0]]
+    """host/VulkanWrapper/ObjLoader.cpp restates tinyobjloader's triangulation (the reference calls LoadObj with triangulate = true,
+    RTModel.cpp:53): triangles as they are, quads along the shorter diagonal, larger polygons ear-clipped from corner 0.  The
+    expected triangles below were derived by hand from those rules (the library is un-vendored: pinned by restatement)."""
+    def tris_of(text, name="t.obj"):
+        p = tmp_path / name
+        p.write_text(text)
+        return scenes.load_obj(str(p))[:, :, :2].tolist()
+    # square quad: equal diagonals -> NOT "shorter 0-2" -> (0,1,3) (1,2,3); then a negative-index triangle with vt / vn
+    t = tris_of("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvn 0 0 1\n"
+                "f 1/1/1 2/1/1 3/1/1 4/1/1\n"
+                "f -4//1 -3//1 -1//1\n")
+    assert t == [[[0, 0], [1, 0], [0, 1]], [[1, 0], [1, 1], [0, 1]], [[0, 0], [1, 0], [0, 1]]]
+    # kite whose diagonal 0-2 (|.|^2 = 2) is shorter than 1-3 (18) -> (0,1,2) (0,2,3)
+    t = tris_of("v 0 0 0\nv 3 0 0\nv 1 1 0\nv 0 3 0\nf 1 2 3 4\n")
+    assert t == [[[0, 0], [3, 0], [1, 1]], [[0, 0], [1, 1], [0, 3]]]
+    # ... and the mirror case: diagonal 1-3 shorter -> (0,1,3) (1,2,3)
+    t = tris_of("v 0 0 0\nv 1 0 0\nv 3 3 0\nv 0 1 0\nf 1 2 3 4\n")
+    assert t == [[[0, 0], [1, 0], [0, 1]], [[1, 0], [3, 3], [0, 1]]]
+    # convex pentagon: every corner is an ear in turn -> a fan from corner 0
+    P = [(0, 0), (2, 0), (3, 1.5), (1, 3), (-1, 1.5)]
+    t = tris_of("".join(f"v {x} {y} 0\n" for x, y in P) + "f 1 2 3 4 5\n")
+    f = lambda *ix: [[list(map(float, P[i])) for i in tri] for tri in ix]  # noqa: E731
+    assert t == f((0, 1, 2), (0, 2, 3), (0, 3, 4))
+    # concave pentagon, corner 1 reflex: corner 0's ear is rejected, clipping starts at corner 1 -> (1,2,3) (1,3,4) (0,1,4)
+    P = [(0, 0), (1, 1), (2, 0), (2, 3), (0, 3)]
+    t = tris_of("".join(f"v {x} {y} 0\n" for x, y in P) + "f 1 2 3 4 5\n")
+    assert t == f((1, 2, 3), (1, 3, 4), (0, 1, 4))
+    # the same polygon in the x = const plane (dominant-plane axes y, z) triangulates the same way
+    t3 = scenes.load_obj(str(_write(tmp_path / "yz.obj", "".join(f"v 7 {x} {y}\n" for x, y in P) + "f 1 2 3 4 5\n")))[:, :, 1:].tolist()
+    assert t3 == f((1, 2, 3), (1, 3, 4), (0, 1, 4))
+    # faces with fewer than three corners are dropped (tinyobjloader warns), line continuation, vertex colours, o / g / s / usemtl ignored
+    t = tris_of("o thing\ng part\ns off\nv 0 0 0 1 0 0\nv 1 0 0 0 1 0\nv 0 1 0 0 0 1\nusemtl none\nf 1 2\nf 1 2 \\\n 3\n")
+    assert t == [[[0, 0], [1, 0], [0, 1]]]
+    # an mtllib that exists is parsed, one that does not is only a warning: the reference never looks at OBJ materials
+    (tmp_path / "m.mtl").write_text("newmtl red\nKd 1 0 0\nKe 0 0 0\nNs 10\nnewmtl glow\nKe 5 5 5\n")
+    t = tris_of("mtllib m.mtl\nmtllib missing.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nusemtl glow\nf 1 2 3\n")
+    assert t == [[[0, 0], [1, 0], [0, 1]]]
     with pytest.raises(capi.RtbError):
         scenes.load_obj(str(tmp_path / "missing.obj"))
     bad = tmp_path / "bad.obj"; bad.write_text("v 0 0 0\nf 1 2 3\n")
     with pytest.raises(capi.RtbError):
         scenes.load_obj(str(bad))
+
+
+def _write(path, text):
+    path.write_text(text)
+    return path
+
+
+def test_png_writer_round_trip(tmp_path):
+    """host/utils/Png.hpp (the headless hosts' present-to-PNG): signature, chunk CRCs, zlib stream and pixels survive a decode,
+    including an image whose raw data needs several stored deflate blocks (> 65535 bytes)."""
+    rng = np.random.default_rng(5)
+    for h, w in [(1, 1), (7, 5), (200, 150)]:
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        p = str(tmp_path / f"t{h}.png")
+        scenes.write_png(p, img)
+        assert np.array_equal(scenes.read_png_rgb(p), img[..., :3])
+    try:
+        from PIL import Image
+        assert np.array_equal(np.asarray(Image.open(p).convert("RGB")), img[..., :3])     # an independent decoder agrees
+    except ImportError:
+        pass
 
 
 def test_standin_assets():

@@ -208,7 +208,7 @@ def test_cuda_matches_reference_binaries(device, name):
         assert np.array_equal(rt.read_image().view(np.uint32), g["images_bvh"][s].view(np.uint32)), f"dispatch {s}"
     # fused submission, every traversal variant
     variants = [0, capi.TRACE_WIDE_NODES, capi.TRACE_WIDE_NODES | capi.TRACE_REFERENCE_ORDER, capi.TRACE_EXACT_NODES,
-                capi.TRACE_COMPRESSED_NODES, capi.TRACE_SIMPLE_KERNEL, capi.TRACE_STREAM_KERNEL, capi.TRACE_NO_PRIMARY_SHARING]
+                capi.TRACE_SIMPLE_KERNEL, capi.TRACE_NO_PRIMARY_SHARING]
     for fl in variants:
         rt.clear_image(); rt.raytrace(g["ubo"], spp, flags=fl); device.wait_idle()
         assert np.array_equal(rt.read_image().view(np.uint32), g["images_bvh"][-1].view(np.uint32)), f"flags {fl}"
