@@ -243,6 +243,12 @@ int rtb_probe_gather(rtb_ctx* ctx, size_t footprintBytes, float* gbPerSecond);
  * `host` should be pinned (rtb_host_alloc) for the copy to overlap other streams. */
 int rtb_download_async(rtb_ctx* ctx, void* host, const void* src, size_t bytes);
 
+/* Diagnostic: the per-primitive hit-point slack eta (bvh_build.cu eta_leaf_kernel) the 4-ary records of the bound scene were grown
+ * by, one float per primitive in leaf order (triangles, then spheres), and the origin region (6 floats: min.xyz, max.xyz) inside
+ * which rays are t-culled.  Fails if the bound scene has no 4-ary records yet.  Synchronises.  (tests: every accepted hit must lie
+ * within eta of its primitive's leaf box) */
+int rtb_export_hit_slack(rtb_ctx* ctx, float* hostEta, size_t count, float* hostOriginRegion6);
+
 /* number of kernels / collectives this context has launched so far (bench.py's gpu_launches) */
 int rtb_launch_count(rtb_ctx* ctx, uint64_t* count);
 

@@ -73,7 +73,7 @@ EXPORTS = [
     "rtb_build_bvh", "rtb_clear_image", "rtb_bind_trace_buffers", "rtb_raytrace", "rtb_resolve_rgba8",
     "rtb_launch_count", "rtb_logistic_step",
     "rtb_comm_unique_id", "rtb_comm_init_rank", "rtb_comm_destroy", "rtb_comm_info", "rtb_comm_all_gather", "rtb_comm_broadcast",
-    "rtb_gather_tiles", "rtb_reduce_samples", "rtb_probe_gather", "rtb_download_async",
+    "rtb_gather_tiles", "rtb_reduce_samples", "rtb_probe_gather", "rtb_download_async", "rtb_export_hit_slack",
 ]
 
 
@@ -143,6 +143,7 @@ def lib():
         "rtb_launch_count": [vp, C.POINTER(C.c_uint64)],
         "rtb_logistic_step": [vp, vp, u32, vp, u32, u32, vp],
         "rtb_probe_gather": [vp, sz, C.POINTER(C.c_float)],
+        "rtb_export_hit_slack": [vp, vp, sz, vp],
         "rtb_download_async": [vp, vp, vp, sz],
         "rtb_comm_unique_id": [vp],
         "rtb_comm_init_rank": [vp, C.c_int, C.c_int, vp],

@@ -383,13 +383,32 @@ __global__ void __launch_bounds__(256) pack_cnodes_kernel(const uint32_t* __rest
 //    31 eps (|oc| + r)^2 / r; |oc| <= distance from the centre to the farthest corner of the grown root box.  The kernel
 //    uses 62 eps = 4e-6 (+ the same 1e-5 R for the rounding of P).
 // The per-node value is the maximum over the node's subtree (climbed like the refit: the second arrival at a node continues).
+//
+// ORIGIN REGION.  Everything above holds for rays whose origin lies in a region Omega with R = the largest coordinate magnitude of
+// Omega (the bounds use |o| <= sqrt(3) R, |v0| <= sqrt(3) R, |t d| = |P - o| <= 2 sqrt(3) R).  Omega is the root box grown by 0.1 %
+// of its largest extent -- every secondary ray starts on a primitive, i.e. inside it -- extended to contain the CAMERA position
+// when that at most quadruples R (a camera far away from a small scene would inflate every record box; its rays then simply stay
+// un-culled, as rays from outside Omega always do).  The kernel stores Omega in originRegion[0..1]; the trace kernels cull a ray
+// by t only if its origin lies inside it.
+__device__ __forceinline__ void origin_region(const float4* __restrict__ rootBox, const f3 cam, float4& lo, float4& hi) {
+    lo = rootBox[0]; hi = rootBox[1];
+    const float grow = 1.0e-3f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
+    lo.x -= grow; lo.y -= grow; lo.z -= grow; hi.x += grow; hi.y += grow; hi.z += grow;
+    const float R = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
+    const float rc = fmaxf(fmaxf(fabsf(cam.x), fabsf(cam.y)), fabsf(cam.z));
+    if (rc <= 4.0f * R) {      // (false for a NaN camera)
+        lo.x = fminf(lo.x, cam.x); lo.y = fminf(lo.y, cam.y); lo.z = fminf(lo.z, cam.z);
+        hi.x = fmaxf(hi.x, cam.x); hi.y = fmaxf(hi.y, cam.y); hi.z = fmaxf(hi.z, cam.z);
+    }
+}
 __global__ void __launch_bounds__(256) eta_leaf_kernel(const float4* __restrict__ ptris, uint32_t T, const float4* __restrict__ psphs,
-                                                       uint32_t S, const float4* __restrict__ rootBox, float* etaLeaf) {
+                                                       uint32_t S, const float4* __restrict__ rootBox, const f3 cam, float* etaLeaf,
+                                                       float4* originRegion) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= T + S) return;
-    float4 lo = rootBox[0], hi = rootBox[1];
-    const float grow = 1.0e-3f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);   // = the ray-origin test of trace_wave.cu
-    lo.x -= grow; lo.y -= grow; lo.z -= grow; hi.x += grow; hi.y += grow; hi.z += grow;
+    float4 lo, hi;
+    origin_region(rootBox, cam, lo, hi);
+    if (g == 0) { originRegion[0] = lo; originRegion[1] = hi; }
     const float R = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
     float eta;
     if (g < T) {
@@ -599,11 +618,11 @@ void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide
 }
 // etaNode[2n-1] <- per-node hit-point slack; parent[2n-1], arrivals[n-1] are scratch.  Returns #launches.
 int launch_eta(cudaStream_t st, const void* nodes, uint32_t n, const void* ptris, uint32_t T, const void* psphs, uint32_t S,
-               const void* rootBox, float* etaNode, uint32_t* parent, unsigned int* arrivals) {
+               void* rootBox, const float* camPos, float* etaNode, uint32_t* parent, unsigned int* arrivals) {
     if (n < 2) return 0;
     cudaMemsetAsync(arrivals, 0, sizeof(unsigned int) * (n - 1), st);
     eta_leaf_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const float4*)ptris, T, (const float4*)psphs, S, (const float4*)rootBox,
-                                                        etaNode + (n - 1));
+                                                        F3(camPos[0], camPos[1], camPos[2]), etaNode + (n - 1), (float4*)rootBox + 2);
     parent_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, parent);
     eta_climb_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t*)nodes, parent, n, etaNode, arrivals);
     return 3;

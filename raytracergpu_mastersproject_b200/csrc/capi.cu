@@ -56,7 +56,7 @@ int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tr
     if (ensure(c, c->psphs, sizeof(float4) * (size_t)S)) return 1;
     if (ensure(c, c->psphMat, sizeof(uint32_t) * (size_t)S)) return 1;
     if (ensure(c, c->pmats, sizeof(float4) * (size_t)M)) return 1;
-    if (ensure(c, c->rootBox, sizeof(float4) * 2)) return 1;
+    if (ensure(c, c->rootBox, sizeof(float4) * 4)) return 1;
     if (ensure(c, c->workCounter, 32)) return 1;
     if (ensure(c, c->errFlag, 16)) return 1;
     if (nodes && !pairsDone) launch_pack_pairs(c->stream, nodes, N, c->pairs.p, c->rootBox.p);
@@ -72,7 +72,7 @@ int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tr
 
 // Derived traversal records (DESIGN.md "data layout"): exact leaf boxes + the 32-byte (mode 1) or 4-ary 64-byte (mode 2) records,
 // once per bound node array.  Returns the number of launches, -1 on failure.
-int derive_records(rtb_ctx* c, int nodesMode) {
+int derive_records(rtb_ctx* c, int nodesMode, const float* camPos) {
     int extra = 0;
     if (nodesMode && (!c->leafBoxReady || (nodesMode == 1 && !c->cnodesReady))) {   // exact leaf boxes (+ the 32-byte records)
         if (nodesMode == 1 && ensure(c, c->cnodes, 32ull * (c->bN - 1))) return -1;
@@ -89,7 +89,7 @@ int derive_records(rtb_ctx* c, int nodesMode) {
         const size_t nn = 2ull * c->bN - 1;
         if (ensure(c, c->wide, 64ull * (c->bN - 1)) || ensure(c, c->etaNode, 4 * nn) || ensure(c, c->etaParent, 4 * nn) ||
             ensure(c, c->etaArrivals, 4ull * c->bN) || ensure(c, c->walkFlag, 16)) return -1;
-        extra += launch_eta(c->stream, c->boundNodesPtr, c->bN, c->ptris.p, c->bT, c->psphs.p, c->bS, c->rootBox.p,
+        extra += launch_eta(c->stream, c->boundNodesPtr, c->bN, c->ptris.p, c->bT, c->psphs.p, c->bS, c->rootBox.p, camPos,
                             (float*)c->etaNode.p, (uint32_t*)c->etaParent.p, (unsigned int*)c->etaArrivals.p);
         launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wide.p, (const float*)c->etaNode.p, (unsigned int*)c->walkFlag.p);
         c->wideReady = true; extra++;
@@ -343,12 +343,12 @@ int rtb_build_bvh(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void* tria
     if (morton1) { launch_morton_repack(c->stream, k0, v0, N, T, morton1); launches++; }
     launch_hlbvh(c->stream, triangles, T, spheres, S, k0, 1, nodes, cinfo); launches++;                           // K5
     if (ensure(c, c->pairs, sizeof(float4) * 4ull * (N > 1 ? N - 1 : 1))) return 1;
-    if (ensure(c, c->rootBox, sizeof(float4) * 2)) return 1;
+    if (ensure(c, c->rootBox, sizeof(float4) * 4)) return 1;
     launch_refit(c->stream, nodes, cinfo, N, N > 1 ? c->pairs.p : nullptr, c->rootBox.p); launches++;            // K6 (+ pair records)
     if (check_launch(c, launches, "BVH build kernels")) return 1;
     if (bind_internal(c, T, S, ubo->numMaterials, triangles, spheres, materials, nodes, /*pairsDone=*/N > 1)) return 1;
     if (N >= WIDE_MIN_PRIMITIVES) {      // the records the default walk of a scene of this size fetches belong to the build (S1), not to the first trace
-        const int extra = derive_records(c, 2);
+        const int extra = derive_records(c, 2, ubo->camPos);
         if (extra < 0) return 1;
         return check_launch(c, extra, "traversal record kernels");
     }
@@ -455,7 +455,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
             const bool derived = c->boundNodes && c->bN > 1 && (!count || walk);
             int nodesMode = !derived ? 0 : (a->flags & RTB_TRACE_EXACT_NODES) ? 0 : (a->flags & RTB_TRACE_WIDE_NODES) ? 2
                                 : (a->flags & RTB_TRACE_COMPRESSED_NODES) ? 1 : (c->bN >= WIDE_MIN_PRIMITIVES ? 2 : 0);
-            int extra = derive_records(c, nodesMode);
+            int extra = derive_records(c, nodesMode, ubo->camPos);
             if (extra < 0) return 1;
             if (nodesMode) { p.sc.cnodes = nodesMode == 1 ? (const uint4*)c->cnodes.p : nullptr; p.sc.leafBox = (const float4*)c->leafBox.p; }
             if (nodesMode == 2) p.sc.wide = (const uint4*)c->wide.p;
@@ -477,6 +477,20 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     }
     c->traced = true;
     return check_launch(c, launches, "trace kernel");
+}
+
+int rtb_export_hit_slack(rtb_ctx* c, float* hostEta, size_t count, float* hostOriginRegion6) {
+    REQUIRE(c && hostEta && hostOriginRegion6, "rtb_export_hit_slack: bad argument");
+    REQUIRE(c->bound && c->wideReady && c->bN > 1, "rtb_export_hit_slack: the bound scene has no 4-ary records (fewer than 8192 primitives and never traced with RTB_TRACE_WIDE_NODES)");
+    REQUIRE(count == c->bN, "rtb_export_hit_slack: count must equal the number of primitives");
+    Activate act(c);
+    float4 region[2];
+    CK(cudaMemcpyAsync(hostEta, (const float*)c->etaNode.p + (c->bN - 1), sizeof(float) * count, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(region, (const float4*)c->rootBox.p + 2, sizeof(region), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    hostOriginRegion6[0] = region[0].x; hostOriginRegion6[1] = region[0].y; hostOriginRegion6[2] = region[0].z;
+    hostOriginRegion6[3] = region[1].x; hostOriginRegion6[4] = region[1].y; hostOriginRegion6[5] = region[1].z;
+    return 0;
 }
 
 int rtb_logistic_step(rtb_ctx* c, void* points, uint32_t count, void* imageRgba8, uint32_t width, uint32_t height, const float* pixelColor) {

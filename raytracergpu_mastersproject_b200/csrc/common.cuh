@@ -105,7 +105,7 @@ struct TraceScene {
     const float4* __restrict__ sphs;     // [S]
     const uint32_t* __restrict__ sphMat; // [S]
     const float4* __restrict__ mats;     // [M]
-    const float4* __restrict__ rootBox;  // [2]: (min.xyz,0) (max.xyz,0) of node 0
+    const float4* __restrict__ rootBox;  // [4]: (min.xyz,0) (max.xyz,0) of node 0; [2..3] the origin region of the t-culled walk (eta_leaf_kernel)
     const uint4* __restrict__ cnodes;    // [N-1][2] 32-byte compressed child-pair records (conservative 8-bit boxes), or null
     const float4* __restrict__ leafBox;  // [N][2]   exact leaf boxes (min.xyz,0) (max.xyz,0), used with cnodes / wide
     const uint4* __restrict__ wide;      // [N-1][4] 64-byte 4-ary records (conservative 8-bit grandchild boxes), or null

@@ -24,7 +24,7 @@ void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pai
 void launch_pack_cnodes(cudaStream_t st, const void* nodes, uint32_t n, void* cnodes, void* leafBox);
 void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode, unsigned int* cullAllowed);
 int launch_eta(cudaStream_t st, const void* nodes, uint32_t n, const void* ptris, uint32_t T, const void* psphs, uint32_t S,
-               const void* rootBox, float* etaNode, uint32_t* parent, unsigned int* arrivals);
+               void* rootBox /* [4]: box + origin region out */, const float* camPos, float* etaNode, uint32_t* parent, unsigned int* arrivals);
 void launch_pack_prims(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* mats, uint32_t M,
                        void* ptris, void* psphs, void* sphMat, void* pmats);
 

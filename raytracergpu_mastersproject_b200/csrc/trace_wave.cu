@@ -257,9 +257,9 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             if (COUNT) { tl.rays++; tl.visits++; }
             if (CULL) update_segment();                                                    // closest = tMax: nothing is culled yet
             const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
-            if (NODES >= 3) {   // the slack the records were grown by covers rays that start inside the scene's box (+ 0.1 %): others are not culled
-                const float grow = 1.0e-3f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
-                cullOk = cullAllowed && o.x >= lo.x - grow && o.x <= hi.x + grow && o.y >= lo.y - grow && o.y <= hi.y + grow && o.z >= lo.z - grow && o.z <= hi.z + grow;
+            if (NODES >= 3) {   // the slack the records were grown by covers rays that start inside the origin region (bvh_build.cu): others are not culled
+                const float4 rl = __ldg(sc.rootBox + 2), rh = __ldg(sc.rootBox + 3);
+                cullOk = cullAllowed && o.x >= rl.x && o.x <= rh.x && o.y >= rl.y && o.y <= rh.y && o.z >= rl.z && o.z <= rh.z;
             }
             if (box_test(o, d, rinv, exactOnly, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) {
                 if (sc.N == 1) enqueue(0u);                                                // the root is the only leaf
@@ -390,8 +390,8 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
             const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
             if (COUNT && lane == 0) { tl.tailRays++; if (!(resume & 1u)) tl.rays++; }   // a resumed ray was counted by the launch that started it
             if (!needExact && ((resume & 1u) || box_test(o, d, rinv, false, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z))) {
-                const float grow = 1.0e-3f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
-                const bool cullOk = *p.cullAllowed != 0u && o.x >= lo.x - grow && o.x <= hi.x + grow && o.y >= lo.y - grow && o.y <= hi.y + grow && o.z >= lo.z - grow && o.z <= hi.z + grow;
+                const float4 rl = __ldg(sc.rootBox + 2), rh = __ldg(sc.rootBox + 3);      // origin region of the t-culled walk (bvh_build.cu)
+                const bool cullOk = *p.cullAllowed != 0u && o.x >= rl.x && o.x <= rh.x && o.y >= rl.y && o.y <= rh.y && o.z >= rl.z && o.z <= rh.z;
                 float closest = T_MAX_RAY, best = T_MAX_RAY;              // lane-local closest hit; warp-wide culling bound
                 bool poison = false, fit = true;
                 uint32_t n = 1;

@@ -92,3 +92,57 @@ def make_ubo(scene, max_depth=8, random_state=12345, vfov=40.0):
     u["numMaterials"] = len(scene["materials"]); u["numLights"] = 20
     u["maxRayTraceDepth"] = max_depth; u["randomState"] = random_state
     return u
+
+
+def fuzz_scene(seed):
+    """Adversarial scene for the nearest-first / t-culled walk (tests/test_gpu_fuzz.py): a cloud of triangles and spheres of mixed
+    sizes placed far from the origin (|coordinate| up to ~1e6, where the hit-point slack's 1e-5 R term matters), with slivers
+    (angles down to 1e-6), exactly coincident and nested / overlapping spheres, duplicate primitives (equal-t ties) and one big
+    light.  Returns (scene, camera positions): one camera outside the scene box and one inside."""
+    rng = np.random.default_rng(1000 + seed)
+    off_mag = [0.0, 1.0e4, 1.0e5, 1.0e6][seed % 4]
+    ext = max(300.0, off_mag * 0.02) * rng.uniform(0.5, 2.0)                 # scene extent
+    offset = rng.uniform(-1, 1, 3); offset = offset / np.linalg.norm(offset) * off_mag
+    nt, ns = int(rng.integers(40, 400)), int(rng.integers(0, 60))
+    mats = [((15, 15, 15), 0), ((0.7, 0.7, 0.7), 1), ((0.6, 0.2, 0.2), 1), ((0.2, 0.6, 0.3), 1), ((0.8, 0.8, 0.2), 2 if seed % 3 == 0 else 1)]
+    T = np.zeros(nt + 2, O.TRIANGLE); S = np.zeros(ns, O.SPHERE)
+    c = offset + rng.uniform(-0.5, 0.5, (nt, 3)) * ext
+    size = ext * 10.0 ** rng.uniform(-3.0, -0.5, (nt, 1))
+    v0 = c + rng.normal(size=(nt, 3)) * size; v1 = c + rng.normal(size=(nt, 3)) * size; v2 = c + rng.normal(size=(nt, 3)) * size
+    sl = rng.random(nt) < 0.25                                               # slivers: v2 almost on the line v0-v1
+    # two seeds of three keep every needle above the 1e-4 rad below which eta_leaf_kernel gives up (eta = inf disables t-culling for
+    # the whole scene); every third seed goes down to 1e-6 rad and exercises exactly that fallback
+    ang = 10.0 ** (rng.uniform(-6, -2, (nt, 1)) if seed % 3 == 2 else rng.uniform(-2.7, -1, (nt, 1)))
+    v2 = np.where(sl[:, None], v0 + (v1 - v0) * rng.uniform(0.2, 0.8, (nt, 1)) + rng.normal(size=(nt, 3)) * size * ang, v2)
+    dup = rng.random(nt) < 0.1                                               # duplicates of the previous triangle: equal-t ties
+    for k in np.nonzero(dup)[0]:
+        if k > 0:
+            v0[k], v1[k], v2[k] = v0[k - 1], v1[k - 1], v2[k - 1]
+    T["v0"][:nt, :3] = v0; T["v1"][:nt, :3] = v1; T["v2"][:nt, :3] = v2
+    T["materialIndex"][:nt] = rng.integers(1, len(mats), nt)
+    lo, hi = offset - 0.55 * ext, offset + 0.55 * ext                        # a light quad above the cloud
+    T["v0"][nt, :3] = (lo[0], hi[1], lo[2]); T["v1"][nt, :3] = (hi[0], hi[1], lo[2]); T["v2"][nt, :3] = (hi[0], hi[1], hi[2])
+    T["v0"][nt + 1, :3] = (lo[0], hi[1], lo[2]); T["v1"][nt + 1, :3] = (hi[0], hi[1], hi[2]); T["v2"][nt + 1, :3] = (lo[0], hi[1], hi[2])
+    if ns:
+        sc_ = offset + rng.uniform(-0.45, 0.45, (ns, 3)) * ext
+        sr = ext * 10.0 ** rng.uniform(-2.5, -0.7, ns)
+        for k in range(1, ns):
+            m = rng.random()
+            if m < 0.2:   sc_[k] = sc_[k - 1]; sr[k] = sr[k - 1] * rng.uniform(0.3, 0.95)      # nested, concentric
+            elif m < 0.3: sc_[k] = sc_[k - 1]; sr[k] = sr[k - 1]                                # coincident
+            elif m < 0.5: sc_[k] = sc_[k - 1] + rng.normal(size=3) * sr[k - 1] * 0.5            # overlapping
+        S["center"][:, :3] = sc_; S["radius"] = sr; S["materialIndex"] = rng.integers(1, len(mats), ns)
+    M = np.zeros(1, O.MODEL); M["m"][0] = np.eye(4, dtype=np.float32).reshape(16)
+    MT = np.zeros(len(mats), O.MATERIAL)
+    for i, (a, t) in enumerate(mats):
+        MT["albedo"][i, :3] = a; MT["materialType"][i] = t
+    scene = dict(models=M, triangles=T, spheres=S, materials=MT)
+    d = rng.normal(size=3); d /= np.linalg.norm(d)
+    cams = [(offset + d * ext * 1.6, offset), (offset + rng.uniform(-0.2, 0.2, 3) * ext, offset + d * ext)]
+    return scene, cams
+
+
+def ubo_with_camera(scene, cam, look, max_depth=16, random_state=7, vfov=50.0):
+    u = make_ubo(scene, max_depth=max_depth, random_state=random_state, vfov=vfov)
+    u["camPos"][0, :3] = np.float32(cam); u["camLookAt"][0, :3] = np.float32(look)
+    return u

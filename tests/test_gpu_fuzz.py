@@ -1,0 +1,88 @@
+"""GPU: randomized hardening of the nearest-first, t-culled walk (trace_wave.cu wave_step_u / trace_tail_kernel).
+
+The walk drops record entries whose slab interval lies beyond the closest hit so far; that is sound only because the record boxes
+were grown by the hit-point slack eta (bvh_build.cu eta_leaf_kernel), whose constants were derived by hand.  Two checks over
+240 seeded adversarial scenes (tests/scene_util.py fuzz_scene: |coordinate| up to 1e6, slivers down to 1e-6 rad, nested /
+coincident / overlapping spheres, duplicated triangles, depth 16, cameras outside and inside the scene box):
+  1. the frame of the culled walk equals the frame of the exact-record walk in the reference's order, bit for bit;
+  2. every primary hit the exact walk accepts lies within the eta the library computed for that primitive of the primitive's
+     reference leaf box (the property the culling argument rests on), checked on the host from the exported eta values.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import scene_util as SU
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+W, H, SPP = 40, 28, 3
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _primary_dirs(ubo, W, H):
+    """primary rays as make_camera / primary_direction evaluate them (binary32, the shader's operation order)"""
+    f = np.float32
+    cam = ubo["camPos"][0, :3].astype(f); look = ubo["camLookAt"][0, :3].astype(f); up = ubo["camUpDir"][0, :3].astype(f)
+    nrm = lambda v: (v / np.sqrt(f(f(v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]), dtype=f)).astype(f)  # noqa: E731
+    cross = lambda a, b: np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], f)  # noqa: E731
+    theta = f(ubo["verticalFOV"][0]) * f(0.017453292519943295)
+    h = f(np.tan(theta / f(2), dtype=f))
+    vh = f(f(2) * h * f(10)); vw = f(vh * f(f(W) / f(H)))
+    w_ = nrm(cam - look); u_ = nrm(cross(up, w_)); v_ = cross(w_, u_)
+    vu = (vw * u_).astype(f); vv = (vh * (-v_)).astype(f)
+    du = (vu / f(W)).astype(f); dv = (vv / f(H)).astype(f)
+    ul = (((cam - f(10) * w_) - vu / f(2)) - vv / f(2)).astype(f)
+    p00 = (ul + f(0.5) * (du + dv)).astype(f)
+    xs = np.arange(W, dtype=f)[None, :, None]; ys = np.arange(H, dtype=f)[:, None, None]
+    ps = ((p00 + xs * du) + ys * dv).astype(f) - cam
+    n1 = (ps / np.sqrt(((ps[..., 0] * ps[..., 0] + ps[..., 1] * ps[..., 1]) + ps[..., 2] * ps[..., 2]).astype(f))[..., None]).astype(f)
+    return cam, n1
+
+
+@pytest.mark.parametrize("block", range(12))
+def test_culled_walk_equals_exact_walk_and_hits_stay_within_eta(device, block):
+    from raytracergpu_mastersproject_b200 import Buffer, Raytracer, capi
+    L = capi.lib()
+    checked_hits = culled_scenes = 0
+    for seed in range(block * 20, block * 20 + 20):
+        sc, cams = SU.fuzz_scene(seed)
+        T, S = len(sc["triangles"]), len(sc["spheres"]); N = T + S
+        for ci, (cam, look) in enumerate(cams):
+            ubo = SU.ubo_with_camera(sc, cam, look, max_depth=16, random_state=seed + 1)
+            rt = Raytracer(device, W, H)
+            rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+            rt.build_bvh(ubo)
+            hp = Buffer(device, 4, W * H); ht = Buffer(device, 4, W * H)
+            rt.clear_image(); rt.raytrace(ubo, SPP, flags=capi.TRACE_EXACT_NODES | capi.TRACE_NO_PRIMARY_SHARING, hit_prim=hp, hit_t=ht); device.wait_idle()
+            exact = rt.read_image(); prim = hp.read(np.uint32).reshape(H, W); t = ht.read(np.float32).reshape(H, W)
+            for fl in (capi.TRACE_WIDE_NODES, capi.TRACE_WIDE_NODES | capi.TRACE_NO_PRIMARY_SHARING):
+                rt.clear_image(); rt.raytrace(ubo, SPP, flags=fl); device.wait_idle()
+                got = rt.read_image()
+                bad = int((_bits(got) != _bits(exact)).any(axis=-1).sum())
+                assert bad == 0, f"seed {seed} camera {ci} flags {fl}: {bad} pixels differ from the exact-record walk"
+            # (2) accepted primary hits within eta of their leaf box
+            eta = np.zeros(N, np.float32); region = np.zeros(6, np.float32)
+            capi.check(L.rtb_export_hit_slack(device.handle, eta.ctypes.data_as(C.c_void_p), N, region.ctypes.data_as(C.c_void_p)))
+            nodes = rt.nodes.read(O.NODE, 2 * N - 1)
+            o, dirs = _primary_dirs(ubo, W, H)
+            inside = bool(np.all(o >= region[:3]) and np.all(o <= region[3:]))
+            hit = prim != 0xFFFFFFFF
+            culled_scenes += int(np.isfinite(eta).all())
+            hit &= np.isfinite(eta)[np.minimum(prim, N - 1)]
+            if not inside or not hit.any():
+                continue
+            g = prim[hit].astype(np.int64)
+            P = o[None, :].astype(np.float64) + t[hit][:, None].astype(np.float64) * dirs[hit].astype(np.float64)
+            box = nodes["aabb"][N - 1 + g].astype(np.float64)                       # minX maxX minY maxY minZ maxZ
+            lo, hi = box[:, 0::2], box[:, 1::2]
+            dist = np.max(np.maximum(np.maximum(lo - P, P - hi), 0.0), axis=1)
+            worst = dist - eta[g].astype(np.float64)
+            assert np.all(worst <= 0), (f"seed {seed} camera {ci}: an accepted hit lies {dist[np.argmax(worst)]:.3e} outside its leaf box, "
+                                        f"eta = {eta[g][np.argmax(worst)]:.3e}")
+            checked_hits += int(hit.sum())
+    assert checked_hits > 1000 and culled_scenes >= 20, (checked_hits, culled_scenes)    # most scenes really run the t-culled walk
