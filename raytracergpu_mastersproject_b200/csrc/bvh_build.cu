@@ -68,6 +68,8 @@ __global__ void enclosing_init_kernel(uint32_t* red, int initInf) {
     const float hi = initInf ? __int_as_float(0xff800000) : 0.0f;
     if (threadIdx.x < 3) red[threadIdx.x] = f2ord(lo);
     else if (threadIdx.x < 6) red[threadIdx.x] = f2ord(hi);
+    else if (threadIdx.x < 9) red[threadIdx.x] = 0xFFFFFFFFu;       // [6..11]: bounds of the primitives (fused build only)
+    else if (threadIdx.x < 12) red[threadIdx.x] = 0u;
 }
 
 __global__ void __launch_bounds__(256) enclosing_reduce_kernel(const float4* __restrict__ tris, uint32_t T,
@@ -91,6 +93,58 @@ __global__ void __launch_bounds__(256) enclosing_reduce_kernel(const float4* __r
             if (lo[k] != 0xFFFFFFFFu) atomicMin(&red[k], lo[k]);
             if (hi[k] != 0u) atomicMax(&red[3 + k], hi[k]);
         }
+    }
+}
+
+// Fused S1 front end of rtb_build_bvh: K1 (transform in place) and K2's reduction in ONE pass over the primitives -- the centroid
+// is taken from the values just stored, so the reduction sees exactly what enclosing_reduce_kernel would read back.  Also reduces
+// the bounds of the primitives themselves into red[6..11] (the origin region / R of the hit-point slack, eta_leaf below, without
+// waiting for the refit to produce the root box).  Block-level reduction first: 12 atomics per block.
+__global__ void __launch_bounds__(256) model_to_world_enclosing_kernel(const float4* __restrict__ models, float4* tris, uint32_t T,
+                                                                       float4* sphs, uint32_t S, uint32_t* red) {
+    __shared__ uint32_t sm[12][8];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v[12] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };
+    if (i < T + S) {
+        f3 c, bl, bh;
+        if (i < T) {
+            float4* t = tris + 4ull * i;
+            const uint4 idx = *reinterpret_cast<const uint4*>(t + 3);
+            const float4* m = models + 4ull * idx.y;
+            const float4 c0 = __ldg(m), c1 = __ldg(m + 1), c2 = __ldg(m + 2), c3 = __ldg(m + 3);
+            const float4 a = mat_mul_point(c0, c1, c2, c3, t[0]), b = mat_mul_point(c0, c1, c2, c3, t[1]), d = mat_mul_point(c0, c1, c2, c3, t[2]);
+            t[0] = a; t[1] = b; t[2] = d;
+            c = F3(((a.x + b.x) + d.x) / 3.0f, ((a.y + b.y) + d.y) / 3.0f, ((a.z + b.z) + d.z) / 3.0f);      // getTriangleCenter :40-42
+            bl = F3(fminf(a.x, fminf(b.x, d.x)), fminf(a.y, fminf(b.y, d.y)), fminf(a.z, fminf(b.z, d.z)));
+            bh = F3(fmaxf(a.x, fmaxf(b.x, d.x)), fmaxf(a.y, fmaxf(b.y, d.y)), fmaxf(a.z, fmaxf(b.z, d.z)));
+        } else {
+            float4* s = sphs + 2ull * (i - T);
+            const uint4 idx = *reinterpret_cast<const uint4*>(s + 1);
+            const float4* m = models + 4ull * idx.z;
+            const float4 a = mat_mul_point(__ldg(m), __ldg(m + 1), __ldg(m + 2), __ldg(m + 3), s[0]);
+            s[0] = a;
+            c = xyz(a);
+            const float r = fabsf(__uint_as_float(idx.x));
+            bl = F3(a.x - r, a.y - r, a.z - r); bh = F3(a.x + r, a.y + r, a.z + r);
+        }
+        v[0] = f2ord(c.x); v[1] = f2ord(c.y); v[2] = f2ord(c.z); v[3] = v[0]; v[4] = v[1]; v[5] = v[2];
+        v[6] = f2ord(bl.x); v[7] = f2ord(bl.y); v[8] = f2ord(bl.z); v[9] = f2ord(bh.x); v[10] = f2ord(bh.y); v[11] = f2ord(bh.z);
+    }
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        const bool isMin = (k % 6) < 3;
+        const uint32_t r = isMin ? __reduce_min_sync(0xFFFFFFFFu, v[k]) : __reduce_max_sync(0xFFFFFFFFu, v[k]);
+        if (lane == 0) sm[k][warp] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const int k = threadIdx.x;
+        const bool isMin = (k % 6) < 3;
+        uint32_t r = sm[k][0];
+        for (int w = 1; w < 8; w++) r = isMin ? min(r, sm[k][w]) : max(r, sm[k][w]);
+        if (isMin) { if (r != 0xFFFFFFFFu) atomicMin(&red[k], r); }
+        else if (r != 0u) atomicMax(&red[k], r);
     }
 }
 
@@ -180,30 +234,77 @@ __device__ __forceinline__ void pad_axis(float& lo, float& hi) {          // pad
     if (hi - lo < 0.001f) { lo -= 0.0005f; hi += 0.0005f; }
 }
 
+// Optional by-products of the K5 leaf pass in the fused build (rtb_build_bvh): the thread that builds leaf g already holds the
+// primitive, so it also writes the exact leaf box, the packed primitive record (pack_prims_kernel's) and the primitive's hit-point
+// slack (eta_leaf_kernel's, with the origin region taken from the primitive bounds model_to_world_enclosing_kernel reduced).
+struct LeafExtras {
+    float4* leafBox;            // [N][2]
+    float4* ptris; float4* psphs; uint32_t* sphMat;
+    float* etaNode;             // [2N-1]: leaf values at [N-1+g]
+    const uint32_t* primBounds; // ordered-int min.xyz, max.xyz of all primitives (red[6..11])
+    float4* originRegion;       // [2]
+    f3 cam;
+};
+__device__ __forceinline__ float eta_triangle(const f3 u, const f3 v, const f3 w, const float R);
+__device__ __forceinline__ float eta_sphere(const float4 sp, const float4 lo, const float4 hi, const float R);
+__device__ __forceinline__ void origin_region_of(float4 lo, float4 hi, const f3 cam, float4& rlo, float4& rhi);
+
+template <bool EXTRAS>
 __global__ void __launch_bounds__(256) hlbvh_kernel(const float4* __restrict__ tris, uint32_t T, const float4* __restrict__ sphs,
-                                                    uint32_t S, Codes codes, uint32_t* nodes /*10 words each*/, uint2* cinfo) {
+                                                    uint32_t S, Codes codes, uint32_t* nodes /*10 words each*/, uint2* cinfo, const LeafExtras ex) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = (int)(T + S);
     const int leafOffset = n - 1;
     if (g < (uint32_t)n) {  // leaf :152-169
         float mnx, mxx, mny, mxy, mnz, mxz;
         uint32_t type, prim;
+        float4 rlo, rhi; float R = 0.f;
+        if (EXTRAS) {
+            // bounds of all primitives, padded like a leaf box can be (padAABB), -> origin region and R
+            const float4 pl = make_float4(ord2f(ex.primBounds[0]) - 0.0005f, ord2f(ex.primBounds[1]) - 0.0005f, ord2f(ex.primBounds[2]) - 0.0005f, 0.f);
+            const float4 ph = make_float4(ord2f(ex.primBounds[3]) + 0.0005f, ord2f(ex.primBounds[4]) + 0.0005f, ord2f(ex.primBounds[5]) + 0.0005f, 0.f);
+            origin_region_of(pl, ph, ex.cam, rlo, rhi);
+            if (g == 0) { ex.originRegion[0] = rlo; ex.originRegion[1] = rhi; }
+            R = fmaxf(fmaxf(fmaxf(fabsf(rlo.x), fabsf(rhi.x)), fmaxf(fabsf(rlo.y), fabsf(rhi.y))), fmaxf(fabsf(rlo.z), fabsf(rhi.z)));
+        }
         if (g < T) {        // getTriangleAABB :132-143 : min(v0, min(v1, v2))
             const float4 a = tris[4ull * g], b = tris[4ull * g + 1], c = tris[4ull * g + 2];
             mnx = gmin(a.x, gmin(b.x, c.x)); mxx = gmax(a.x, gmax(b.x, c.x));
             mny = gmin(a.y, gmin(b.y, c.y)); mxy = gmax(a.y, gmax(b.y, c.y));
             mnz = gmin(a.z, gmin(b.z, c.z)); mxz = gmax(a.z, gmax(b.z, c.z));
             type = RTB_TRIANGLE_PRIMITIVE; prim = g;
+            if (EXTRAS) {   // pack_prims_kernel's triangle record: triangleHit's ray-independent prologue, same operation order
+                const uint4 idx = *reinterpret_cast<const uint4*>(tris + 4ull * g + 3);
+                const f3 v0 = xyz(a), u = xyz(b) - v0, v = xyz(c) - v0;
+                const f3 nU = cross(u, v);
+                const f3 nn = normalize(nU);
+                const f3 w = nU / dot(nU, nU);
+                ex.ptris[4ull * g] = make_float4(v0.x, v0.y, v0.z, __uint_as_float(idx.x));
+                ex.ptris[4ull * g + 1] = make_float4(nn.x, nn.y, nn.z, u.x);
+                ex.ptris[4ull * g + 2] = make_float4(u.y, u.z, v.x, v.y);
+                ex.ptris[4ull * g + 3] = make_float4(v.z, w.x, w.y, w.z);
+                ex.etaNode[leafOffset + (int)g] = eta_triangle(u, v, w, R);
+            }
         } else {            // getSphereAABB :117-130
             const float4 c = sphs[2ull * (g - T)];
-            const float r = sphs[2ull * (g - T) + 1].x;
+            const float4 rr = sphs[2ull * (g - T) + 1];
+            const float r = rr.x;
             const float lx = c.x - r, ly = c.y - r, lz = c.z - r, rx = c.x + r, ry = c.y + r, rz = c.z + r;
             mnx = gmin(lx, rx); mxx = gmax(lx, rx);
             mny = gmin(ly, ry); mxy = gmax(ly, ry);
             mnz = gmin(lz, rz); mxz = gmax(lz, rz);
             type = RTB_SPHERE_PRIMITIVE; prim = g - T;
+            if (EXTRAS) {
+                ex.psphs[g - T] = make_float4(c.x, c.y, c.z, r);
+                ex.sphMat[g - T] = __float_as_uint(rr.y);
+                ex.etaNode[leafOffset + (int)g] = eta_sphere(make_float4(c.x, c.y, c.z, r), rlo, rhi, R);
+            }
         }
         pad_axis(mnx, mxx); pad_axis(mny, mxy); pad_axis(mnz, mxz);
+        if (EXTRAS) {
+            ex.leafBox[2ull * g] = make_float4(mnx, mny, mnz, 0.f);
+            ex.leafBox[2ull * g + 1] = make_float4(mxx, mxy, mxz, 0.f);
+        }
         uint32_t* nd = nodes + 10ull * (uint32_t)(leafOffset + (int)g);   // 40-byte records: 8-byte aligned
         reinterpret_cast<float2*>(nd)[0] = make_float2(mnx, mxx);
         reinterpret_cast<float2*>(nd)[1] = make_float2(mny, mxy);
@@ -254,7 +355,7 @@ __global__ void __launch_bounds__(256) hlbvh_kernel(const float4* __restrict__ t
 // children.  The shader relies on `coherent`; here: L2-scoped loads (__ldcg) + __threadfence() before the
 // counter atomic.  fp min/max of fixed operands (left, right) -> deterministic whatever the arrival order.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinfo, uint32_t n, float4* pairs, float4* rootBox) {
+__global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinfo, uint32_t n, float4* pairs, float4* rootBox, float* etaNode) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const uint32_t leafOffset = n - 1;
@@ -273,6 +374,7 @@ __global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinf
         __stcg(reinterpret_cast<float2*>(nd), make_float2(gmin(lx.x, rx.x), gmax(lx.y, rx.y)));
         __stcg(reinterpret_cast<float2*>(nd) + 1, make_float2(gmin(ly.x, ry.x), gmax(ly.y, ry.y)));
         __stcg(reinterpret_cast<float2*>(nd) + 2, make_float2(gmin(lz.x, rz.x), gmax(lz.y, rz.y)));
+        if (etaNode) __stcg(&etaNode[nodeId], fmaxf(__ldcg(&etaNode[ch.x]), __ldcg(&etaNode[ch.y])));   // largest hit-point slack of the subtree
         if (pairs) {    // the thread that unions a node holds both child boxes: emit the node's 64-byte traversal record here
             float4* out = pairs + 4ull * nodeId;
             out[0] = make_float4(lx.x, ly.x, lz.x, __uint_as_float(ch.x));
@@ -390,8 +492,7 @@ __global__ void __launch_bounds__(256) pack_cnodes_kernel(const uint32_t* __rest
 // when that at most quadruples R (a camera far away from a small scene would inflate every record box; its rays then simply stay
 // un-culled, as rays from outside Omega always do).  The kernel stores Omega in originRegion[0..1]; the trace kernels cull a ray
 // by t only if its origin lies inside it.
-__device__ __forceinline__ void origin_region(const float4* __restrict__ rootBox, const f3 cam, float4& lo, float4& hi) {
-    lo = rootBox[0]; hi = rootBox[1];
+__device__ __forceinline__ void origin_region_of(float4 lo, float4 hi, const f3 cam, float4& rlo, float4& rhi) {
     const float grow = 1.0e-3f * fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
     lo.x -= grow; lo.y -= grow; lo.z -= grow; hi.x += grow; hi.y += grow; hi.z += grow;
     const float R = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
@@ -400,6 +501,23 @@ __device__ __forceinline__ void origin_region(const float4* __restrict__ rootBox
         lo.x = fminf(lo.x, cam.x); lo.y = fminf(lo.y, cam.y); lo.z = fminf(lo.z, cam.z);
         hi.x = fmaxf(hi.x, cam.x); hi.y = fmaxf(hi.y, cam.y); hi.z = fmaxf(hi.z, cam.z);
     }
+    rlo = lo; rhi = hi;
+}
+__device__ __forceinline__ float eta_triangle(const f3 u, const f3 v, const f3 w, const float R) {
+    const float lu = sqrtf(dot(u, u)), lv = sqrtf(dot(v, v)), lw = sqrtf(dot(w, w));
+    const float invSin = lu * lv * lw;
+    float eta = 64.0f * 5.9604645e-8f * (1.0f + invSin) * lw * lu * lv * (lu + lv) + 1.0e-5f * R;
+    if (!(invSin < 1.0e4f) || !(lw < 1.0e18f)) eta = __int_as_float(0x7f800000);
+    if (!(eta < 3.0e38f)) eta = __int_as_float(0x7f800000);               // NaN / overflow
+    return eta;
+}
+__device__ __forceinline__ float eta_sphere(const float4 sp, const float4 lo, const float4 hi, const float R) {
+    const float dx = fmaxf(fabsf(sp.x - lo.x), fabsf(hi.x - sp.x)), dy = fmaxf(fabsf(sp.y - lo.y), fabsf(hi.y - sp.y)),
+                dz = fmaxf(fabsf(sp.z - lo.z), fabsf(hi.z - sp.z));
+    const float r = fabsf(sp.w), D = sqrtf(dx * dx + dy * dy + dz * dz) + r;
+    float eta = 4.0e-6f * D * D / r + 1.0e-5f * R;
+    if (!(eta < 3.0e38f)) eta = __int_as_float(0x7f800000);               // NaN / overflow
+    return eta;
 }
 __global__ void __launch_bounds__(256) eta_leaf_kernel(const float4* __restrict__ ptris, uint32_t T, const float4* __restrict__ psphs,
                                                        uint32_t S, const float4* __restrict__ rootBox, const f3 cam, float* etaLeaf,
@@ -407,25 +525,16 @@ __global__ void __launch_bounds__(256) eta_leaf_kernel(const float4* __restrict_
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= T + S) return;
     float4 lo, hi;
-    origin_region(rootBox, cam, lo, hi);
+    origin_region_of(rootBox[0], rootBox[1], cam, lo, hi);
     if (g == 0) { originRegion[0] = lo; originRegion[1] = hi; }
     const float R = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
     float eta;
     if (g < T) {
         const float4 r1 = ptris[4ull * g + 1], r2 = ptris[4ull * g + 2], r3 = ptris[4ull * g + 3];
-        const f3 u = F3(r1.w, r2.x, r2.y), v = F3(r2.z, r2.w, r3.x), w = F3(r3.y, r3.z, r3.w);
-        const float lu = sqrtf(dot(u, u)), lv = sqrtf(dot(v, v)), lw = sqrtf(dot(w, w));
-        const float invSin = lu * lv * lw;
-        eta = 64.0f * 5.9604645e-8f * (1.0f + invSin) * lw * lu * lv * (lu + lv) + 1.0e-5f * R;
-        if (!(invSin < 1.0e4f) || !(lw < 1.0e18f)) eta = __int_as_float(0x7f800000);
+        eta = eta_triangle(F3(r1.w, r2.x, r2.y), F3(r2.z, r2.w, r3.x), F3(r3.y, r3.z, r3.w), R);
     } else {
-        const float4 sp = psphs[g - T];
-        const float dx = fmaxf(fabsf(sp.x - lo.x), fabsf(hi.x - sp.x)), dy = fmaxf(fabsf(sp.y - lo.y), fabsf(hi.y - sp.y)),
-                    dz = fmaxf(fabsf(sp.z - lo.z), fabsf(hi.z - sp.z));
-        const float r = fabsf(sp.w), D = sqrtf(dx * dx + dy * dy + dz * dz) + r;
-        eta = 4.0e-6f * D * D / r + 1.0e-5f * R;
+        eta = eta_sphere(psphs[g - T], lo, hi, R);
     }
-    if (!(eta < 3.0e38f)) eta = __int_as_float(0x7f800000);               // NaN / overflow
     etaLeaf[g] = eta;
 }
 __global__ void __launch_bounds__(256) parent_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint32_t* parent) {
@@ -533,6 +642,37 @@ __global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restri
     for (int j = 0; j < 4; j++) out[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
 }
 
+#ifdef RTB_SMEM_TOP
+// A/B variant "top tree levels staged in shared memory": the first RTB_SMEM_TOP records of the 4-ary hierarchy in breadth-first
+// order, copied into a table whose internal entry ids are replaced by TOP_FLAG | table index when the entry is in the table too.
+// One thread (sequential breadth-first queue): measurement aid, not tuned.
+__global__ void build_top_table_kernel(const uint4* __restrict__ wide, uint32_t n, uint4* top, uint32_t* topGlobal) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const uint32_t leafOffset = n - 1;
+    uint32_t count = 1;
+    topGlobal[0] = 0;
+    for (uint32_t i = 0; i < RTB_SMEM_TOP; i++) {
+        if (i >= count) { for (int j = 0; j < 4; j++) top[4 * i + j] = make_uint4(0, 0, 0, 0); topGlobal[i] = 0; continue; }
+        uint4 r[4];
+        for (int j = 0; j < 4; j++) r[j] = wide[4ull * topGlobal[i] + j];
+        const uint32_t meta = r[0].w >> 24;
+        uint32_t ids[4] = { r[2].z, r[2].w, r[3].x, r[3].y };
+        for (int e = 0; e < 4; e++) {
+            const bool present = (meta >> (4 + e)) & 1u, leaf = (meta >> e) & 1u;
+            if (!present || leaf || ids[e] >= leafOffset || count >= RTB_SMEM_TOP) continue;
+            topGlobal[count] = ids[e];
+            ids[e] = 0x80000000u | count;
+            count++;
+        }
+        r[2].z = ids[0]; r[2].w = ids[1]; r[3].x = ids[2]; r[3].y = ids[3];
+        for (int j = 0; j < 4; j++) top[4 * i + j] = r[j];
+    }
+}
+void launch_build_top_table(cudaStream_t st, const void* wide, uint32_t n, void* top, void* topGlobal) {
+    build_top_table_kernel<<<1, 32, 0, st>>>((const uint4*)wide, n, (uint4*)top, (uint32_t*)topGlobal);
+}
+#endif
+
 __global__ void __launch_bounds__(256) pack_prims_kernel(const float4* __restrict__ tris, uint32_t T, const float4* __restrict__ sphs,
                                                          uint32_t S, const float4* __restrict__ mats, uint32_t M, float4* ptris,
                                                          float4* psphs, uint32_t* sphMat, float4* pmats) {
@@ -599,11 +739,30 @@ void launch_morton_repack(cudaStream_t st, const uint32_t* keys, const uint32_t*
 void launch_hlbvh(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const uint32_t* codes,
                   uint32_t codeStrideWords, void* nodes, void* cinfo) {
     Codes c{ codes, codeStrideWords, (int)(T + S) };
-    hlbvh_kernel<<<blocks_for((uint64_t)T + S, 256), 256, 0, st>>>((const float4*)tris, T, (const float4*)sphs, S, c,
-                                                                   (uint32_t*)nodes, (uint2*)cinfo);
+    LeafExtras none{};
+    hlbvh_kernel<false><<<blocks_for((uint64_t)T + S, 256), 256, 0, st>>>((const float4*)tris, T, (const float4*)sphs, S, c,
+                                                                          (uint32_t*)nodes, (uint2*)cinfo, none);
 }
-void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox) {
-    refit_kernel<<<blocks_for(n, 256), 256, 0, st>>>((uint32_t*)nodes, (uint2*)cinfo, n, (float4*)pairs, (float4*)rootBox);
+// K5 of the fused build: also writes the exact leaf boxes, the packed primitive records and the per-primitive hit-point slack
+void launch_hlbvh_fused(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const uint32_t* codes, void* nodes,
+                        void* cinfo, void* leafBox, void* ptris, void* psphs, void* sphMat, float* etaNode, const uint32_t* primBounds,
+                        void* originRegion, const float* camPos) {
+    Codes c{ codes, 1, (int)(T + S) };
+    LeafExtras ex{ (float4*)leafBox, (float4*)ptris, (float4*)psphs, (uint32_t*)sphMat, etaNode, primBounds, (float4*)originRegion,
+                   F3(camPos[0], camPos[1], camPos[2]) };
+    hlbvh_kernel<true><<<blocks_for((uint64_t)T + S, 256), 256, 0, st>>>((const float4*)tris, T, (const float4*)sphs, S, c,
+                                                                         (uint32_t*)nodes, (uint2*)cinfo, ex);
+}
+void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox, float* etaNode) {
+    refit_kernel<<<blocks_for(n, 256), 256, 0, st>>>((uint32_t*)nodes, (uint2*)cinfo, n, (float4*)pairs, (float4*)rootBox, etaNode);
+}
+// K1 + K2 in one pass (fused build).  Returns #launches.
+int launch_model_to_world_enclosing(cudaStream_t st, const void* models, void* tris, uint32_t T, void* sphs, uint32_t S, uint32_t* red,
+                                    void* enclosing, int initInf) {
+    enclosing_init_kernel<<<1, 32, 0, st>>>(red, initInf);
+    model_to_world_enclosing_kernel<<<blocks_for((uint64_t)T + S, 256), 256, 0, st>>>((const float4*)models, (float4*)tris, T, (float4*)sphs, S, red);
+    enclosing_finalize_kernel<<<1, 32, 0, st>>>(red, (float4*)enclosing);
+    return 3;
 }
 void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pairs, void* rootBox) {
     const uint32_t work = n > 1 ? n - 1 : 1;

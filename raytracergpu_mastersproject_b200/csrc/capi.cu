@@ -49,7 +49,7 @@ Camera make_camera(const rtb_ubo* ubo, uint32_t W, uint32_t H) {
 }
 
 int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tris, const void* sphs, const void* mats, const void* nodes,
-                  bool pairsDone = false) {
+                  bool pairsDone = false, bool primsDone = false) {
     const uint32_t N = T + S;
     if (ensure(c, c->pairs, sizeof(float4) * 4ull * (N > 1 ? N - 1 : 1))) return 1;
     if (ensure(c, c->ptris, sizeof(float4) * 4ull * T)) return 1;
@@ -60,7 +60,8 @@ int bind_internal(rtb_ctx* c, uint32_t T, uint32_t S, uint32_t M, const void* tr
     if (ensure(c, c->workCounter, 32)) return 1;
     if (ensure(c, c->errFlag, 16)) return 1;
     if (nodes && !pairsDone) launch_pack_pairs(c->stream, nodes, N, c->pairs.p, c->rootBox.p);
-    launch_pack_prims(c->stream, tris, T, sphs, S, mats, M, c->ptris.p, c->psphs.p, c->psphMat.p, c->pmats.p);
+    if (primsDone) launch_pack_prims(c->stream, tris, 0, sphs, 0, mats, M, c->ptris.p, c->psphs.p, c->psphMat.p, c->pmats.p);   // materials only
+    else launch_pack_prims(c->stream, tris, T, sphs, S, mats, M, c->ptris.p, c->psphs.p, c->psphMat.p, c->pmats.p);
     c->boundNodesPtr = nodes;
     c->cnodesReady = false;                 // the compressed / wide records are derived on first use
     c->wideReady = false;
@@ -93,6 +94,10 @@ int derive_records(rtb_ctx* c, int nodesMode, const float* camPos) {
                             (float*)c->etaNode.p, (uint32_t*)c->etaParent.p, (unsigned int*)c->etaArrivals.p);
         launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wide.p, (const float*)c->etaNode.p, (unsigned int*)c->walkFlag.p);
         c->wideReady = true; extra++;
+#ifdef RTB_SMEM_TOP
+        if (ensure(c, c->topTable, 64ull * RTB_SMEM_TOP) || ensure(c, c->topGlobal, 4ull * RTB_SMEM_TOP)) return -1;
+        launch_build_top_table(c->stream, c->wide.p, c->bN, c->topTable.p, c->topGlobal.p); extra++;
+#endif
     }
     return extra;
 }
@@ -133,6 +138,15 @@ int rtb_ctx_create(int device, void* stream, rtb_ctx** out) {
     }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    // RTB_WAVE_TAIL_OVERLAP=1 (experimental, default off): trace_tail_kernel is additionally launched on a second stream beside the
+    // main trace launch, so that parked long rays are worked off while it drains.  Measured on B200 (profiles/r02_tail_overlap.txt):
+    // correct but slower (36.1 -> 62.4 ms per C2 frame), so the tail launch stays strictly behind the main launch.
+    const char* ovl = getenv("RTB_WAVE_TAIL_OVERLAP");
+    if (ovl && atoi(ovl) != 0) {
+        cudaStreamCreateWithFlags(&c->auxStream, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming);
+    }
     if (const char* e = getenv("RTB_WAVE_TMIN")) c->knobs.tMin = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_SORTED_PUSH")) c->knobs.sortedPush = atoi(e);
     if (const char* e = getenv("RTB_WAVE_QGATE")) c->knobs.qGate = (uint32_t)atoi(e);
@@ -151,11 +165,12 @@ int rtb_ctx_destroy(rtb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (Scratch* s : { &c->sortKeys[0], &c->sortKeys[1], &c->sortVals[0], &c->sortVals[1], &c->sortCounts, &c->encRed, &c->enclosing,
                         &c->cinfo, &c->nodes, &c->pairs, &c->ptris, &c->psphs, &c->psphMat, &c->pmats, &c->rootBox, &c->workCounter,
-                        &c->errFlag, &c->walkFlag, &c->gatherBuf, &c->bandRgba8, &c->etaNode, &c->etaParent, &c->etaArrivals, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->activeXY, &c->sampleBuf, &c->primaryHits, &c->poolSlot, &c->poolColor,
+                        &c->errFlag, &c->walkFlag, &c->topTable, &c->topGlobal, &c->gatherBuf, &c->bandRgba8, &c->etaNode, &c->etaParent, &c->etaArrivals, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->activeXY, &c->sampleBuf, &c->primaryHits, &c->poolSlot, &c->poolColor,
                         &c->poolAtt, &c->poolOrg, &c->poolDir, &c->poolNrm, &c->poolList, &c->poolCnt, &c->parkBuf })
         release(*s);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    if (c->auxStream) { cudaStreamSynchronize(c->auxStream); cudaStreamDestroy(c->auxStream); cudaEventDestroy(c->evFork); cudaEventDestroy(c->evJoin); }
     if (c->ownStream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -267,7 +282,7 @@ int rtb_model_to_world(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void*
 int rtb_enclosing_aabb(rtb_ctx* c, const rtb_ubo* ubo, void* enclosing, const void* triangles, const void* spheres, uint32_t flags) {
     REQUIRE(c && ubo && enclosing, "rtb_enclosing_aabb: bad argument");
     Activate act(c);
-    if (ensure(c, c->encRed, 32)) return 1;
+    if (ensure(c, c->encRed, 64)) return 1;
     const int n = launch_enclosing(c->stream, triangles, ubo->numTriangles, spheres, ubo->numSpheres, (uint32_t*)c->encRed.p, enclosing,
                                    (flags & RTB_TRACE_ENCLOSING_INF) ? 1 : 0, c->smCount);
     return check_launch(c, n, "enclosing_aabb kernels");
@@ -315,7 +330,7 @@ int rtb_build_hlbvh(rtb_ctx* c, const rtb_ubo* ubo, const void* triangles, const
 int rtb_refit_aabbs(rtb_ctx* c, const rtb_ubo* ubo, void* nodes, void* cinfo) {
     REQUIRE(c && ubo && nodes && cinfo, "rtb_refit_aabbs: bad argument");
     Activate act(c);
-    launch_refit(c->stream, nodes, cinfo, ubo->numTriangles + ubo->numSpheres, nullptr, nullptr);
+    launch_refit(c->stream, nodes, cinfo, ubo->numTriangles + ubo->numSpheres, nullptr, nullptr, nullptr);
     return check_launch(c, 1, "refit_kernel");
 }
 
@@ -330,11 +345,38 @@ int rtb_build_bvh(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void* tria
     if (!enclosing) { if (ensure(c, c->enclosing, 32)) return 1; enclosing = c->enclosing.p; }
     if (!cinfo) { if (ensure(c, c->cinfo, 8ull * (2ull * N - 1))) return 1; cinfo = c->cinfo.p; }
     if (!nodes) { if (ensure(c, c->nodes, 40ull * (2ull * N - 1))) return 1; nodes = c->nodes.p; }
-    if (ensure(c, c->encRed, 32)) return 1;
+    if (ensure(c, c->encRed, 64)) return 1;
     if (sort_scratch(c, N)) return 1;
     uint32_t *k0 = (uint32_t*)c->sortKeys[0].p, *k1 = (uint32_t*)c->sortKeys[1].p;
     uint32_t *v0 = (uint32_t*)c->sortVals[0].p, *v1 = (uint32_t*)c->sortVals[1].p;
     int launches = 0;
+    if (N >= WIDE_MIN_PRIMITIVES) {
+        // Fused build for scenes that are walked over the 4-ary records: K1 + K2 in one pass, the K5 leaf pass also emits the exact leaf
+        // boxes / packed primitives / per-primitive hit-point slack, the K6 climb also carries the slack and the child-pair records.
+        // The reference-layout outputs (nodes, morton1, enclosing, cinfo) are the same bits as the stage-by-stage entry points produce.
+        const size_t nn = 2ull * N - 1;
+        if (ensure(c, c->pairs, sizeof(float4) * 4ull * (N - 1)) || ensure(c, c->rootBox, sizeof(float4) * 4) || ensure(c, c->ptris, sizeof(float4) * 4ull * T) ||
+            ensure(c, c->psphs, sizeof(float4) * (size_t)S) || ensure(c, c->psphMat, sizeof(uint32_t) * (size_t)S) || ensure(c, c->leafBox, 32ull * N) ||
+            ensure(c, c->wide, 64ull * (N - 1)) || ensure(c, c->etaNode, 4 * nn) || ensure(c, c->walkFlag, 16)) return 1;
+        launches += launch_model_to_world_enclosing(c->stream, models, triangles, T, spheres, S, (uint32_t*)c->encRed.p, enclosing,
+                                                    (flags & RTB_TRACE_ENCLOSING_INF) ? 1 : 0);                   // K1 + K2
+        launch_morton(c->stream, triangles, T, spheres, S, enclosing, nullptr, k0, v0); launches++;              // K3 (SoA out)
+        launches += launch_radix_sort(c->stream, k0, v0, k1, v1, N, (uint32_t*)c->sortCounts.p);                  // K4
+        if (morton1) { launch_morton_repack(c->stream, k0, v0, N, T, morton1); launches++; }
+        launch_hlbvh_fused(c->stream, triangles, T, spheres, S, k0, nodes, cinfo, c->leafBox.p, c->ptris.p, c->psphs.p, c->psphMat.p,
+                           (float*)c->etaNode.p, (const uint32_t*)c->encRed.p + 6, (float4*)c->rootBox.p + 2, ubo->camPos); launches++;   // K5
+        launch_refit(c->stream, nodes, cinfo, N, c->pairs.p, c->rootBox.p, (float*)c->etaNode.p); launches++;    // K6 (+ pair records, slack)
+        if (check_launch(c, launches, "BVH build kernels")) return 1;
+        if (bind_internal(c, T, S, ubo->numMaterials, triangles, spheres, materials, nodes, /*pairsDone=*/true, /*primsDone=*/true)) return 1;
+        launch_pack_wide(c->stream, nodes, N, c->wide.p, (const float*)c->etaNode.p, (unsigned int*)c->walkFlag.p);
+        c->leafBoxReady = true; c->wideReady = true;
+#ifdef RTB_SMEM_TOP
+        if (ensure(c, c->topTable, 64ull * RTB_SMEM_TOP) || ensure(c, c->topGlobal, 4ull * RTB_SMEM_TOP)) return 1;
+        launch_build_top_table(c->stream, c->wide.p, N, c->topTable.p, c->topGlobal.p);
+        return check_launch(c, 2, "pack_wide_kernel");
+#endif
+        return check_launch(c, 1, "pack_wide_kernel");
+    }
     launch_model_to_world(c->stream, models, triangles, T, spheres, S); launches++;                             // K1
     launches += launch_enclosing(c->stream, triangles, T, spheres, S, (uint32_t*)c->encRed.p, enclosing,
                                  (flags & RTB_TRACE_ENCLOSING_INF) ? 1 : 0, c->smCount);                          // K2
@@ -344,15 +386,9 @@ int rtb_build_bvh(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void* tria
     launch_hlbvh(c->stream, triangles, T, spheres, S, k0, 1, nodes, cinfo); launches++;                           // K5
     if (ensure(c, c->pairs, sizeof(float4) * 4ull * (N > 1 ? N - 1 : 1))) return 1;
     if (ensure(c, c->rootBox, sizeof(float4) * 4)) return 1;
-    launch_refit(c->stream, nodes, cinfo, N, N > 1 ? c->pairs.p : nullptr, c->rootBox.p); launches++;            // K6 (+ pair records)
+    launch_refit(c->stream, nodes, cinfo, N, N > 1 ? c->pairs.p : nullptr, c->rootBox.p, nullptr); launches++;   // K6 (+ pair records)
     if (check_launch(c, launches, "BVH build kernels")) return 1;
-    if (bind_internal(c, T, S, ubo->numMaterials, triangles, spheres, materials, nodes, /*pairsDone=*/N > 1)) return 1;
-    if (N >= WIDE_MIN_PRIMITIVES) {      // the records the default walk of a scene of this size fetches belong to the build (S1), not to the first trace
-        const int extra = derive_records(c, 2, ubo->camPos);
-        if (extra < 0) return 1;
-        return check_launch(c, extra, "traversal record kernels");
-    }
-    return 0;
+    return bind_internal(c, T, S, ubo->numMaterials, triangles, spheres, materials, nodes, /*pairsDone=*/N > 1);
 }
 
 // ---- S2 --------------------------------------------------------------------------------------------------------
@@ -459,6 +495,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
             if (extra < 0) return 1;
             if (nodesMode) { p.sc.cnodes = nodesMode == 1 ? (const uint4*)c->cnodes.p : nullptr; p.sc.leafBox = (const float4*)c->leafBox.p; }
             if (nodesMode == 2) p.sc.wide = (const uint4*)c->wide.p;
+            p.sc.top = (const uint4*)c->topTable.p; p.sc.topGlobal = (const uint32_t*)c->topGlobal.p;
             if (nodesMode == 2 && !cull && !(a->flags & RTB_TRACE_REFERENCE_ORDER)) nodesMode = 3;
             p.cullAllowed = (const unsigned int*)c->walkFlag.p;
             p.primaryHits = nullptr; p.primaryMode = 0;
@@ -468,11 +505,15 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
             }
             if (nodesMode == 3 && (p.coopMax || p.coopTurns)) {      // parking is optional for a lane: a full buffer just means "walk it yourself"
                 const size_t cap = (size_t)c->smCount * 8 * 128;
-                if (ensure(c, c->parkBuf, cap * 15 * sizeof(float4))) return 1;
+                if (ensure(c, c->parkBuf, cap * 16 * sizeof(float4))) return 1;
                 p.parkBuf = (float4*)c->parkBuf.p; p.parkCapacity = (uint32_t)cap;
+                p.parkEpoch = c->parkEpoch;
+                c->parkEpoch += 2u * (uint32_t)((a->sampleCount + perPass - 1) / perPass);      // two parking launches per pass, one epoch each
                 p.parkCount = (unsigned int*)c->workCounter.p + 4; p.parkCursor = (unsigned int*)c->workCounter.p + 5;
-            } else { p.coopMax = 0; p.coopTurns = 0; }
-            launches = extra + launch_trace_wave(c->stream, p, count, ext, cull, nodesMode, c->smCount, (uint32_t)perPass);
+                p.doneWarps = (unsigned int*)c->workCounter.p + 6;
+            } else { p.coopMax = 0; p.coopTurns = 0; p.doneWarps = nullptr; }
+            const TailOverlap ov{ c->auxStream, c->evFork, c->evJoin };
+            launches = extra + launch_trace_wave(c->stream, p, count, ext, cull, nodesMode, c->smCount, (uint32_t)perPass, ov);
         }
     }
     c->traced = true;

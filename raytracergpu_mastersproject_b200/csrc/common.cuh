@@ -109,6 +109,8 @@ struct TraceScene {
     const uint4* __restrict__ cnodes;    // [N-1][2] 32-byte compressed child-pair records (conservative 8-bit boxes), or null
     const float4* __restrict__ leafBox;  // [N][2]   exact leaf boxes (min.xyz,0) (max.xyz,0), used with cnodes / wide
     const uint4* __restrict__ wide;      // [N-1][4] 64-byte 4-ary records (conservative 8-bit grandchild boxes), or null
+    const uint4* __restrict__ top;       // A/B build RTB_SMEM_TOP: [k][4] the first k records in breadth-first order, entry ids inside the table tagged
+    const uint32_t* __restrict__ topGlobal;   // [k] node index of each table record
     uint32_t T, S, N;
 };
 
@@ -155,6 +157,10 @@ struct TraceParams {
     unsigned int* parkCount;           // paths parked by the main launch
     unsigned int* parkCursor;          // fetch cursor of the tail launch
     uint32_t parkCapacity;
+    uint32_t parkEpoch;                // ready-flag value of this launch (last word of a park record); changes with every launch that parks, so the flags never need clearing
+    unsigned int* doneWarps;           // [0] warps of the main launch that have finished (and park nothing any more), [1] its CTAs that have started
+    uint32_t tailConcurrent;           // trace_tail_kernel: 1 = runs beside the main launch and polls, 0 = final drain in stream order
+    uint32_t mainWarps;                // warps of the main launch: the concurrent tail launch leaves when doneWarps reaches it
     // wave kernel, per pass: (pixel, sample) work items
     unsigned long long* workCounter64; // [0] work-item counter, [1] (as unsigned*) active-pixel count
     unsigned int* activeCount;         // = (unsigned*)(workCounter64 + 1)

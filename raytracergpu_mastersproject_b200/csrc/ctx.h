@@ -37,13 +37,17 @@ struct rtb_ctx {
     cudaStream_t stream = nullptr;
     bool ownStream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t auxStream = nullptr;             // the tail launch runs here, concurrently with the main trace launch
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     uint64_t launches = 0;
     char name[256] = { 0 };
     // build scratch (grow-only)
     rtb::Scratch sortKeys[2], sortVals[2], sortCounts, encRed, enclosing, cinfo, nodes;
     // the bound raytrace set: traversal records derived from the reference-layout arrays
     rtb::Scratch pairs, ptris, psphs, psphMat, pmats, rootBox, workCounter, errFlag, parkBuf;
+    uint32_t parkEpoch = 0;           // last epoch handed to a launch (see TraceParams::parkEpoch)
     rtb::Scratch etaNode, etaParent, etaArrivals;   // per-node hit-point slack (launch_eta) and its scratch
+    rtb::Scratch topTable, topGlobal; // A/B build RTB_SMEM_TOP
     rtb::Scratch walkFlag;            // device word: 1 = records grown by a finite slack, t-culling allowed (pack_wide_kernel)
     rtb::Scratch cnodes, leafBox, wide;    // compressed 32-byte / wide 64-byte traversal records + exact leaf boxes
     rtb::Scratch activePix, activeXY, sampleBuf, primaryHits;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots

@@ -19,7 +19,13 @@ void launch_morton_unpack(cudaStream_t st, const void* morton, uint32_t n, uint3
 void launch_morton_repack(cudaStream_t st, const uint32_t* keys, const uint32_t* vals, uint32_t n, uint32_t T, void* morton);
 void launch_hlbvh(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const uint32_t* codes,
                   uint32_t codeStrideWords, void* nodes, void* cinfo);
-void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox);   // pairs != NULL: also emit traversal records
+void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox, float* etaNode);   // pairs != NULL: also emit traversal records; etaNode != NULL: also climb the hit-point slack
+void launch_hlbvh_fused(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const uint32_t* codes, void* nodes,
+                        void* cinfo, void* leafBox, void* ptris, void* psphs, void* sphMat, float* etaNode, const uint32_t* primBounds,
+                        void* originRegion, const float* camPos);
+void launch_build_top_table(cudaStream_t st, const void* wide, uint32_t n, void* top, void* topGlobal);   // RTB_SMEM_TOP builds only
+int launch_model_to_world_enclosing(cudaStream_t st, const void* models, void* tris, uint32_t T, void* sphs, uint32_t S, uint32_t* red,
+                                    void* enclosing, int initInf);
 void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pairs, void* rootBox);
 void launch_pack_cnodes(cudaStream_t st, const void* nodes, uint32_t n, void* cnodes, void* leafBox);
 void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode, unsigned int* cullAllowed);
@@ -34,7 +40,10 @@ size_t radix_sort_counts_bytes(uint32_t n);
 
 // trace.cu
 void launch_trace(cudaStream_t st, TraceParams p, bool count, bool ext, bool linear, int smCount);
-int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint32_t samplesPerPass);   // trace_wave.cu
+// second stream + fork / join events for the tail launch that runs concurrently with the main trace launch (aux == nullptr: same stream)
+struct TailOverlap { cudaStream_t aux; cudaEvent_t fork, join; };
+int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint32_t samplesPerPass,
+                      const TailOverlap& ov);   // trace_wave.cu
 int launch_trace_stream(cudaStream_t st, TraceParams p, bool count, bool ext, int smCount, uint32_t samplesPerPass);   // trace_stream.cu
 void launch_logistic(cudaStream_t st, void* points, uint32_t count, void* image, uint32_t W, uint32_t H, const float* pixelColor);
 void launch_clear_image(cudaStream_t st, void* img, size_t pixels, int smCount);

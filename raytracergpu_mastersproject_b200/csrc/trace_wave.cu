@@ -42,7 +42,8 @@ namespace rtb {
 constexpr int WAVE_THREADS = 128;
 // parked path / ray record, float4 units: 0 (o, rng) 1 (d, depth) 2 (colour, pixel) 3 (attenuation, sample)
 // 4 (slot lo, slot hi, cur, flags: bit 0 ray in flight | bit 1 hit | sp << 8) 5 (rec.t, rec.normal) 6 (mat, prim, back, closest) 7..14 stack[32]
-constexpr unsigned PARK_STRIDE = 15;
+// 15 (.x = ready flag: the epoch of the launch that parked it, release-stored after the rest of the record)
+constexpr unsigned PARK_STRIDE = 16;
 #ifdef RTB_TAIL_PROBE   // debug build only (make EXTRA=-DRTB_TAIL_PROBE): per-warp timeline of the main launch, dumped to $RTB_TAIL_PROBE_FILE
 __device__ uint4 g_probeLane[8192 * 32];             // per lane: its longest ray (T steps, pixel, sample | depth << 16 | exact << 31, L tests)
 __device__ unsigned long long g_probe[3][8192];     // [0] first item pulled, [1] first lane retired (queue drained), [2] warp exit
@@ -53,6 +54,38 @@ __device__ __forceinline__ unsigned long long probe_now() { unsigned long long t
 #endif
 constexpr int WAVE_MIN_BLOCKS = 6;
 constexpr int WIDE_MIN_BLOCKS = RTB_WIDE_MINB;   // resident CTAs per SM for the 4-ary variant
+
+constexpr uint32_t COOP_CAP = 512;
+// the pending-set stack of a tail warp: a plain shared array (trace_tail_kernel) or the warp's own slice of the main kernel's
+// [level][thread] traversal stack, free once all its lanes are dead (32 levels x 32 lanes = 1024 entries)
+struct LinearStack {
+    uint32_t* s;
+    __device__ __forceinline__ uint32_t& operator[](uint32_t i) const { return s[i]; }
+};
+struct StridedStack {
+    uint32_t (*s)[WAVE_THREADS];
+    unsigned base;
+    __device__ __forceinline__ uint32_t& operator[](uint32_t i) const { return s[i >> 5][base + (i & 31u)]; }
+};
+template <bool EXT, bool COUNT, class STK>
+__device__ __forceinline__ void tail_item(const TraceParams& p, const uint32_t item, const STK stk, const unsigned lane, Tally& tl, unsigned& err);
+// A/B build RTB_SMEM_TOP: stack entries of the main kernel may be table indices; the tail kernel walks global records only
+__device__ __forceinline__ uint32_t untag_top(const TraceScene& sc, const uint32_t id) {
+#ifdef RTB_SMEM_TOP
+    if (id != 0xFFFFFFFFu && (id & 0x80000000u)) return __ldg(sc.topGlobal + (id & 0x7FFFFFFFu));
+#endif
+    return id;
+}
+// release-store of a park slot's ready flag: the record written before it is visible to whoever reads the flag (acquire side: the
+// tail launch reads the flag, fences, then loads the record past L1)
+__device__ __forceinline__ void publish_parked(unsigned int* flag, const unsigned int epoch) {
+#ifdef RTB_SIMT_EMU
+    *flag = epoch;
+#else
+    __threadfence();
+    *flag = epoch;
+#endif
+}
 
 // CULL (RTB_TRACE_CULLED, default OFF, NOT the reference's traversal): additionally skips children whose box lies outside
 // the axis-aligned box of the ray SEGMENT [tMin, closest-so-far] grown by a safety margin.  The reference visits every
@@ -68,9 +101,18 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
     __shared__ WaveSmem<WAVE_THREADS> sm;
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned tid = threadIdx.x;
+#ifdef RTB_SMEM_TOP
+    __shared__ uint4 smTop[NODES >= 3 ? RTB_SMEM_TOP * 4 : 1];
+    if (NODES >= 3) { for (unsigned i = tid; i < RTB_SMEM_TOP * 4; i += WAVE_THREADS) smTop[i] = p.sc.top[i]; __syncthreads(); }
+    constexpr uint32_t ROOT = NODES >= 3 ? 0x80000000u : 0u;
+#else
+    const uint4* smTop = nullptr;
+    constexpr uint32_t ROOT = 0u;
+#endif
     const unsigned lane = tid & 31;
     const TraceScene& sc = p.sc;
     const uint32_t leafOffset = sc.N - 1;
+    if (NODES >= 3 && p.doneWarps != nullptr && tid == 0) atomicAdd(p.doneWarps + 1, 1u);   // this CTA is resident (see trace_tail_kernel)
     const uint32_t activeCount = *p.activeCount;
     // item i -> group of 32 active pixels g = i / (32 * S), sample s = (i % (32 * S)) / 32, pixel slot g * 32 + i % 32:
     // the 32 items a warp pulls together are the same sample of 32 neighbouring pixels (coherent primary rays)
@@ -144,6 +186,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
                         e[7 + j] = make_float4(__uint_as_float(sm.stack[4 * j][tid]), __uint_as_float(sm.stack[4 * j + 1][tid]),
                                                __uint_as_float(sm.stack[4 * j + 2][tid]), __uint_as_float(sm.stack[4 * j + 3][tid]));
                     rayActive = false; travDone = true; sp = 0; cur = 0xFFFFFFFFu;      // the lane is free for the next item
+                    publish_parked((unsigned int*)(e + 15), p.parkEpoch);                  // the concurrent tail launch may take it from here
                     if (COUNT) tl.parked++;
                 }
             }
@@ -245,6 +288,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
                     e[3] = make_float4(att.x, att.y, att.z, __uint_as_float(smp));
                     e[4] = make_float4(__uint_as_float((uint32_t)slotIndex), __uint_as_float((uint32_t)((unsigned long long)slotIndex >> 32)), 0.f, 0.f);
                     rayActive = false;
+                    publish_parked((unsigned int*)(e + 15), p.parkEpoch);
                     if (COUNT) tl.parked++;
                     continue;                                             // pulls from the drained queue -> dead
                 }
@@ -263,7 +307,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             }
             if (box_test(o, d, rinv, exactOnly, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) {
                 if (sc.N == 1) enqueue(0u);                                                // the root is the only leaf
-                else { cur = 0; travDone = false; }
+                else { cur = exactOnly ? 0u : ROOT; travDone = false; }
             }
         }
 #ifdef RTB_TAIL_PROBE
@@ -297,7 +341,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             if (can) {
                 // CN: 32-byte compressed records; rays with a zero / denormal direction component (reference yields inf / NaN)
                 // keep to the exact 64-byte records
-                if (NODES >= 3 && !exactOnly) wave_step_u<NODES == 4>(sc, sm, tid, o, rinv, cullOk ? closest : __int_as_float(0x7f800000), cullOk ? T_MIN_RAY : __int_as_float(0xff800000), cur, sp, qCount, travDone, lstack, err, leafOffset);
+                if (NODES >= 3 && !exactOnly) wave_step_u<NODES == 4>(sc, sm, tid, o, rinv, cullOk ? closest : __int_as_float(0x7f800000), cullOk ? T_MIN_RAY : __int_as_float(0xff800000), cur, sp, qCount, travDone, lstack, err, leafOffset, smTop);
                 else if (NODES == 2 && !exactOnly) wave_step_w<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
 #ifdef RTB_AB_KERNELS
                 else if (NODES == 1 && !exactOnly) wave_step_c<CULL>(sc, sm, tid, leafOffset, o, rinv, cur, sp, qHead, qCount, travDone, lstack, err, segLo, segHi);
@@ -334,6 +378,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
         qHead = 0;                                                        // every FIFO is empty: rewind (wave_step_w relies on it)
     }
 
+    // tell the concurrently running trace_tail_kernel that this warp parks nothing any more
+    if (NODES >= 3 && p.doneWarps != nullptr) { __threadfence(); if (lane == 0) atomicAdd(p.doneWarps, 1u); }
 #ifdef RTB_TAIL_PROBE
     if (lane == 0 && pw < 8192) g_probe[2][pw] = probe_now();
     if (pw < 8192) g_probeLane[pw * 32 + lane] = prMax;
@@ -356,193 +402,245 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
 // set send the ray to hit_bvh(): the reference's own walk on the exact records.  Shading is the main kernel's S phase,
 // evaluated redundantly by every lane (uniform state, no divergence).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t COOP_CAP = 512;
+
+// Finishes ONE parked path / ray, one ray per warp (see above).  Every lane of the warp calls it with the same item.
+template <bool EXT, bool COUNT, class STK>
+__device__ __forceinline__ void tail_item(const TraceParams& p, const uint32_t item, const STK stk, const unsigned lane, Tally& tl, unsigned& err) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const TraceScene& sc = p.sc;
+    const uint32_t leafOffset = sc.N - 1;
+    const float T_MIN_RAY = 0.001f, T_MAX_RAY = 10000000.0f;
+    const float INF = __int_as_float(0x7f800000);
+    const float4* e = p.parkBuf + (size_t)PARK_STRIDE * item;
+    const float4 q0 = __ldcg(e), q1 = __ldcg(e + 1), q2 = __ldcg(e + 2), q3 = __ldcg(e + 3), q4 = __ldcg(e + 4);
+    uint32_t resume = __float_as_uint(q4.w);                          // bit 0: the first ray is in flight (pending set + closest hit parked)
+    f3 o = xyz(q0), d = xyz(q1), color = xyz(q2), att = xyz(q3);
+    uint32_t rng = __float_as_uint(q0.w), depth = __float_as_uint(q1.w);
+    const uint32_t pix = __float_as_uint(q2.w), smp = __float_as_uint(q3.w);
+    const size_t slotIndex = (size_t)__float_as_uint(q4.x) | ((size_t)__float_as_uint(q4.y) << 32);
+    while (true) {                                                    // one ray of the path per turn
+        bool hit = false;
+        Hit rec; rec.t = 0.f; rec.normal = F3(0, 0, 0); rec.mat = 0; rec.prim = 0; rec.back = 0;
+        const f3 rinv = F3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        bool needExact = !(fabsf(rinv.x) < 3.0e38f && fabsf(rinv.y) < 3.0e38f && fabsf(rinv.z) < 3.0e38f);
+        const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
+        if (COUNT && lane == 0) { tl.tailRays++; if (!(resume & 1u)) tl.rays++; }   // a resumed ray was counted by the launch that started it
+        if (!needExact && ((resume & 1u) || box_test(o, d, rinv, false, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z))) {
+            const float4 rl = __ldg(sc.rootBox + 2), rh = __ldg(sc.rootBox + 3);      // origin region of the t-culled walk (bvh_build.cu)
+            const bool cullOk = *p.cullAllowed != 0u && o.x >= rl.x && o.x <= rh.x && o.y >= rl.y && o.y <= rh.y && o.z >= rl.z && o.z <= rh.z;
+            float closest = T_MAX_RAY, best = T_MAX_RAY;              // lane-local closest hit; warp-wide culling bound
+            bool poison = false, fit = true;
+            uint32_t n = 1;
+            if (resume & 1u) {                                        // continue a parked ray: its stack + cur, lane 0 keeps its closest hit
+                const uint32_t psp = resume >> 8, pcur = __float_as_uint(q4.z);
+                const float4 q5 = __ldcg(e + 5), q6 = __ldcg(e + 6);
+                if (lane < psp) stk[lane] = untag_top(sc, __float_as_uint(__ldcg((const float*)(e + 7) + lane)));
+                if (lane == 0 && pcur != 0xFFFFFFFFu) stk[psp] = untag_top(sc, pcur);
+                n = psp + (pcur != 0xFFFFFFFFu ? 1u : 0u);
+                closest = best = q6.w;                                // the others may only accept t <= the parked closest; ties: see the reduce
+                if (lane == 0 && (resume & 2u)) {
+                    hit = true; rec.t = q5.x; rec.normal = F3(q5.y, q5.z, q5.w);
+                    rec.mat = __float_as_uint(q6.x); rec.prim = __float_as_uint(q6.y); rec.back = (int)__float_as_uint(q6.z);
+                }
+                resume = 0;
+            } else if (lane == 0) stk[0] = 0u;
+            __syncwarp();
+            while (n > 0) {
+                if (COUNT && lane == 0) tl.tailTurns++;
+                const uint32_t take = n < 32u ? n : 32u;
+                const uint32_t my = lane < take ? stk[n - 1u - lane] : 0xFFFFFFFFu;
+                n -= take;
+                __syncwarp();
+                uint32_t intMask = 0, id0 = 0, id1 = 0, id2 = 0, id3 = 0;
+                if (my != 0xFFFFFFFFu) {
+                    if (COUNT) { tl.rec++; tl.recUnique++; }      // the lanes of a tail warp expand distinct entries of one ray
+                    const uint4* rp = sc.wide + 4ull * my;
+                    const f8 h0 = ldg256(rp), h1 = ldg256(rp + 2);
+                    const uint32_t w3 = __float_as_uint(h0.lo.w);
+                    const uint32_t lox = __float_as_uint(h0.hi.x), loy = __float_as_uint(h0.hi.y), loz = __float_as_uint(h0.hi.z),
+                                   hix = __float_as_uint(h0.hi.w), hiy = __float_as_uint(h1.lo.x), hiz = __float_as_uint(h1.lo.y);
+                    id0 = __float_as_uint(h1.lo.z); id1 = __float_as_uint(h1.lo.w); id2 = __float_as_uint(h1.hi.x); id3 = __float_as_uint(h1.hi.y);
+                    const float sx = __uint_as_float((w3 & 0xFFu) << 23), sy = __uint_as_float(((w3 >> 8) & 0xFFu) << 23),
+                                sz = __uint_as_float(((w3 >> 16) & 0xFFu) << 23);
+                    const float ax = sx * rinv.x, ay = sy * rinv.y, az = sz * rinv.z;
+                    const float bx = (h0.lo.x - o.x) * rinv.x, by = (h0.lo.y - o.y) * rinv.y, bz = (h0.lo.z - o.z) * rinv.z;
+                    const float m = fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(bx)), fmaf(255.0f, fabsf(ay), fabsf(by))), fmaf(255.0f, fabsf(az), fabsf(bz)));
+                    const float tol = -2.0e-6f * m;                   // the error budget of wave_step_u; NaN / inf -> nothing is dropped
+                    const float farLimit = (cullOk ? best : INF) - tol, nearLimit = (cullOk ? T_MIN_RAY : -INF) + tol;
+                    const bool ngx = rinv.x < 0.0f, ngy = rinv.y < 0.0f, ngz = rinv.z < 0.0f;
+                    const uint32_t nX = ngx ? hix : lox, fX = ngx ? lox : hix;
+                    const uint32_t nY = ngy ? hiy : loy, fY = ngy ? loy : hiy;
+                    const uint32_t nZ = ngz ? hiz : loz, fZ = ngz ? loz : hiz;
+                    const uint32_t meta = w3 >> 24;
+                    uint32_t passMask = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+#define RTB_B(w) __uint2float_rn(((w) >> (8 * k)) & 0xFFu)
+                        const float tn = fmaxf(fmaxf(fmaf(RTB_B(nX), ax, bx), fmaf(RTB_B(nY), ay, by)), fmaf(RTB_B(nZ), az, bz));
+                        const float tf = fminf(fminf(fmaf(RTB_B(fX), ax, bx), fmaf(RTB_B(fY), ay, by)), fmaf(RTB_B(fZ), az, bz));
+#undef RTB_B
+                        const bool pass = !((tf - tn) < tol) && !(tn > farLimit) && !(tf < nearLimit);
+                        passMask |= pass ? (1u << k) : 0u;
+                    }
+                    passMask &= meta >> 4;
+                    const uint32_t leafMask = meta & 0xFu;
+                    intMask = passMask & ~leafMask;
+                    const uint32_t enqMask = passMask & leafMask;
+#pragma unroll 1
+                    for (int k = 0; k < 4; k++) {
+                        if (!((enqMask >> k) & 1u)) continue;
+                        const uint32_t g = (k == 0 ? id0 : k == 1 ? id1 : k == 2 ? id2 : id3) - leafOffset;
+                        if (COUNT) tl.lbox++;
+                        if (leaf_box_passes(sc, g, o, d, rinv, false)) leaf_test_unordered<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl, poison);
+                    }
+                }
+                if (n + 128u > COOP_CAP) { fit = false; break; }      // warp-uniform
+                { const bool b = intMask & 1u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id0; n += __popc(bal); }
+                { const bool b = intMask & 2u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id1; n += __popc(bal); }
+                { const bool b = intMask & 4u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id2; n += __popc(bal); }
+                { const bool b = intMask & 8u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id3; n += __popc(bal); }
+                __syncwarp();
+                float mn = closest;                                   // never NaN: a NaN hit only raises poison
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) mn = fminf(mn, __shfl_xor_sync(FULL, mn, off));
+                best = mn;
+            }
+            __syncwarp();
+#ifdef RTB_TAIL_TEST_FALLBACK   // test builds only (tests/test_emulated_kernels.py): every third ray takes the exact fallback below
+            if ((item + depth) % 3u == 0u) fit = false;
+#endif
+            if (!fit || __any_sync(FULL, poison)) {
+                needExact = true;
+            } else {
+                // lexicographic minimum (t, primitive id) over the lanes that hold a hit, broadcast to every lane
+                float bt = hit ? rec.t : INF;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) bt = fminf(bt, __shfl_xor_sync(FULL, bt, off));
+                uint32_t bp = (hit && rec.t == bt) ? rec.prim : 0xFFFFFFFFu;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) bp = min(bp, __shfl_xor_sync(FULL, bp, off));
+                const unsigned winBal = __ballot_sync(FULL, hit && rec.t == bt && rec.prim == bp);
+                hit = winBal != 0u;
+                const int win = hit ? __ffs(winBal) - 1 : 0;
+                rec.t = __shfl_sync(FULL, rec.t, win);
+                rec.normal = F3(__shfl_sync(FULL, rec.normal.x, win), __shfl_sync(FULL, rec.normal.y, win), __shfl_sync(FULL, rec.normal.z, win));
+                rec.mat = __shfl_sync(FULL, rec.mat, win); rec.prim = __shfl_sync(FULL, rec.prim, win); rec.back = __shfl_sync(FULL, rec.back, win);
+            }
+        }
+        if (needExact) {                                              // the reference's walk, every lane alike (rare: NaN hits, axis-parallel rays)
+            Tally scratch = { 0, 0, 0, 0, 0 };
+            hit = hit_bvh<COUNT>(sc, o, d, T_MIN_RAY, T_MAX_RAY, rec, scratch, err);
+            if (COUNT && lane == 0) { tl.rec += (scratch.visits - 1) / 2; tl.tri += scratch.tri; tl.sph += scratch.sph; }
+        }
+        if (p.primaryMode == 1u) {                                    // primary-hit launch: keep the hit record, no shading
+            if (lane == 0) {
+                float4* h = p.primaryHits + 3ull * pix;
+                h[0] = make_float4(rec.t, rec.normal.x, rec.normal.y, rec.normal.z);
+                h[1] = make_float4(__uint_as_float(rec.prim), __uint_as_float(rec.mat), __uint_as_float(hit ? 1u : 0u), __uint_as_float((uint32_t)rec.back));
+                h[2] = make_float4(d.x, d.y, d.z, 0.f);
+            }
+            break;
+        }
+        // ---- the main kernel's S phase (rayColor loop body :283-307), uniform over the warp ----
+        if (depth == 0 && smp == 0 && p.firstPass && p.hitPrim && lane == 0) {
+            p.hitPrim[pix] = hit ? rec.prim : 0xFFFFFFFFu;
+            if (p.hitT) p.hitT[pix] = hit ? rec.t : 0.0f;
+        }
+        bool pathEnd = true;
+        if (!hit) {
+            color = color + F3(0.f, 0.f, 0.f) * att;
+        } else {
+            const float4 m = __ldg(sc.mats + rec.mat);
+            if (COUNT && lane == 0) tl.mat++;
+            const uint32_t type = __float_as_uint(m.w);
+            const f3 albedo = xyz(m);
+            const f3 emitted = (type == RTB_LIGHT) ? albedo : F3(0.f, 0.f, 0.f);
+            color = color + emitted * att;
+            if (type == RTB_DIFFUSE) {
+                const f3 P = o + rec.t * d;
+                const f3 nd = normalize(rec.normal + random_unit_vector(rng));
+                o = P; d = nd;
+                att = att * albedo;
+                pathEnd = false;
+            } else if (EXT && type != RTB_LIGHT) {
+                f3 a2, nd;
+                const f3 P = o + rec.t * d;
+                if (scatter_extension(type, albedo, d, rec, rng, a2, nd)) { o = P; d = nd; att = att * a2; pathEnd = false; }
+            }
+            depth++;
+            if (depth >= p.maxDepth) pathEnd = true;
+        }
+        if (pathEnd) {
+            if (COUNT && lane == 0) tl.paths++;
+            if (lane == 0) {
+                float4* out = p.sampleBuf + slotIndex;
+                out->x = color.x; out->y = color.y; out->z = color.z;   // .w keeps the sample's incoming alpha
+                if (p.rngOut && p.lastPass && smp + 1 == p.sampleCount) p.rngOut[pix] = rng;
+            }
+            break;
+        }
+    }
+}
+
 template <bool EXT, bool COUNT>
 __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TraceParams p) {
     __shared__ uint32_t coopStack[WAVE_THREADS / 32][COOP_CAP];
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31;
-    uint32_t* stk = coopStack[threadIdx.x >> 5];
-    const TraceScene& sc = p.sc;
-    const uint32_t leafOffset = sc.N - 1;
-    const float T_MIN_RAY = 0.001f, T_MAX_RAY = 10000000.0f;
-    const float INF = __int_as_float(0x7f800000);
-    const uint32_t parked = min(*p.parkCount, p.parkCapacity);
+    const LinearStack stk{ coopStack[threadIdx.x >> 5] };
     unsigned err = 0;
     Tally tl = { 0, 0, 0, 0, 0 };
-    while (true) {
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(p.parkCursor, 1u);
-        item = __shfl_sync(FULL, item, 0);
-        if (item >= parked) break;
-        const float4* e = p.parkBuf + (size_t)PARK_STRIDE * item;
-        const float4 q0 = e[0], q1 = e[1], q2 = e[2], q3 = e[3], q4 = e[4];
-        uint32_t resume = __float_as_uint(q4.w);                          // bit 0: the first ray is in flight (pending set + closest hit parked)
-        f3 o = xyz(q0), d = xyz(q1), color = xyz(q2), att = xyz(q3);
-        uint32_t rng = __float_as_uint(q0.w), depth = __float_as_uint(q1.w);
-        const uint32_t pix = __float_as_uint(q2.w), smp = __float_as_uint(q3.w);
-        const size_t slotIndex = (size_t)__float_as_uint(q4.x) | ((size_t)__float_as_uint(q4.y) << 32);
-        while (true) {                                                    // one ray of the path per turn
-            bool hit = false;
-            Hit rec; rec.t = 0.f; rec.normal = F3(0, 0, 0); rec.mat = 0; rec.prim = 0; rec.back = 0;
-            const f3 rinv = F3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-            bool needExact = !(fabsf(rinv.x) < 3.0e38f && fabsf(rinv.y) < 3.0e38f && fabsf(rinv.z) < 3.0e38f);
-            const float4 lo = __ldg(sc.rootBox), hi = __ldg(sc.rootBox + 1);
-            if (COUNT && lane == 0) { tl.tailRays++; if (!(resume & 1u)) tl.rays++; }   // a resumed ray was counted by the launch that started it
-            if (!needExact && ((resume & 1u) || box_test(o, d, rinv, false, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z))) {
-                const float4 rl = __ldg(sc.rootBox + 2), rh = __ldg(sc.rootBox + 3);      // origin region of the t-culled walk (bvh_build.cu)
-                const bool cullOk = *p.cullAllowed != 0u && o.x >= rl.x && o.x <= rh.x && o.y >= rl.y && o.y <= rh.y && o.z >= rl.z && o.z <= rh.z;
-                float closest = T_MAX_RAY, best = T_MAX_RAY;              // lane-local closest hit; warp-wide culling bound
-                bool poison = false, fit = true;
-                uint32_t n = 1;
-                if (resume & 1u) {                                        // continue a parked ray: its stack + cur, lane 0 keeps its closest hit
-                    const uint32_t psp = resume >> 8, pcur = __float_as_uint(q4.z);
-                    const float4 q5 = e[5], q6 = e[6];
-                    if (lane < psp) stk[lane] = __float_as_uint(((const float*)(e + 7))[lane]);
-                    if (lane == 0 && pcur != 0xFFFFFFFFu) stk[psp] = pcur;
-                    n = psp + (pcur != 0xFFFFFFFFu ? 1u : 0u);
-                    closest = best = q6.w;                                // the others may only accept t <= the parked closest; ties: see the reduce
-                    if (lane == 0 && (resume & 2u)) {
-                        hit = true; rec.t = q5.x; rec.normal = F3(q5.y, q5.z, q5.w);
-                        rec.mat = __float_as_uint(q6.x); rec.prim = __float_as_uint(q6.y); rec.back = (int)__float_as_uint(q6.z);
-                    }
-                    resume = 0;
-                } else if (lane == 0) stk[0] = 0u;
-                __syncwarp();
-                while (n > 0) {
-                    if (COUNT && lane == 0) tl.tailTurns++;
-                    const uint32_t take = n < 32u ? n : 32u;
-                    const uint32_t my = lane < take ? stk[n - 1u - lane] : 0xFFFFFFFFu;
-                    n -= take;
-                    __syncwarp();
-                    uint32_t intMask = 0, id0 = 0, id1 = 0, id2 = 0, id3 = 0;
-                    if (my != 0xFFFFFFFFu) {
-                        if (COUNT) { tl.rec++; tl.recUnique++; }      // the lanes of a tail warp expand distinct entries of one ray
-                        const uint4* rp = sc.wide + 4ull * my;
-                        const f8 h0 = ldg256(rp), h1 = ldg256(rp + 2);
-                        const uint32_t w3 = __float_as_uint(h0.lo.w);
-                        const uint32_t lox = __float_as_uint(h0.hi.x), loy = __float_as_uint(h0.hi.y), loz = __float_as_uint(h0.hi.z),
-                                       hix = __float_as_uint(h0.hi.w), hiy = __float_as_uint(h1.lo.x), hiz = __float_as_uint(h1.lo.y);
-                        id0 = __float_as_uint(h1.lo.z); id1 = __float_as_uint(h1.lo.w); id2 = __float_as_uint(h1.hi.x); id3 = __float_as_uint(h1.hi.y);
-                        const float sx = __uint_as_float((w3 & 0xFFu) << 23), sy = __uint_as_float(((w3 >> 8) & 0xFFu) << 23),
-                                    sz = __uint_as_float(((w3 >> 16) & 0xFFu) << 23);
-                        const float ax = sx * rinv.x, ay = sy * rinv.y, az = sz * rinv.z;
-                        const float bx = (h0.lo.x - o.x) * rinv.x, by = (h0.lo.y - o.y) * rinv.y, bz = (h0.lo.z - o.z) * rinv.z;
-                        const float m = fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(bx)), fmaf(255.0f, fabsf(ay), fabsf(by))), fmaf(255.0f, fabsf(az), fabsf(bz)));
-                        const float tol = -2.0e-6f * m;                   // the error budget of wave_step_u; NaN / inf -> nothing is dropped
-                        const float farLimit = (cullOk ? best : INF) - tol, nearLimit = (cullOk ? T_MIN_RAY : -INF) + tol;
-                        const bool ngx = rinv.x < 0.0f, ngy = rinv.y < 0.0f, ngz = rinv.z < 0.0f;
-                        const uint32_t nX = ngx ? hix : lox, fX = ngx ? lox : hix;
-                        const uint32_t nY = ngy ? hiy : loy, fY = ngy ? loy : hiy;
-                        const uint32_t nZ = ngz ? hiz : loz, fZ = ngz ? loz : hiz;
-                        const uint32_t meta = w3 >> 24;
-                        uint32_t passMask = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-#define RTB_B(w) __uint2float_rn(((w) >> (8 * k)) & 0xFFu)
-                            const float tn = fmaxf(fmaxf(fmaf(RTB_B(nX), ax, bx), fmaf(RTB_B(nY), ay, by)), fmaf(RTB_B(nZ), az, bz));
-                            const float tf = fminf(fminf(fmaf(RTB_B(fX), ax, bx), fmaf(RTB_B(fY), ay, by)), fmaf(RTB_B(fZ), az, bz));
-#undef RTB_B
-                            const bool pass = !((tf - tn) < tol) && !(tn > farLimit) && !(tf < nearLimit);
-                            passMask |= pass ? (1u << k) : 0u;
-                        }
-                        passMask &= meta >> 4;
-                        const uint32_t leafMask = meta & 0xFu;
-                        intMask = passMask & ~leafMask;
-                        const uint32_t enqMask = passMask & leafMask;
-#pragma unroll 1
-                        for (int k = 0; k < 4; k++) {
-                            if (!((enqMask >> k) & 1u)) continue;
-                            const uint32_t g = (k == 0 ? id0 : k == 1 ? id1 : k == 2 ? id2 : id3) - leafOffset;
-                            if (COUNT) tl.lbox++;
-                            if (leaf_box_passes(sc, g, o, d, rinv, false)) leaf_test_unordered<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl, poison);
-                        }
-                    }
-                    if (n + 128u > COOP_CAP) { fit = false; break; }      // warp-uniform
-                    { const bool b = intMask & 1u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id0; n += __popc(bal); }
-                    { const bool b = intMask & 2u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id1; n += __popc(bal); }
-                    { const bool b = intMask & 4u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id2; n += __popc(bal); }
-                    { const bool b = intMask & 8u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id3; n += __popc(bal); }
-                    __syncwarp();
-                    float mn = closest;                                   // never NaN: a NaN hit only raises poison
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) mn = fminf(mn, __shfl_xor_sync(FULL, mn, off));
-                    best = mn;
-                }
-                __syncwarp();
-#ifdef RTB_TAIL_TEST_FALLBACK   // test builds only (tests/test_emulated_kernels.py): every third ray takes the exact fallback below
-                if ((item + depth) % 3u == 0u) fit = false;
+    if (!p.tailConcurrent) {
+        // FINAL launch (in stream order behind the main launch): everything parked and not yet taken is complete and visible
+        const uint32_t parked = min(*p.parkCount, p.parkCapacity);
+        while (true) {
+            uint32_t item = 0;
+            if (lane == 0) item = atomicAdd(p.parkCursor, 1u);
+            item = __shfl_sync(FULL, item, 0);
+            if (item >= parked) break;
+            tail_item<EXT, COUNT>(p, item, stk, lane, tl, err);
+        }
+    } else {
+        // CONCURRENT launch (second stream, enqueued right behind the main launch): its CTAs become resident as CTAs of the main launch
+        // exit, take what has been published so far (slot below the park count whose ready flag carries this launch's epoch) and leave
+        // once every warp of the main launch has signed off and nothing is left -- the long rays that used to be the launch's tail are
+        // worked off DURING the launch.  Deadlock freedom: a CTA of this launch that becomes resident before ALL CTAs of the (persistent)
+        // main launch have started leaves at once -- it must not hold an SM slot a main CTA is waiting for -- and no warp polls for more
+        // than 20 ms; whatever is left over is finished by the FINAL launch.
+        const unsigned mainCtas = p.mainWarps / (WAVE_THREADS / 32);
+        if (*(volatile unsigned int*)(p.doneWarps + 1) < mainCtas) return;
+        unsigned long long t0 = 0;
+#ifndef RTB_SIMT_EMU
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
 #endif
-                if (!fit || __any_sync(FULL, poison)) {
-                    needExact = true;
-                } else {
-                    // lexicographic minimum (t, primitive id) over the lanes that hold a hit, broadcast to every lane
-                    float bt = hit ? rec.t : INF;
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) bt = fminf(bt, __shfl_xor_sync(FULL, bt, off));
-                    uint32_t bp = (hit && rec.t == bt) ? rec.prim : 0xFFFFFFFFu;
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) bp = min(bp, __shfl_xor_sync(FULL, bp, off));
-                    const unsigned winBal = __ballot_sync(FULL, hit && rec.t == bt && rec.prim == bp);
-                    hit = winBal != 0u;
-                    const int win = hit ? __ffs(winBal) - 1 : 0;
-                    rec.t = __shfl_sync(FULL, rec.t, win);
-                    rec.normal = F3(__shfl_sync(FULL, rec.normal.x, win), __shfl_sync(FULL, rec.normal.y, win), __shfl_sync(FULL, rec.normal.z, win));
-                    rec.mat = __shfl_sync(FULL, rec.mat, win); rec.prim = __shfl_sync(FULL, rec.prim, win); rec.back = __shfl_sync(FULL, rec.back, win);
+        while (true) {
+            uint32_t item = 0xFFFFFFFFu;
+            if (lane == 0) {
+                while (true) {
+                    const unsigned done = *(volatile unsigned int*)p.doneWarps;       // read BEFORE the count: once all producers are gone the count is final
+                    __threadfence();
+                    const unsigned n = min(*(volatile unsigned int*)p.parkCount, p.parkCapacity);
+                    const unsigned c = *(volatile unsigned int*)p.parkCursor;
+                    if (c < n) {
+                        if (*(volatile unsigned int*)(p.parkBuf + (size_t)PARK_STRIDE * c + 15) == p.parkEpoch) {
+                            if (atomicCAS(p.parkCursor, c, c + 1u) == c) { item = c; break; }
+                            continue;
+                        }
+                    } else if (done >= p.mainWarps) break;
+#ifdef RTB_SIMT_EMU
+                    break;                    // (emulated launches are synchronous: nothing can change while this one runs)
+#else
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 20000000ull) break;
+                    __nanosleep(400);
+#endif
                 }
             }
-            if (needExact) {                                              // the reference's walk, every lane alike (rare: NaN hits, axis-parallel rays)
-                Tally scratch = { 0, 0, 0, 0, 0 };
-                hit = hit_bvh<COUNT>(sc, o, d, T_MIN_RAY, T_MAX_RAY, rec, scratch, err);
-                if (COUNT && lane == 0) { tl.rec += (scratch.visits - 1) / 2; tl.tri += scratch.tri; tl.sph += scratch.sph; }
-            }
-            if (p.primaryMode == 1u) {                                    // primary-hit launch: keep the hit record, no shading
-                if (lane == 0) {
-                    float4* h = p.primaryHits + 3ull * pix;
-                    h[0] = make_float4(rec.t, rec.normal.x, rec.normal.y, rec.normal.z);
-                    h[1] = make_float4(__uint_as_float(rec.prim), __uint_as_float(rec.mat), __uint_as_float(hit ? 1u : 0u), __uint_as_float((uint32_t)rec.back));
-                    h[2] = make_float4(d.x, d.y, d.z, 0.f);
-                }
-                break;
-            }
-            // ---- the main kernel's S phase (rayColor loop body :283-307), uniform over the warp ----
-            if (depth == 0 && smp == 0 && p.firstPass && p.hitPrim && lane == 0) {
-                p.hitPrim[pix] = hit ? rec.prim : 0xFFFFFFFFu;
-                if (p.hitT) p.hitT[pix] = hit ? rec.t : 0.0f;
-            }
-            bool pathEnd = true;
-            if (!hit) {
-                color = color + F3(0.f, 0.f, 0.f) * att;
-            } else {
-                const float4 m = __ldg(sc.mats + rec.mat);
-                if (COUNT && lane == 0) tl.mat++;
-                const uint32_t type = __float_as_uint(m.w);
-                const f3 albedo = xyz(m);
-                const f3 emitted = (type == RTB_LIGHT) ? albedo : F3(0.f, 0.f, 0.f);
-                color = color + emitted * att;
-                if (type == RTB_DIFFUSE) {
-                    const f3 P = o + rec.t * d;
-                    const f3 nd = normalize(rec.normal + random_unit_vector(rng));
-                    o = P; d = nd;
-                    att = att * albedo;
-                    pathEnd = false;
-                } else if (EXT && type != RTB_LIGHT) {
-                    f3 a2, nd;
-                    const f3 P = o + rec.t * d;
-                    if (scatter_extension(type, albedo, d, rec, rng, a2, nd)) { o = P; d = nd; att = att * a2; pathEnd = false; }
-                }
-                depth++;
-                if (depth >= p.maxDepth) pathEnd = true;
-            }
-            if (pathEnd) {
-                if (COUNT && lane == 0) tl.paths++;
-                if (lane == 0) {
-                    float4* out = p.sampleBuf + slotIndex;
-                    out->x = color.x; out->y = color.y; out->z = color.z;   // .w keeps the sample's incoming alpha
-                    if (p.rngOut && p.lastPass && smp + 1 == p.sampleCount) p.rngOut[pix] = rng;
-                }
-                break;
-            }
+            item = __shfl_sync(FULL, item, 0);
+            if (item == 0xFFFFFFFFu) break;
+            __threadfence();
+            tail_item<EXT, COUNT>(p, item, stk, lane, tl, err);
         }
     }
     if (err) atomicOr(p.errFlag, err);
@@ -550,15 +648,16 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
 }
 
 template <bool COUNT, bool EXT, bool CULL, int NODES>
-static void launch_wave_variant(cudaStream_t st, const TraceParams& p, int smCount, uint64_t need) {
+static void launch_wave_variant(cudaStream_t st, TraceParams& p, int smCount, uint64_t need) {
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_wave_kernel<COUNT, EXT, CULL, NODES>, WAVE_THREADS, 0);
     uint64_t grid = (uint64_t)smCount * (nb > 0 ? nb : 1);                 // persistent: resident CTAs per SM x SM count
     if (grid > need) grid = need;
+    p.mainWarps = (uint32_t)grid * (WAVE_THREADS / 32);                    // what the concurrent tail launch waits for
     trace_wave_kernel<COUNT, EXT, CULL, NODES><<<(unsigned)grid, WAVE_THREADS, 0, st>>>(p);
 }
 
-static void dispatch_wave(cudaStream_t st, const TraceParams& p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint64_t need) {
+static void dispatch_wave(cudaStream_t st, TraceParams& p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint64_t need) {
     const int v = (count ? 4 : 0) | (ext ? 2 : 0) | (cull ? 1 : 0);
     if (nodesMode == 3 && p.sortedPush) {
         if (count) { if (ext) launch_wave_variant<true, true, false, 4>(st, p, smCount, need); else launch_wave_variant<true, false, false, 4>(st, p, smCount, need); }
@@ -599,7 +698,8 @@ static void dispatch_wave(cudaStream_t st, const TraceParams& p, bool count, boo
 }
 
 // One S2 submission = ceil(sampleCount / samplesPerPass) passes of { pre-pass, [primary hits,] trace, accumulate }.  Returns #launches.
-int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint32_t samplesPerPass) {
+int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool cull, int nodesMode, int smCount, uint32_t samplesPerPass,
+                      const TailOverlap& ov) {
     const bool walk = p.walkCounters != nullptr;           // RTB_TRACE_WALK_COUNT: the production walk, counting what it fetches
     if ((count && !walk) || p.sc.N < 2) nodesMode = 0;     // RTB_TRACE_COUNT counts the reference's visits: exact records, reference order
     if (walk && nodesMode != 3) nodesMode = 0;             // (the walk counters are built into the two production variants)
@@ -632,13 +732,26 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool
             if (ext) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_tail_kernel<true, false>, WAVE_THREADS, 0);
             else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_tail_kernel<false, false>, WAVE_THREADS, 0);
             const unsigned grid = (unsigned)smCount * (unsigned)(nb > 0 ? nb : 1);
-            if (walk) { if (ext) trace_tail_kernel<true, true><<<grid, WAVE_THREADS, 0, st>>>(p); else trace_tail_kernel<false, true><<<grid, WAVE_THREADS, 0, st>>>(p); }
-            else if (ext) trace_tail_kernel<true, false><<<grid, WAVE_THREADS, 0, st>>>(p);
-            else trace_tail_kernel<false, false><<<grid, WAVE_THREADS, 0, st>>>(p);
-            launches++;
+            auto go = [&](cudaStream_t ts) {
+                if (walk) { if (ext) trace_tail_kernel<true, true><<<grid, WAVE_THREADS, 0, ts>>>(p); else trace_tail_kernel<false, true><<<grid, WAVE_THREADS, 0, ts>>>(p); }
+                else if (ext) trace_tail_kernel<true, false><<<grid, WAVE_THREADS, 0, ts>>>(p);
+                else trace_tail_kernel<false, false><<<grid, WAVE_THREADS, 0, ts>>>(p);
+                launches++;
+            };
+            if (ov.aux) {      // concurrent launch on the second stream (may start while the main launch, just enqueued on `st`, is running) ...
+                p.tailConcurrent = 1u;
+                cudaStreamWaitEvent(ov.aux, ov.fork, 0);
+                go(ov.aux);
+                cudaEventRecord(ov.join, ov.aux);
+                cudaStreamWaitEvent(st, ov.join, 0);
+            }
+            p.tailConcurrent = 0u;                                          // ... and the final one, in stream order: whatever is left
+            go(st);
         };
         if (share && first == 0) {                                          // one primary ray per active pixel -> primaryHits
             p.primaryMode = 1;
+            p.parkEpoch++;
+            if (tail && ov.aux) cudaEventRecord(ov.fork, st);               // everything the tail launch depends on precedes this point
             dispatch_wave(st, p, count, ext, cull, nodesMode, smCount, ((uint64_t)pixels + WAVE_THREADS - 1) / WAVE_THREADS);
             if (tail && p.coopTurns != 0u) launch_tail();
             cudaMemsetAsync(p.workCounter64, 0, 8, st);                     // rewind the work counter, keep the active-pixel count
@@ -646,7 +759,9 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool
             launches++;
         }
         p.primaryMode = share ? 2u : 0u;
+        p.parkEpoch++;
         const uint64_t need = ((uint64_t)pixels * p.sampleCount + WAVE_THREADS - 1) / WAVE_THREADS;   // never more lanes than items
+        if (tail && ov.aux) cudaEventRecord(ov.fork, st);
         dispatch_wave(st, p, count, ext, cull, nodesMode, smCount, need);
         if (tail) launch_tail();
         wave_accumulate_kernel<0><<<(pixels + 255) / 256, 256, 0, st>>>(p);

@@ -405,10 +405,21 @@ __device__ __forceinline__ void wave_step_w(const TraceScene& sc, WaveSmem<THREA
 template <bool SORTED_PUSH, int THREADS>
 __device__ __forceinline__ void wave_step_u(const TraceScene& sc, WaveSmem<THREADS>& sm, const unsigned tid, const f3 o, const f3 rinv,
                                             const float closest, const float tMinRay, uint32_t& cur, int& sp, uint32_t& qCount,
-                                            bool& travDone, uint32_t* lstack, unsigned& err, const uint32_t leafOffset) {
+                                            bool& travDone, uint32_t* lstack, unsigned& err, const uint32_t leafOffset, const uint4* smTop = nullptr) {
     if (cur != 0xFFFFFFFFu) {
+#ifdef RTB_SMEM_TOP   // A/B variant: records of the top levels come from the CTA's shared-memory copy (ids tagged with bit 31)
+        f8 h0, h1;
+        if (cur & 0x80000000u) {
+            const float4* r = reinterpret_cast<const float4*>(smTop) + 4u * (cur & 0x7FFFFFFFu);
+            h0.lo = r[0]; h0.hi = r[1]; h1.lo = r[2]; h1.hi = r[3];
+        } else {
+            const uint4* rp = sc.wide + 4ull * cur;
+            h0 = ldg256(rp); h1 = ldg256(rp + 2);
+        }
+#else
         const uint4* rp = sc.wide + 4ull * cur;
         const f8 h0 = ldg256(rp), h1 = ldg256(rp + 2);
+#endif
         const uint32_t w3 = __float_as_uint(h0.lo.w);
         const uint32_t lox = __float_as_uint(h0.hi.x), loy = __float_as_uint(h0.hi.y), loz = __float_as_uint(h0.hi.z),
                        hix = __float_as_uint(h0.hi.w), hiy = __float_as_uint(h1.lo.x), hiz = __float_as_uint(h1.lo.y);

@@ -1,0 +1,24 @@
+# every command is wrapped in `timeout`: a kernel that waits on another must never hold the box
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+T="timeout -k 5 300"
+$T python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r02d_pytest_gpu.txt
+cat gpurun_out/r02d_pytest_gpu.txt
+B="timeout -k 5 180 python bench.py --breakdown none --min-seconds 0 --no-cpu-baseline --steps 10 --warmup 2"
+J='import json,sys; d=json.loads(sys.stdin.read()); print(d["ms_per_step"], d["breakdown"]["trace_ms"], d["breakdown"]["bvh_build_ms"], d["frame_check"]["status"], d["e2e"]["ms_per_step"], d["gpu_launches"])'
+for ov in 1 0; do
+  echo "overlap=$ov full" >> gpurun_out/r02d_ab.txt
+  RTB_WAVE_TAIL_OVERLAP=$ov $B 2>>gpurun_out/r02d_err.txt | python -c "$J" >> gpurun_out/r02d_ab.txt
+  echo "overlap=$ov rank0of8" >> gpurun_out/r02d_ab.txt
+  RTB_WAVE_TAIL_OVERLAP=$ov $B --emulate-rank 0/8 2>>gpurun_out/r02d_err.txt | python -c "$J" >> gpurun_out/r02d_ab.txt
+done
+for cfg in C1 C3 C4 C5; do
+  echo "$cfg" >> gpurun_out/r02d_ab.txt
+  $B --config $cfg --steps 3 --warmup 1 2>>gpurun_out/r02d_err.txt | python -c "$J" >> gpurun_out/r02d_ab.txt
+done
+cat gpurun_out/r02d_ab.txt
+tail -c 600 gpurun_out/r02d_err.txt
+timeout -k 5 400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "walk_counters or tail_handover_forced" > gpurun_out/r02d_memcheck.txt 2>&1; echo "memcheck rc=$?" >> gpurun_out/r02d_memcheck.txt
+tail -5 gpurun_out/r02d_memcheck.txt
+echo done
