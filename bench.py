@@ -653,6 +653,10 @@ class Frame:
                     if ent and S.world == 1 and not self.emu:
                         traffic, lim = ent.get("dram_bytes_per_launch"), ent.get("limiter")
                         out["traffic_source"] = ent.get("source")
+                        # ncu's count of distinct 32-byte sectors the global loads of the trace launches requested, beside this run's
+                        # own estimate of the same quantity: coalesced records + the other loads (agreement: the counters count what runs)
+                        out["l1tex_global_load_sector_bytes_ncu"] = ent.get("l1tex_global_load_sector_bytes")
+                        out["l1tex_global_load_sector_bytes_counted"] = int(wb["load_bytes"] - wb["record_bytes"] + wb["coalesced_record_bytes"])
                 except Exception:  # noqa: BLE001
                     pass
             out["traffic"] = traffic

@@ -5,8 +5,9 @@
         --clock-control none -k regex:trace_ --csv --log-file gpurun_out/traffic_C2.csv python bench.py --config C2 --steps 1 --warmup 1 ...
     python profiles/collect_traffic.py gpurun_out/traffic_C2.csv C2
 
-One frame of the production path = [primary-hit launch of trace_wave_kernel, trace_tail_kernel,] main launch of trace_wave_kernel,
-trace_tail_kernel; the LAST such group of un-instrumented kernels (template argument COUNT = 0) in the log is taken.
+One frame of the production path = [primary-hit launch of trace_wave_kernel, trace_tail_kernel,] then per pass the main launch of
+trace_wave_kernel + trace_tail_kernel; the launches of the LAST frame of un-instrumented kernels (template argument COUNT = 0) are summed
+("per launch" = per rtb_raytrace call, like bench.py's roofline.achieved).
 """
 import csv
 import json
@@ -31,13 +32,11 @@ def main():
         u = row["Metric Unit"]
         scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1.0)
         launches[i][row["Metric Name"]] = v * scale
-    prod = [i for i in order if re.search(r"trace_wave_kernel<0, [01], 0, [34]>|trace_tail_kernel<[01], 0>", launches[i]["name"])]
-    # last frame: walk back from the end to the last main launch (the longest trace_wave_kernel among the final four)
-    tail = prod[-4:]
-    if len(tail) == 4 and "trace_wave_kernel" in launches[tail[0]]["name"] and "trace_wave_kernel" in launches[tail[2]]["name"]:
-        frame = tail
-    else:
-        frame = prod[-2:]
+    prod = [i for i in order if re.search(r"trace_wave_kernel<0, [01], 0, [034]>|trace_tail_kernel<[01], 0>", launches[i]["name"])]
+    # bench.py --steps 1 --warmup 1 renders five un-instrumented frames (warm-up, timed step, two e2e warm-ups, e2e step), each
+    # with the same launches (a frame may take several passes): the last fifth of the production launches is one frame
+    assert prod and len(prod) % 5 == 0, (len(prod), "expected 5 identical frames")
+    frame = prod[-(len(prod) // 5):]
     tot = lambda m: sum(launches[i].get(m, 0.0) for i in frame)  # noqa: E731
     main_launch = max(frame, key=lambda i: launches[i].get("gpu__time_duration.sum", 0.0))
     ent = {

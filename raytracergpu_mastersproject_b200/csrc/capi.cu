@@ -152,6 +152,7 @@ int rtb_ctx_create(int device, void* stream, rtb_ctx** out) {
     if (const char* e = getenv("RTB_WAVE_QGATE")) c->knobs.qGate = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_COOP")) c->knobs.coopMax = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_COOP_TURNS")) c->knobs.coopTurns = (uint32_t)atoi(e);
+    if (const char* e = getenv("RTB_WAVE_TAIL_SPIN_US")) c->knobs.tailSpinUs = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_SAMPLE_BUF_MB")) c->knobs.sampleBufBytes = (size_t)atoll(e) << 20;
     if (const char* e = getenv("RTB_STREAM_POOL")) c->knobs.streamPool = (size_t)atoll(e);
     *out = c;
@@ -443,7 +444,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     p.errFlag = (unsigned int*)c->errFlag.p;
     p.tMin = c->knobs.tMin;
     p.sortedPush = c->knobs.sortedPush >= 0 ? (uint32_t)c->knobs.sortedPush : (c->bS > c->bT ? 1u : 0u);   // measured: +16 % C3, -2..7 % C2/C4/C5
-    p.qGate = c->knobs.qGate; p.coopMax = c->knobs.coopMax; p.coopTurns = c->knobs.coopTurns;
+    p.qGate = c->knobs.qGate; p.coopMax = c->knobs.coopMax; p.coopTurns = c->knobs.coopTurns; p.tailSpinUs = c->knobs.tailSpinUs;
     const bool walk = (a->flags & RTB_TRACE_WALK_COUNT) != 0;
     const bool count = (a->flags & RTB_TRACE_COUNT) != 0 || walk, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;
     p.counters = walk ? nullptr : (unsigned long long*)a->counters;

@@ -160,6 +160,7 @@ struct TraceParams {
     uint32_t parkEpoch;                // ready-flag value of this launch (last word of a park record); changes with every launch that parks, so the flags never need clearing
     unsigned int* doneWarps;           // [0] warps of the main launch that have finished (and park nothing any more), [1] its CTAs that have started
     uint32_t tailConcurrent;           // trace_tail_kernel: 1 = runs beside the main launch and polls, 0 = final drain in stream order
+    uint32_t tailSpinUs;               // concurrent tail launch: upper bound of a warp's polling time
     uint32_t mainWarps;                // warps of the main launch: the concurrent tail launch leaves when doneWarps reaches it
     // wave kernel, per pass: (pixel, sample) work items
     unsigned long long* workCounter64; // [0] work-item counter, [1] (as unsigned*) active-pixel count

@@ -67,6 +67,7 @@ struct rtb_ctx {
         uint32_t qGate = 4;           // RTB_WAVE_QGATE
         uint32_t coopMax = 8;         // RTB_WAVE_COOP: tail hand-over threshold (live lanes per warp)
         uint32_t coopTurns = 32;      // RTB_WAVE_COOP_TURNS: long-ray hand-over threshold (turns)
+        uint32_t tailSpinUs = 20000;  // RTB_WAVE_TAIL_SPIN_US: polling bound of the experimental concurrent tail launch
         size_t sampleBufBytes = 4ull << 30;   // RTB_WAVE_SAMPLE_BUF_MB: per-(sample, pixel) slot budget
         size_t streamPool = 0;        // RTB_STREAM_POOL (A/B streaming kernel)
     } knobs;

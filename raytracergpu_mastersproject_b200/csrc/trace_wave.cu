@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
         // once every warp of the main launch has signed off and nothing is left -- the long rays that used to be the launch's tail are
         // worked off DURING the launch.  Deadlock freedom: a CTA of this launch that becomes resident before ALL CTAs of the (persistent)
         // main launch have started leaves at once -- it must not hold an SM slot a main CTA is waiting for -- and no warp polls for more
-        // than 20 ms; whatever is left over is finished by the FINAL launch.
+        // than tailSpinUs (20 ms); whatever is left over is finished by the FINAL launch.
         const unsigned mainCtas = p.mainWarps / (WAVE_THREADS / 32);
         if (*(volatile unsigned int*)(p.doneWarps + 1) < mainCtas) return;
         unsigned long long t0 = 0;
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TracePar
 #else
                     unsigned long long t1;
                     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-                    if (t1 - t0 > 20000000ull) break;
+                    if (t1 - t0 > (unsigned long long)p.tailSpinUs * 1000ull) break;
                     __nanosleep(400);
 #endif
                 }

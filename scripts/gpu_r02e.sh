@@ -33,3 +33,12 @@ for cfg in C3 C5; do
 done
 ls -la gpurun_out/*.ncu-rep
 echo done
+# experiment: what the concurrent tail launch waits for (polling bound 20 ms / 2 ms / 0.2 ms)
+B="timeout -k 5 120 python bench.py --breakdown none --min-seconds 0 --no-cpu-baseline --no-frame-check --steps 10 --warmup 2 --emulate-rank 0/8"
+J='import json,sys; d=json.loads(sys.stdin.read()); print(d["ms_per_step"], d["breakdown"]["trace_ms"])'
+for us in 20000 2000 200; do
+  echo "overlap=1 spin_us=$us rank0of8" >> gpurun_out/r02_tail_spin.txt
+  RTB_WAVE_TAIL_OVERLAP=1 RTB_WAVE_TAIL_SPIN_US=$us $B 2>/dev/null | python -c "$J" >> gpurun_out/r02_tail_spin.txt
+done
+cat gpurun_out/r02_tail_spin.txt
+echo done2
