@@ -244,10 +244,14 @@ struct LeafExtras {
     const uint32_t* primBounds; // ordered-int min.xyz, max.xyz of all primitives (red[6..11])
     float4* originRegion;       // [2]
     f3 cam;
+    unsigned int* bigCount;     // hoisting (pack_wide_kernel): number of big leaves, and the first MAX_BIG of them
+    uint32_t* bigList;
 };
 __device__ __forceinline__ float eta_triangle(const f3 u, const f3 v, const f3 w, const float R);
 __device__ __forceinline__ float eta_sphere(const float4 sp, const float4 lo, const float4 hi, const float R);
 __device__ __forceinline__ void origin_region_of(float4 lo, float4 hi, const f3 cam, const bool mayExtend, float4& rlo, float4& rhi);
+__device__ __forceinline__ float hoist_threshold(const uint32_t* pb);
+__device__ __forceinline__ bool box_is_big(const float mnx, const float mxx, const float mny, const float mxy, const float mnz, const float mxz, const float thr);
 // A triangle's slack grows linearly with the region's size (1e-5 R: negligible against a triangle), a sphere's with the SQUARE of its
 // diameter divided by the radius: extending the region to a distant camera would inflate every sphere box (measured on C3, 100 k spheres
 // of radius 1..4: 43.0 -> 48.7 record fetches per ray, 491 -> 552 ms).  So the region is extended only for scenes that are mostly triangles.
@@ -308,6 +312,10 @@ __global__ void __launch_bounds__(256) hlbvh_kernel(const float4* __restrict__ t
         if (EXTRAS) {
             ex.leafBox[2ull * g] = make_float4(mnx, mny, mnz, 0.f);
             ex.leafBox[2ull * g + 1] = make_float4(mxx, mxy, mxz, 0.f);
+            if (box_is_big(mnx, mxx, mny, mxy, mnz, mxz, hoist_threshold(ex.primBounds))) {
+                const unsigned int k = atomicAdd(ex.bigCount, 1u);
+                if (k < 45u) ex.bigList[k] = g;                  // MAX_BIG
+            }
         }
         uint32_t* nd = nodes + 10ull * (uint32_t)(leafOffset + (int)g);   // 40-byte records: 8-byte aligned
         reinterpret_cast<float2*>(nd)[0] = make_float2(mnx, mxx);
@@ -359,10 +367,14 @@ __global__ void __launch_bounds__(256) hlbvh_kernel(const float4* __restrict__ t
 // children.  The shader relies on `coherent`; here: L2-scoped loads (__ldcg) + __threadfence() before the
 // counter atomic.  fp min/max of fixed operands (left, right) -> deterministic whatever the arrival order.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinfo, uint32_t n, float4* pairs, float4* rootBox, float* etaNode) {
+__device__ __forceinline__ float hoist_threshold(const uint32_t* pb);
+__device__ __forceinline__ bool box_is_big(const float mnx, const float mxx, const float mny, const float mxy, const float mnz, const float mxz, const float thr);
+__global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinfo, uint32_t n, float4* pairs, float4* rootBox, float* etaNode,
+                                                    float4* tight, const uint32_t* primBounds) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const uint32_t leafOffset = n - 1;
+    const float thr = tight ? hoist_threshold(primBounds) : 0.f;
     uint32_t nodeId = __ldcg(&cinfo[leafOffset + g]).x;
     while (true) {
         const int visitations = atomicAdd(reinterpret_cast<int*>(&cinfo[nodeId]) + 1, 1);
@@ -379,6 +391,17 @@ __global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinf
         __stcg(reinterpret_cast<float2*>(nd) + 1, make_float2(gmin(ly.x, ry.x), gmax(ly.y, ry.y)));
         __stcg(reinterpret_cast<float2*>(nd) + 2, make_float2(gmin(lz.x, rz.x), gmax(lz.y, rz.y)));
         if (etaNode) __stcg(&etaNode[nodeId], fmaxf(__ldcg(&etaNode[ch.x]), __ldcg(&etaNode[ch.y])));   // largest hit-point slack of the subtree
+        if (tight) {    // union over the NON-big leaves below (hoisting, see pack_wide_kernel): an empty box has min = +inf, max = -inf
+            const float INF = __int_as_float(0x7f800000);
+            float4 tl = make_float4(INF, INF, INF, 0.f), th = make_float4(-INF, -INF, -INF, 0.f);
+            if (ch.x >= leafOffset) { if (!box_is_big(lx.x, lx.y, ly.x, ly.y, lz.x, lz.y, thr)) { tl = make_float4(lx.x, ly.x, lz.x, 0.f); th = make_float4(lx.y, ly.y, lz.y, 0.f); } }
+            else { tl = __ldcg(&tight[2ull * ch.x]); th = __ldcg(&tight[2ull * ch.x + 1]); }
+            float4 ul = make_float4(INF, INF, INF, 0.f), uh = make_float4(-INF, -INF, -INF, 0.f);
+            if (ch.y >= leafOffset) { if (!box_is_big(rx.x, rx.y, ry.x, ry.y, rz.x, rz.y, thr)) { ul = make_float4(rx.x, ry.x, rz.x, 0.f); uh = make_float4(rx.y, ry.y, rz.y, 0.f); } }
+            else { ul = __ldcg(&tight[2ull * ch.y]); uh = __ldcg(&tight[2ull * ch.y + 1]); }
+            __stcg(&tight[2ull * nodeId], make_float4(fminf(tl.x, ul.x), fminf(tl.y, ul.y), fminf(tl.z, ul.z), 0.f));
+            __stcg(&tight[2ull * nodeId + 1], make_float4(fmaxf(th.x, uh.x), fmaxf(th.y, uh.y), fmaxf(th.z, uh.z), 0.f));
+        }
         if (pairs) {    // the thread that unions a node holds both child boxes: emit the node's 64-byte traversal record here
             float4* out = pairs + 4ull * nodeId;
             out[0] = make_float4(lx.x, ly.x, lz.x, __uint_as_float(ch.x));
@@ -570,45 +593,38 @@ __global__ void __launch_bounds__(256) eta_climb_kernel(const uint32_t* __restri
 //   (lo.x lo.y lo.z hi.x hi.y hi.z), byte e = entry e, so the kernel picks a ray's near / far planes of all four entries
 //   with one select per word | 10-13: entry node indices (a leaf is leafOffset + primitive id) | 14-15 unused
 // The records are grown by the hit-point slack only if the ROOT's slack (= the scene's largest) is finite; otherwise they stay
-// tight and *cullAllowed = 0 tells the trace kernels to walk them without t-culling (decided on the device: no read-back).
-__global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* wide, const float* __restrict__ etaNode,
-                                                        unsigned int* cullAllowed) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < 2 || i >= n - 1) return;
-    bool slackOk = false;
-    if (etaNode) { const float etaRoot = etaNode[0]; slackOk = etaRoot >= 0.0f && etaRoot < 3.0e38f; }
-    if (i == 0 && cullAllowed) *cullAllowed = slackOk ? 1u : 0u;
-    const uint32_t leafOffset = n - 1;
-    // The entries are a cut through X's subtree, kept in visiting order (right before left, raytraceBVH.comp:241-244): start from
-    // X's two children and keep replacing the internal entry with the largest surface area by its own two children while a slot
-    // is free (the entry a ray is most likely to enter is the one worth resolving inside this record).
-    uint32_t entry[4]; int cnt = 2;
-    entry[0] = nodes[10ull * i + 7]; entry[1] = nodes[10ull * i + 6];
-    while (cnt < 4) {
-        int pick = -1; float best = -1.0f;
-        for (int e = 0; e < cnt; e++) {
-            if (entry[e] >= leafOffset) continue;
-            const float* b = reinterpret_cast<const float*>(nodes + 10ull * entry[e]);
-            const float dx = b[1] - b[0], dy = b[3] - b[2], dz = b[5] - b[4];
-            const float area = dx * dy + dy * dz + dz * dx;
-            if (pick < 0 || area > best) { pick = e; best = area; }
-        }
-        if (pick < 0) break;
-        const uint32_t k = entry[pick];
-        for (int e = cnt; e > pick + 1; e--) entry[e] = entry[e - 1];
-        entry[pick] = nodes[10ull * k + 7]; entry[pick + 1] = nodes[10ull * k + 6];
-        cnt++;
-    }
-    float lo[4][3], hi[4][3], org[3], top[3];
+// tight and flags[0] = 0 tells the trace kernels to walk them without t-culling (decided on the device: no read-back).
+// ---- Hoisting of BIG primitives (round 2).  A primitive whose leaf box has more than 1/256 of the surface area of the scene's box (a wall,
+// a floor, a light panel) sits somewhere deep in the Morton-order tree and inflates every ancestor's box to room size: a ray that starts inside
+// such a box can never drop it by t, so EVERY ray walks the whole chain of inflated records (C2: 6 such triangles, 7 records on every ray's
+// path, 24 % of all traverse steps).  The order-free walk does not care where a leaf hangs, so the derived records (not the reference-layout
+// node array, which stays the reference's) take the big leaves out of the hierarchy: `tight` boxes are the unions over the NON-big leaves
+// (computed by the refit climb beside the reference's boxes), entries that are big leaves or have nothing but big leaves below them are
+// dropped from the cuts (single-child chains collapse on the way), and a short chain of extra records in front of the root -- three big
+// leaves and a link each -- presents the big leaves to every ray directly.  At most MAX_BIG of them; beyond that (or with none) nothing is hoisted.
+constexpr uint32_t MAX_BIG = 45;
+struct HoistInfo {
+    const float4* tight;            // [N-1][2] (min.xyz, -) (max.xyz, -) per internal node; an empty box has min > max.  null = no hoisting
+    const unsigned int* bigCount;   // number of big leaves the leaf pass found
+    const uint32_t* bigList;        // the first MAX_BIG of them (primitive ids)
+    const uint32_t* primBounds;     // ordered-int bounds of all primitives (model_to_world_enclosing_kernel)
+};
+__device__ __forceinline__ float hoist_threshold(const uint32_t* pb) {
+    const float dx = ord2f(pb[3]) - ord2f(pb[0]), dy = ord2f(pb[4]) - ord2f(pb[1]), dz = ord2f(pb[5]) - ord2f(pb[2]);
+    return (dx * dy + dy * dz + dz * dx) * (1.0f / 256.0f);
+}
+__device__ __forceinline__ bool box_is_big(const float mnx, const float mxx, const float mny, const float mxy, const float mnz, const float mxz, const float thr) {
+    const float dx = mxx - mnx, dy = mxy - mny, dz = mxz - mnz;
+    return dx * dy + dy * dz + dz * dx > thr;      // false for a NaN threshold or box
+}
+
+// quantise up to four entry boxes OUTWARD to 8 bits per plane relative to the record's origin / power-of-two scales and store the record
+__device__ __forceinline__ void store_wide_record(uint4* out, const int cnt, const float (*lo)[3], const float (*hi)[3], const uint32_t* ids, const uint32_t leafMask) {
+    float org[3], top[3];
     for (int k = 0; k < 3; k++) { org[k] = __int_as_float(0x7f800000); top[k] = __int_as_float(0xff800000); }
-    for (int e = 0; e < cnt; e++) {
-        const float* b = reinterpret_cast<const float*>(nodes + 10ull * entry[e]);
-        const float eta = slackOk ? etaNode[entry[e]] : 0.0f;                          // largest hit-point slack in the entry's subtree
-        for (int k = 0; k < 3; k++) {
-            lo[e][k] = __fsub_rd(b[2 * k], eta); hi[e][k] = __fadd_ru(b[2 * k + 1], eta);
-            org[k] = fminf(org[k], lo[e][k]); top[k] = fmaxf(top[k], hi[e][k]);
-        }
-    }
+    for (int e = 0; e < cnt; e++)
+        for (int k = 0; k < 3; k++) { org[k] = fminf(org[k], lo[e][k]); top[k] = fmaxf(top[k], hi[e][k]); }
+    if (cnt == 0) { org[0] = org[1] = org[2] = 0.f; top[0] = top[1] = top[2] = 0.f; }
     uint32_t E[3], q[24];
     for (int j = 0; j < 24; j++) q[j] = 0;
     for (int k = 0; k < 3; k++) {
@@ -629,32 +645,119 @@ __global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restri
             q[4 * (3 + k) + e] = (uint32_t)qh;
         }
     }
-    uint32_t meta = 0, ids[4] = { 0, 0, 0, 0 };
-    for (int e = 0; e < cnt; e++) {
-        const bool leaf = entry[e] >= leafOffset;
-        meta |= (leaf ? 1u : 0u) << e;
-        meta |= 1u << (4 + e);
-        ids[e] = entry[e];
-    }
+    uint32_t meta = leafMask & 0xFu;
+    for (int e = 0; e < cnt; e++) meta |= 1u << (4 + e);
     uint32_t w[16];
     w[0] = __float_as_uint(org[0]); w[1] = __float_as_uint(org[1]); w[2] = __float_as_uint(org[2]);
     w[3] = E[0] | (E[1] << 8) | (E[2] << 16) | (meta << 24);
     for (int j = 0; j < 6; j++) w[4 + j] = q[4 * j] | (q[4 * j + 1] << 8) | (q[4 * j + 2] << 16) | (q[4 * j + 3] << 24);
-    for (int e = 0; e < 4; e++) w[10 + e] = ids[e];
+    for (int e = 0; e < 4; e++) w[10 + e] = e < cnt ? ids[e] : 0u;
     w[14] = 0; w[15] = 0;
-    uint4* out = wide + 4ull * i;
     for (int j = 0; j < 4; j++) out[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+}
+
+// flags[0] = 1: the records were grown by a finite hit-point slack, the walk may cull by t | flags[1] = record the walk starts at
+__global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* wide, const float* __restrict__ etaNode,
+                                                        unsigned int* flags, const HoistInfo h) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < 2 || i >= n - 1) return;
+    bool slackOk = false;
+    if (etaNode) { const float etaRoot = etaNode[0]; slackOk = etaRoot >= 0.0f && etaRoot < 3.0e38f; }
+    if (i == 0 && flags) { flags[0] = slackOk ? 1u : 0u; flags[1] = 0u; }
+    const uint32_t leafOffset = n - 1;
+    bool hoist = false; float thr = 0.f;
+    if (h.tight) { const unsigned int nb = *h.bigCount; hoist = nb > 0u && nb <= MAX_BIG; if (hoist) thr = hoist_threshold(h.primBounds); }
+    // box of an entry as the records see it; false = the entry is not part of the derived hierarchy (a hoisted leaf, or nothing but hoisted leaves below)
+    auto entry_box = [&](const uint32_t e, float* lo3, float* hi3) -> bool {
+        if (e < leafOffset && hoist) {
+            const float4 l = h.tight[2ull * e], u = h.tight[2ull * e + 1];
+            lo3[0] = l.x; lo3[1] = l.y; lo3[2] = l.z; hi3[0] = u.x; hi3[1] = u.y; hi3[2] = u.z;
+            return l.x <= u.x;
+        }
+        const float* b = reinterpret_cast<const float*>(nodes + 10ull * e);
+        lo3[0] = b[0]; lo3[1] = b[2]; lo3[2] = b[4]; hi3[0] = b[1]; hi3[1] = b[3]; hi3[2] = b[5];
+        return !(hoist && e >= leafOffset && box_is_big(b[0], b[1], b[2], b[3], b[4], b[5], thr));
+    };
+    // The entries are a cut through X's subtree, kept in visiting order (right before left, raytraceBVH.comp:241-244): start from
+    // X's two children and keep replacing the internal entry with the largest surface area by its own two children while a slot
+    // is free (the entry a ray is most likely to enter is the one worth resolving inside this record).
+    uint32_t entry[5]; int cnt = 0;
+    float lo[5][3], hi[5][3];
+    { const uint32_t c[2] = { nodes[10ull * i + 7], nodes[10ull * i + 6] };
+      for (int k = 0; k < 2; k++) if (entry_box(c[k], lo[cnt], hi[cnt])) entry[cnt++] = c[k]; }
+    for (int guard = 0; guard < 256; guard++) {
+        int pick = -1; float best = -1.0f;
+        for (int e = 0; e < cnt; e++) {
+            if (entry[e] >= leafOffset) continue;
+            const float dx = hi[e][0] - lo[e][0], dy = hi[e][1] - lo[e][1], dz = hi[e][2] - lo[e][2];
+            const float area = dx * dy + dy * dz + dz * dx;
+            if (pick < 0 || area > best) { pick = e; best = area; }
+        }
+        if (pick < 0) break;
+        const uint32_t k = entry[pick];
+        const uint32_t c[2] = { nodes[10ull * k + 7], nodes[10ull * k + 6] };
+        float cl[2][3], chh[2][3]; bool ok[2];
+        for (int j = 0; j < 2; j++) ok[j] = entry_box(c[j], cl[j], chh[j]);
+        const int add = (ok[0] ? 1 : 0) + (ok[1] ? 1 : 0);
+        if (cnt - 1 + add > 4) break;                          // both children are real and the record is full: X stays an entry
+        // replace entry `pick` by its real children (in visiting order); an only child takes its place, none removes it
+        for (int e = pick; e + 1 < cnt; e++) { entry[e] = entry[e + 1]; for (int a = 0; a < 3; a++) { lo[e][a] = lo[e + 1][a]; hi[e][a] = hi[e + 1][a]; } }
+        cnt--;
+        for (int j = 1; j >= 0; j--) {
+            if (!ok[j]) continue;
+            for (int e = cnt; e > pick; e--) { entry[e] = entry[e - 1]; for (int a = 0; a < 3; a++) { lo[e][a] = lo[e - 1][a]; hi[e][a] = hi[e - 1][a]; } }
+            entry[pick] = c[j]; for (int a = 0; a < 3; a++) { lo[pick][a] = cl[j][a]; hi[pick][a] = chh[j][a]; }
+            cnt++;
+        }
+        if (!hoist && cnt >= 4) break;
+    }
+    uint32_t leafMask = 0;
+    for (int e = 0; e < cnt; e++) {
+        const float eta = slackOk ? etaNode[entry[e]] : 0.0f;                          // largest hit-point slack in the entry's subtree
+        for (int k = 0; k < 3; k++) { lo[e][k] = __fsub_rd(lo[e][k], eta); hi[e][k] = __fadd_ru(hi[e][k], eta); }
+        if (entry[e] >= leafOffset) leafMask |= 1u << e;
+    }
+    store_wide_record(wide + 4ull * i, cnt, lo, hi, entry, leafMask);
+}
+
+// The records in front of the root that present the hoisted big leaves to every ray: record k (at index n - 1 + k) = big leaves 3k .. 3k+2 and
+// a link to record k + 1, the last one to the root's own record.  One thread: at most 15 records.
+__global__ void pack_top_records_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* wide, const float* __restrict__ etaNode,
+                                        unsigned int* flags, const HoistInfo h) {
+    if (blockIdx.x != 0 || threadIdx.x != 0 || n < 2 || !h.tight) return;
+    const unsigned int nb = *h.bigCount;
+    if (nb == 0u || nb > MAX_BIG) return;
+    const float etaRoot = etaNode[0];
+    const bool slackOk = etaRoot >= 0.0f && etaRoot < 3.0e38f;
+    const uint32_t leafOffset = n - 1, K = (nb + 2u) / 3u;
+    for (uint32_t k = 0; k < K; k++) {
+        float lo[4][3], hi[4][3]; uint32_t ids[4]; int cnt = 0; uint32_t leafMask = 0;
+        for (uint32_t j = 3u * k; j < nb && j < 3u * k + 3u; j++) {
+            const uint32_t e = leafOffset + h.bigList[j];
+            const float* b = reinterpret_cast<const float*>(nodes + 10ull * e);
+            const float eta = slackOk ? etaNode[e] : 0.0f;
+            for (int a = 0; a < 3; a++) { lo[cnt][a] = __fsub_rd(b[2 * a], eta); hi[cnt][a] = __fadd_ru(b[2 * a + 1], eta); }
+            ids[cnt] = e; leafMask |= 1u << cnt; cnt++;
+        }
+        {   // the link: everything else lies inside the root's (reference) box
+            const float* b = reinterpret_cast<const float*>(nodes);
+            const float eta = slackOk ? etaRoot : 0.0f;
+            for (int a = 0; a < 3; a++) { lo[cnt][a] = __fsub_rd(b[2 * a], eta); hi[cnt][a] = __fadd_ru(b[2 * a + 1], eta); }
+            ids[cnt] = k + 1u < K ? leafOffset + k + 1u : 0u; cnt++;
+        }
+        store_wide_record(wide + 4ull * (leafOffset + k), cnt, lo, hi, ids, leafMask);
+    }
+    flags[1] = leafOffset;                                       // the walk starts at the first of them
 }
 
 #ifdef RTB_SMEM_TOP
 // A/B variant "top tree levels staged in shared memory": the first RTB_SMEM_TOP records of the 4-ary hierarchy in breadth-first
 // order, copied into a table whose internal entry ids are replaced by TOP_FLAG | table index when the entry is in the table too.
 // One thread (sequential breadth-first queue): measurement aid, not tuned.
-__global__ void build_top_table_kernel(const uint4* __restrict__ wide, uint32_t n, uint4* top, uint32_t* topGlobal) {
+__global__ void build_top_table_kernel(const uint4* __restrict__ wide, uint32_t n, uint4* top, uint32_t* topGlobal, const unsigned int* flags) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    const uint32_t leafOffset = n - 1;
     uint32_t count = 1;
-    topGlobal[0] = 0;
+    topGlobal[0] = flags[1];                                     // the record the walk starts at (pack_top_records_kernel)
     for (uint32_t i = 0; i < RTB_SMEM_TOP; i++) {
         if (i >= count) { for (int j = 0; j < 4; j++) top[4 * i + j] = make_uint4(0, 0, 0, 0); topGlobal[i] = 0; continue; }
         uint4 r[4];
@@ -663,7 +766,7 @@ __global__ void build_top_table_kernel(const uint4* __restrict__ wide, uint32_t 
         uint32_t ids[4] = { r[2].z, r[2].w, r[3].x, r[3].y };
         for (int e = 0; e < 4; e++) {
             const bool present = (meta >> (4 + e)) & 1u, leaf = (meta >> e) & 1u;
-            if (!present || leaf || ids[e] >= leafOffset || count >= RTB_SMEM_TOP) continue;
+            if (!present || leaf || count >= RTB_SMEM_TOP) continue;
             topGlobal[count] = ids[e];
             ids[e] = 0x80000000u | count;
             count++;
@@ -672,8 +775,8 @@ __global__ void build_top_table_kernel(const uint4* __restrict__ wide, uint32_t 
         for (int j = 0; j < 4; j++) top[4 * i + j] = r[j];
     }
 }
-void launch_build_top_table(cudaStream_t st, const void* wide, uint32_t n, void* top, void* topGlobal) {
-    build_top_table_kernel<<<1, 32, 0, st>>>((const uint4*)wide, n, (uint4*)top, (uint32_t*)topGlobal);
+void launch_build_top_table(cudaStream_t st, const void* wide, uint32_t n, void* top, void* topGlobal, const unsigned int* flags) {
+    build_top_table_kernel<<<1, 32, 0, st>>>((const uint4*)wide, n, (uint4*)top, (uint32_t*)topGlobal, flags);
 }
 #endif
 
@@ -750,15 +853,18 @@ void launch_hlbvh(cudaStream_t st, const void* tris, uint32_t T, const void* sph
 // K5 of the fused build: also writes the exact leaf boxes, the packed primitive records and the per-primitive hit-point slack
 void launch_hlbvh_fused(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const uint32_t* codes, void* nodes,
                         void* cinfo, void* leafBox, void* ptris, void* psphs, void* sphMat, float* etaNode, const uint32_t* primBounds,
-                        void* originRegion, const float* camPos) {
+                        void* originRegion, const float* camPos, unsigned int* bigCount, uint32_t* bigList) {
     Codes c{ codes, 1, (int)(T + S) };
+    cudaMemsetAsync(bigCount, 0, sizeof(unsigned int), st);
     LeafExtras ex{ (float4*)leafBox, (float4*)ptris, (float4*)psphs, (uint32_t*)sphMat, etaNode, primBounds, (float4*)originRegion,
-                   F3(camPos[0], camPos[1], camPos[2]) };
+                   F3(camPos[0], camPos[1], camPos[2]), bigCount, bigList };
     hlbvh_kernel<true><<<blocks_for((uint64_t)T + S, 256), 256, 0, st>>>((const float4*)tris, T, (const float4*)sphs, S, c,
                                                                          (uint32_t*)nodes, (uint2*)cinfo, ex);
 }
-void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox, float* etaNode) {
-    refit_kernel<<<blocks_for(n, 256), 256, 0, st>>>((uint32_t*)nodes, (uint2*)cinfo, n, (float4*)pairs, (float4*)rootBox, etaNode);
+void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox, float* etaNode, void* tight,
+                  const uint32_t* primBounds) {
+    refit_kernel<<<blocks_for(n, 256), 256, 0, st>>>((uint32_t*)nodes, (uint2*)cinfo, n, (float4*)pairs, (float4*)rootBox, etaNode,
+                                                     (float4*)tight, primBounds);
 }
 // K1 + K2 in one pass (fused build).  Returns #launches.
 int launch_model_to_world_enclosing(cudaStream_t st, const void* models, void* tris, uint32_t T, void* sphs, uint32_t S, uint32_t* red,
@@ -775,9 +881,15 @@ void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pai
 void launch_pack_cnodes(cudaStream_t st, const void* nodes, uint32_t n, void* cnodes, void* leafBox) {
     pack_cnodes_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)cnodes, (float4*)leafBox);
 }
-void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode, unsigned int* cullAllowed) {
-    if (n < 2) return;
-    pack_wide_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)wide, etaNode, cullAllowed);
+// tight != NULL: hoist the big leaves (see pack_wide_kernel); `wide` then needs room for n - 1 + 16 records.  Returns #launches.
+int launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode, unsigned int* flags, const void* tight,
+                     const unsigned int* bigCount, const uint32_t* bigList, const uint32_t* primBounds) {
+    if (n < 2) return 0;
+    const HoistInfo h{ (const float4*)tight, bigCount, bigList, primBounds };
+    pack_wide_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)wide, etaNode, flags, h);
+    if (!tight) return 1;
+    pack_top_records_kernel<<<1, 32, 0, st>>>((const uint32_t*)nodes, n, (uint4*)wide, etaNode, flags, h);
+    return 2;
 }
 // etaNode[2n-1] <- per-node hit-point slack; parent[2n-1], arrivals[n-1] are scratch.  Returns #launches.
 int launch_eta(cudaStream_t st, const void* nodes, uint32_t n, const void* ptris, uint32_t T, const void* psphs, uint32_t S,

@@ -104,10 +104,12 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
 #ifdef RTB_SMEM_TOP
     __shared__ uint4 smTop[NODES >= 3 ? RTB_SMEM_TOP * 4 : 1];
     if (NODES >= 3) { for (unsigned i = tid; i < RTB_SMEM_TOP * 4; i += WAVE_THREADS) smTop[i] = p.sc.top[i]; __syncthreads(); }
-    constexpr uint32_t ROOT = NODES >= 3 ? 0x80000000u : 0u;
+#define RTB_ROOT_RECORD() (NODES >= 3 ? 0x80000000u : 0u)          /* entry 0 of the table = the record the walk starts at */
 #else
     const uint4* smTop = nullptr;
-    constexpr uint32_t ROOT = 0u;
+    // the record the walk starts at: the root's, or the first of the records that hold the hoisted big leaves (pack_top_records_kernel);
+    // re-read per ray (an L1 hit) rather than held in a register: the kernel sits exactly at its 72-register budget
+#define RTB_ROOT_RECORD() (NODES >= 3 ? __ldg(p.cullAllowed + 1) : 0u)
 #endif
     const unsigned lane = tid & 31;
     const TraceScene& sc = p.sc;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             }
             if (box_test(o, d, rinv, exactOnly, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) {
                 if (sc.N == 1) enqueue(0u);                                                // the root is the only leaf
-                else { cur = exactOnly ? 0u : ROOT; travDone = false; }
+                else { cur = exactOnly ? 0u : RTB_ROOT_RECORD(); travDone = false; }
             }
         }
 #ifdef RTB_TAIL_PROBE
@@ -443,7 +445,7 @@ __device__ __forceinline__ void tail_item(const TraceParams& p, const uint32_t i
                     rec.mat = __float_as_uint(q6.x); rec.prim = __float_as_uint(q6.y); rec.back = (int)__float_as_uint(q6.z);
                 }
                 resume = 0;
-            } else if (lane == 0) stk[0] = 0u;
+            } else if (lane == 0) stk[0] = p.cullAllowed[1];              // the record the walk starts at (pack_top_records_kernel)
             __syncwarp();
             while (n > 0) {
                 if (COUNT && lane == 0) tl.tailTurns++;

@@ -86,3 +86,49 @@ def test_culled_walk_equals_exact_walk_and_hits_stay_within_eta(device, block):
                                         f"eta = {eta[g][np.argmax(worst)]:.3e}")
             checked_hits += int(hit.sum())
     assert checked_hits > 1000 and culled_scenes >= 20, (checked_hits, culled_scenes)    # most scenes really run the t-culled walk
+
+
+@pytest.mark.parametrize("n_big", [0, 1, 3, 4, 7, 45, 46, 120])
+def test_hoisted_big_primitives(device, n_big):
+    """Scenes of >= 8192 primitives take the fused build, whose derived records hoist the BIG leaves (boxes above 1/256 of the scene's
+    surface area) out of the hierarchy into a chain of records in front of the root (bvh_build.cu pack_wide_kernel): none, fewer than one
+    record's worth, exactly full records, the maximum (45), one too many (nothing is hoisted) and far too many; big triangles AND big
+    spheres, overlapping each other and the small geometry, duplicated (equal-t ties between a hoisted and an in-tree primitive).  The
+    production frame must equal the exact-record walk's bit for bit, shared and unshared primaries, and the reference-order walk over
+    the un-hoisted records must too."""
+    from raytracergpu_mastersproject_b200 import Raytracer, capi
+    rng = np.random.default_rng(77 + n_big)
+    nt = 9000
+    T = np.zeros(nt + n_big + (2 if n_big else 0), O.TRIANGLE)
+    c = rng.uniform(100, 450, (nt, 3)); sz = rng.uniform(1, 6, (nt, 1))
+    T["v0"][:nt, :3] = c + rng.normal(size=(nt, 3)) * sz; T["v1"][:nt, :3] = c + rng.normal(size=(nt, 3)) * sz; T["v2"][:nt, :3] = c + rng.normal(size=(nt, 3)) * sz
+    T["materialIndex"][:nt] = rng.integers(1, 4, nt)
+    for k in range(n_big):                                   # big triangles: walls, floors, slanted sheets through the cloud
+        a = rng.uniform(0, 550, 3); u = rng.normal(size=3); v = rng.normal(size=3)
+        u *= rng.uniform(300, 700) / np.linalg.norm(u); v *= rng.uniform(300, 700) / np.linalg.norm(v)
+        T["v0"][nt + k, :3] = a; T["v1"][nt + k, :3] = a + u; T["v2"][nt + k, :3] = a + v
+        T["materialIndex"][nt + k] = 0 if k == 0 else int(rng.integers(1, 4))
+    if n_big:                                                # an exact duplicate of a small triangle made big's neighbour, and of a big one
+        T[nt + n_big] = T[nt]; T[nt + n_big + 1] = T[5]
+    ns = 40 + (3 if n_big else 0)
+    S = np.zeros(ns, O.SPHERE)
+    S["center"][:, :3] = rng.uniform(100, 450, (ns, 3)); S["radius"] = rng.uniform(2, 12, ns); S["materialIndex"] = rng.integers(1, 4, ns)
+    if n_big:
+        S["radius"][-3:] = (160.0, 220.0, 90.0)              # big spheres: hoisted too
+    M = np.zeros(1, O.MODEL); M["m"][0] = np.eye(4, dtype=np.float32).reshape(16)
+    MT = np.zeros(4, O.MATERIAL)
+    for i, (a, t) in enumerate([((12, 12, 12), 0), ((0.7, 0.7, 0.7), 1), ((0.6, 0.3, 0.2), 1), ((0.2, 0.5, 0.7), 1)]):
+        MT["albedo"][i, :3] = a; MT["materialType"][i] = t
+    sc = dict(models=M, triangles=T, spheres=S, materials=MT)
+    W, H, spp = 64, 40, 3
+    for cam, look in [((275.0, 275.0, -800.0), (275.0, 275.0, 0.0)), ((300.0, 260.0, 240.0), (100.0, 300.0, 500.0))]:
+        ubo = SU.ubo_with_camera(sc, cam, look, max_depth=8, random_state=5)
+        rt = Raytracer(device, W, H)
+        rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+        rt.build_bvh(ubo)
+        rt.clear_image(); rt.raytrace(ubo, spp, flags=capi.TRACE_EXACT_NODES | capi.TRACE_NO_PRIMARY_SHARING); device.wait_idle()
+        exact = rt.read_image()
+        for fl in (0, capi.TRACE_NO_PRIMARY_SHARING, capi.TRACE_REFERENCE_ORDER, capi.TRACE_CULLED):
+            rt.clear_image(); rt.raytrace(ubo, spp, flags=fl); device.wait_idle()
+            bad = int((_bits(rt.read_image()) != _bits(exact)).any(axis=-1).sum())
+            assert bad == 0, f"{n_big} big primitives, camera {cam}, flags {fl}: {bad} pixels differ from the exact-record walk"
