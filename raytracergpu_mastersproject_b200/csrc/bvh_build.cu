@@ -4,6 +4,7 @@
 //
 // Output contract: the HLBVHNode[2N-1] / MortonPrimitive[N] / enclosing-AABB buffers are bit-identical to what
 // the reference's shaders leave in their SSBOs (as pinned in DESIGN.md); every kernel cites the shader it replaces.
+#include "build_shared.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -47,13 +48,6 @@ __global__ void __launch_bounds__(256) model_to_world_kernel(const float4* __res
 // grid-wide reduction: registers -> warp redux -> global atomics on order-preserving integer images of the
 // floats (total order, -0 < +0, so the result is independent of the reduction order).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t f2ord(float f) {
-    const uint32_t b = __float_as_uint(f);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float ord2f(uint32_t u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
-}
 __device__ __forceinline__ f3 prim_center(const float4* __restrict__ tris, uint32_t T, const float4* __restrict__ sphs, uint32_t i) {
     if (i < T) {  // getTriangleCenter: ((v0 + v1 + v2) / 3).xyz  (GetEnclosingAABB.comp:40-42)
         const float4 a = tris[4ull * i], b = tris[4ull * i + 1], c = tris[4ull * i + 2];
@@ -218,18 +212,6 @@ __global__ void __launch_bounds__(256) morton_repack_kernel(const uint32_t* __re
 // ---------------------------------------------------------------------------------------------------------
 // K5  ConstructHLBVH.comp -- Karras topology over the sorted codes + leaf boxes in ORIGINAL primitive order
 // ---------------------------------------------------------------------------------------------------------
-struct Codes {
-    const uint32_t* __restrict__ p; uint32_t stride; int n;
-    __device__ __forceinline__ uint32_t operator[](int i) const { return __ldg(p + (size_t)i * stride); }
-};
-// countLeadingZeroesFromDifference :58-70 ; 31 - findMSB(x) == clz(x) for x != 0
-__device__ __forceinline__ int delta(const Codes& c, int i, uint32_t codeI, int j) {
-    if (j < 0 || j > c.n - 1) return -1;
-    const uint32_t codeJ = c[j];
-    if (codeI == codeJ) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
-    return __clz(codeI ^ codeJ);
-}
-
 __device__ __forceinline__ void pad_axis(float& lo, float& hi) {          // padAABB :41-54
     if (hi - lo < 0.001f) { lo -= 0.0005f; hi += 0.0005f; }
 }
@@ -244,14 +226,14 @@ struct LeafExtras {
     const uint32_t* primBounds; // ordered-int min.xyz, max.xyz of all primitives (red[6..11])
     float4* originRegion;       // [2]
     f3 cam;
-    unsigned int* bigCount;     // hoisting (pack_wide_kernel): number of big leaves, and the first MAX_BIG of them
+    unsigned int* bigCount;     // traversal hierarchy (traversal_tree.cu): number of big leaves, the first MAX_BIG of them,
     uint32_t* bigList;
+    uint32_t* smallBounds;      // and the ordered-int bounds of the centres of all the others
 };
 __device__ __forceinline__ float eta_triangle(const f3 u, const f3 v, const f3 w, const float R);
 __device__ __forceinline__ float eta_sphere(const float4 sp, const float4 lo, const float4 hi, const float R);
 __device__ __forceinline__ void origin_region_of(float4 lo, float4 hi, const f3 cam, const bool mayExtend, float4& rlo, float4& rhi);
-__device__ __forceinline__ float hoist_threshold(const uint32_t* pb);
-__device__ __forceinline__ bool box_is_big(const float mnx, const float mxx, const float mny, const float mxy, const float mnz, const float mxz, const float thr);
+
 // A triangle's slack grows linearly with the region's size (1e-5 R: negligible against a triangle), a sphere's with the SQUARE of its
 // diameter divided by the radius: extending the region to a distant camera would inflate every sphere box (measured on C3, 100 k spheres
 // of radius 1..4: 43.0 -> 48.7 record fetches per ray, 491 -> 552 ms).  So the region is extended only for scenes that are mostly triangles.
@@ -263,6 +245,7 @@ __global__ void __launch_bounds__(256) hlbvh_kernel(const float4* __restrict__ t
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = (int)(T + S);
     const int leafOffset = n - 1;
+    uint32_t sb[6] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };   // EXTRAS: ordered-int centre of this leaf if it is not big
     if (g < (uint32_t)n) {  // leaf :152-169
         float mnx, mxx, mny, mxy, mnz, mxz;
         uint32_t type, prim;
@@ -312,9 +295,13 @@ __global__ void __launch_bounds__(256) hlbvh_kernel(const float4* __restrict__ t
         if (EXTRAS) {
             ex.leafBox[2ull * g] = make_float4(mnx, mny, mnz, 0.f);
             ex.leafBox[2ull * g + 1] = make_float4(mxx, mxy, mxz, 0.f);
+            // traversal hierarchy (traversal_tree.cu): the BIG leaves are listed, the centres of the others are bounded (block reduction below)
             if (box_is_big(mnx, mxx, mny, mxy, mnz, mxz, hoist_threshold(ex.primBounds))) {
                 const unsigned int k = atomicAdd(ex.bigCount, 1u);
-                if (k < 45u) ex.bigList[k] = g;                  // MAX_BIG
+                if (k < MAX_BIG) ex.bigList[k] = g;
+            } else {
+                const float cx = 0.5f * (mnx + mxx), cy = 0.5f * (mny + mxy), cz = 0.5f * (mnz + mxz);
+                sb[0] = sb[3] = f2ord(cx); sb[1] = sb[4] = f2ord(cy); sb[2] = sb[5] = f2ord(cz);
             }
         }
         uint32_t* nd = nodes + 10ull * (uint32_t)(leafOffset + (int)g);   // 40-byte records: 8-byte aligned
@@ -325,31 +312,8 @@ __global__ void __launch_bounds__(256) hlbvh_kernel(const float4* __restrict__ t
         reinterpret_cast<uint2*>(nd)[4] = make_uint2(prim, type);
     }
     if ((int)g < n - 1) {   // internal :172-209
-        const int id = (int)g;
-        const uint32_t codeI = codes[id];
-        // determineRange :72-96
-        const int deltaL = delta(codes, id, codeI, id - 1);
-        const int deltaR = delta(codes, id, codeI, id + 1);
-        const int dir = (deltaR >= deltaL) ? 1 : -1;
-        const int deltaMin = min(deltaL, deltaR);
-        int lMax = 2;
-        while (delta(codes, id, codeI, id + lMax * dir) > deltaMin) lMax <<= 1;
-        int l = 0;
-        for (int t = lMax >> 1; t > 0; t >>= 1)
-            if (delta(codes, id, codeI, id + (l + t) * dir) > deltaMin) l += t;
-        const int endId = id + l * dir;
-        const int first = min(id, endId), last = max(id, endId);
-        // findSplit :98-115
-        const uint32_t codeF = codes[first];
-        const int commonPrefix = delta(codes, first, codeF, last);
-        int split = first, stride = last - first;
-        do {
-            stride = (stride + 1) >> 1;
-            const int newSplit = split + stride;
-            if (newSplit < last && delta(codes, first, codeF, newSplit) > commonPrefix) split = newSplit;
-        } while (stride > 1);
-        const int leftChild = (split == first) ? leafOffset + split : split;
-        const int rightChild = (split + 1 == last) ? leafOffset + split + 1 : split + 1;
+        int leftChild, rightChild;
+        karras_children(codes, (int)g, leafOffset, leftChild, rightChild);   // determineRange :72-96, findSplit :98-115
         uint32_t* nd = nodes + 10ull * g;
         reinterpret_cast<float2*>(nd)[0] = make_float2(0.f, 0.f);
         reinterpret_cast<float2*>(nd)[1] = make_float2(0.f, 0.f);
@@ -360,6 +324,23 @@ __global__ void __launch_bounds__(256) hlbvh_kernel(const float4* __restrict__ t
         cinfo[rightChild] = make_uint2(g, 0u);
     }
     if (g == 0) cinfo[0] = make_uint2(0u, 0u);   // :212-214
+    if (EXTRAS) {                                // bounds of the non-big leaves' centres -> ex.smallBounds (ordered ints), 6 atomics per block
+        __shared__ uint32_t sm[6][8];
+        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const uint32_t r = k < 3 ? __reduce_min_sync(0xFFFFFFFFu, sb[k]) : __reduce_max_sync(0xFFFFFFFFu, sb[k]);
+            if (lane == 0) sm[k][warp] = r;
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            const int k = threadIdx.x;
+            uint32_t r = sm[k][0];
+            for (int w = 1; w < 8; w++) r = k < 3 ? min(r, sm[k][w]) : max(r, sm[k][w]);
+            if (k < 3) { if (r != 0xFFFFFFFFu) atomicMin(&ex.smallBounds[k], r); }
+            else if (r != 0u) atomicMax(&ex.smallBounds[k], r);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -367,14 +348,11 @@ __global__ void __launch_bounds__(256) hlbvh_kernel(const float4* __restrict__ t
 // children.  The shader relies on `coherent`; here: L2-scoped loads (__ldcg) + __threadfence() before the
 // counter atomic.  fp min/max of fixed operands (left, right) -> deterministic whatever the arrival order.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float hoist_threshold(const uint32_t* pb);
-__device__ __forceinline__ bool box_is_big(const float mnx, const float mxx, const float mny, const float mxy, const float mnz, const float mxz, const float thr);
-__global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinfo, uint32_t n, float4* pairs, float4* rootBox, float* etaNode,
-                                                    float4* tight, const uint32_t* primBounds) {
+
+__global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinfo, uint32_t n, float4* pairs, float4* rootBox, float* etaNode) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const uint32_t leafOffset = n - 1;
-    const float thr = tight ? hoist_threshold(primBounds) : 0.f;
     uint32_t nodeId = __ldcg(&cinfo[leafOffset + g]).x;
     while (true) {
         const int visitations = atomicAdd(reinterpret_cast<int*>(&cinfo[nodeId]) + 1, 1);
@@ -391,17 +369,6 @@ __global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinf
         __stcg(reinterpret_cast<float2*>(nd) + 1, make_float2(gmin(ly.x, ry.x), gmax(ly.y, ry.y)));
         __stcg(reinterpret_cast<float2*>(nd) + 2, make_float2(gmin(lz.x, rz.x), gmax(lz.y, rz.y)));
         if (etaNode) __stcg(&etaNode[nodeId], fmaxf(__ldcg(&etaNode[ch.x]), __ldcg(&etaNode[ch.y])));   // largest hit-point slack of the subtree
-        if (tight) {    // union over the NON-big leaves below (hoisting, see pack_wide_kernel): an empty box has min = +inf, max = -inf
-            const float INF = __int_as_float(0x7f800000);
-            float4 tl = make_float4(INF, INF, INF, 0.f), th = make_float4(-INF, -INF, -INF, 0.f);
-            if (ch.x >= leafOffset) { if (!box_is_big(lx.x, lx.y, ly.x, ly.y, lz.x, lz.y, thr)) { tl = make_float4(lx.x, ly.x, lz.x, 0.f); th = make_float4(lx.y, ly.y, lz.y, 0.f); } }
-            else { tl = __ldcg(&tight[2ull * ch.x]); th = __ldcg(&tight[2ull * ch.x + 1]); }
-            float4 ul = make_float4(INF, INF, INF, 0.f), uh = make_float4(-INF, -INF, -INF, 0.f);
-            if (ch.y >= leafOffset) { if (!box_is_big(rx.x, rx.y, ry.x, ry.y, rz.x, rz.y, thr)) { ul = make_float4(rx.x, ry.x, rz.x, 0.f); uh = make_float4(rx.y, ry.y, rz.y, 0.f); } }
-            else { ul = __ldcg(&tight[2ull * ch.y]); uh = __ldcg(&tight[2ull * ch.y + 1]); }
-            __stcg(&tight[2ull * nodeId], make_float4(fminf(tl.x, ul.x), fminf(tl.y, ul.y), fminf(tl.z, ul.z), 0.f));
-            __stcg(&tight[2ull * nodeId + 1], make_float4(fmaxf(th.x, uh.x), fmaxf(th.y, uh.y), fmaxf(th.z, uh.z), 0.f));
-        }
         if (pairs) {    // the thread that unions a node holds both child boxes: emit the node's 64-byte traversal record here
             float4* out = pairs + 4ull * nodeId;
             out[0] = make_float4(lx.x, ly.x, lz.x, __uint_as_float(ch.x));
@@ -594,160 +561,46 @@ __global__ void __launch_bounds__(256) eta_climb_kernel(const uint32_t* __restri
 //   with one select per word | 10-13: entry node indices (a leaf is leafOffset + primitive id) | 14-15 unused
 // The records are grown by the hit-point slack only if the ROOT's slack (= the scene's largest) is finite; otherwise they stay
 // tight and flags[0] = 0 tells the trace kernels to walk them without t-culling (decided on the device: no read-back).
-// ---- Hoisting of BIG primitives (round 2).  A primitive whose leaf box has more than 1/256 of the surface area of the scene's box (a wall,
-// a floor, a light panel) sits somewhere deep in the Morton-order tree and inflates every ancestor's box to room size: a ray that starts inside
-// such a box can never drop it by t, so EVERY ray walks the whole chain of inflated records (C2: 6 such triangles, 7 records on every ray's
-// path, 24 % of all traverse steps).  The order-free walk does not care where a leaf hangs, so the derived records (not the reference-layout
-// node array, which stays the reference's) take the big leaves out of the hierarchy: `tight` boxes are the unions over the NON-big leaves
-// (computed by the refit climb beside the reference's boxes), entries that are big leaves or have nothing but big leaves below them are
-// dropped from the cuts (single-child chains collapse on the way), and a short chain of extra records in front of the root -- three big
-// leaves and a link each -- presents the big leaves to every ray directly.  At most MAX_BIG of them; beyond that (or with none) nothing is hoisted.
-constexpr uint32_t MAX_BIG = 45;
-struct HoistInfo {
-    const float4* tight;            // [N-1][2] (min.xyz, -) (max.xyz, -) per internal node; an empty box has min > max.  null = no hoisting
-    const unsigned int* bigCount;   // number of big leaves the leaf pass found
-    const uint32_t* bigList;        // the first MAX_BIG of them (primitive ids)
-    const uint32_t* primBounds;     // ordered-int bounds of all primitives (model_to_world_enclosing_kernel)
-};
-__device__ __forceinline__ float hoist_threshold(const uint32_t* pb) {
-    const float dx = ord2f(pb[3]) - ord2f(pb[0]), dy = ord2f(pb[4]) - ord2f(pb[1]), dz = ord2f(pb[5]) - ord2f(pb[2]);
-    return (dx * dy + dy * dz + dz * dx) * (1.0f / 256.0f);
-}
-__device__ __forceinline__ bool box_is_big(const float mnx, const float mxx, const float mny, const float mxy, const float mnz, const float mxz, const float thr) {
-    const float dx = mxx - mnx, dy = mxy - mny, dz = mxz - mnz;
-    return dx * dy + dy * dz + dz * dx > thr;      // false for a NaN threshold or box
-}
-
-// quantise up to four entry boxes OUTWARD to 8 bits per plane relative to the record's origin / power-of-two scales and store the record
-__device__ __forceinline__ void store_wide_record(uint4* out, const int cnt, const float (*lo)[3], const float (*hi)[3], const uint32_t* ids, const uint32_t leafMask) {
-    float org[3], top[3];
-    for (int k = 0; k < 3; k++) { org[k] = __int_as_float(0x7f800000); top[k] = __int_as_float(0xff800000); }
-    for (int e = 0; e < cnt; e++)
-        for (int k = 0; k < 3; k++) { org[k] = fminf(org[k], lo[e][k]); top[k] = fmaxf(top[k], hi[e][k]); }
-    if (cnt == 0) { org[0] = org[1] = org[2] = 0.f; top[0] = top[1] = top[2] = 0.f; }
-    uint32_t E[3], q[24];
-    for (int j = 0; j < 24; j++) q[j] = 0;
-    for (int k = 0; k < 3; k++) {
-        const float ext = __fsub_ru(top[k], org[k]);
-        uint32_t ex = 1;
-        if (ext > 0.f) {
-            const uint32_t bits = __float_as_uint(__fdiv_ru(ext, 255.0f));
-            ex = (bits >> 23) + ((bits & 0x7FFFFFu) ? 1u : 0u);
-            if (ex < 1) ex = 1;
-            if (ex > 253) ex = 253;
-        }
-        E[k] = ex;
-        const float inv = __uint_as_float((254u - ex) << 23);
-        for (int e = 0; e < cnt; e++) {
-            float ql = floorf(__fsub_rd(lo[e][k], org[k]) * inv); ql = fminf(fmaxf(ql, 0.f), 255.f);
-            float qh = ceilf(__fsub_ru(hi[e][k], org[k]) * inv); qh = fminf(fmaxf(qh, 0.f), 255.f);
-            q[4 * k + e] = (uint32_t)ql;
-            q[4 * (3 + k) + e] = (uint32_t)qh;
-        }
-    }
-    uint32_t meta = leafMask & 0xFu;
-    for (int e = 0; e < cnt; e++) meta |= 1u << (4 + e);
-    uint32_t w[16];
-    w[0] = __float_as_uint(org[0]); w[1] = __float_as_uint(org[1]); w[2] = __float_as_uint(org[2]);
-    w[3] = E[0] | (E[1] << 8) | (E[2] << 16) | (meta << 24);
-    for (int j = 0; j < 6; j++) w[4 + j] = q[4 * j] | (q[4 * j + 1] << 8) | (q[4 * j + 2] << 16) | (q[4 * j + 3] << 24);
-    for (int e = 0; e < 4; e++) w[10 + e] = e < cnt ? ids[e] : 0u;
-    w[14] = 0; w[15] = 0;
-    for (int j = 0; j < 4; j++) out[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-}
-
-// flags[0] = 1: the records were grown by a finite hit-point slack, the walk may cull by t | flags[1] = record the walk starts at
+// flags[0] = 1: the records were grown by a finite hit-point slack, the walk may cull by t | flags[1] = record the walk starts at (0: the root's)
+// These are the records over the REFERENCE's tree (every leaf in its place, entries in the reference's visiting order): what the reference-order
+// walk needs, and what scenes outside the fused build get.  rtb_build_bvh derives the records of its own traversal hierarchy instead (traversal_tree.cu).
 __global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* wide, const float* __restrict__ etaNode,
-                                                        unsigned int* flags, const HoistInfo h) {
+                                                        unsigned int* flags) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < 2 || i >= n - 1) return;
     bool slackOk = false;
     if (etaNode) { const float etaRoot = etaNode[0]; slackOk = etaRoot >= 0.0f && etaRoot < 3.0e38f; }
     if (i == 0 && flags) { flags[0] = slackOk ? 1u : 0u; flags[1] = 0u; }
     const uint32_t leafOffset = n - 1;
-    bool hoist = false; float thr = 0.f;
-    if (h.tight) { const unsigned int nb = *h.bigCount; hoist = nb > 0u && nb <= MAX_BIG; if (hoist) thr = hoist_threshold(h.primBounds); }
-    // box of an entry as the records see it; false = the entry is not part of the derived hierarchy (a hoisted leaf, or nothing but hoisted leaves below)
-    auto entry_box = [&](const uint32_t e, float* lo3, float* hi3) -> bool {
-        if (e < leafOffset && hoist) {
-            const float4 l = h.tight[2ull * e], u = h.tight[2ull * e + 1];
-            lo3[0] = l.x; lo3[1] = l.y; lo3[2] = l.z; hi3[0] = u.x; hi3[1] = u.y; hi3[2] = u.z;
-            return l.x <= u.x;
-        }
-        const float* b = reinterpret_cast<const float*>(nodes + 10ull * e);
-        lo3[0] = b[0]; lo3[1] = b[2]; lo3[2] = b[4]; hi3[0] = b[1]; hi3[1] = b[3]; hi3[2] = b[5];
-        return !(hoist && e >= leafOffset && box_is_big(b[0], b[1], b[2], b[3], b[4], b[5], thr));
-    };
     // The entries are a cut through X's subtree, kept in visiting order (right before left, raytraceBVH.comp:241-244): start from
     // X's two children and keep replacing the internal entry with the largest surface area by its own two children while a slot
     // is free (the entry a ray is most likely to enter is the one worth resolving inside this record).
-    uint32_t entry[5]; int cnt = 0;
-    float lo[5][3], hi[5][3];
-    { const uint32_t c[2] = { nodes[10ull * i + 7], nodes[10ull * i + 6] };
-      for (int k = 0; k < 2; k++) if (entry_box(c[k], lo[cnt], hi[cnt])) entry[cnt++] = c[k]; }
-    for (int guard = 0; guard < 256; guard++) {
+    uint32_t entry[4]; int cnt = 2;
+    entry[0] = nodes[10ull * i + 7]; entry[1] = nodes[10ull * i + 6];
+    while (cnt < 4) {
         int pick = -1; float best = -1.0f;
         for (int e = 0; e < cnt; e++) {
             if (entry[e] >= leafOffset) continue;
-            const float dx = hi[e][0] - lo[e][0], dy = hi[e][1] - lo[e][1], dz = hi[e][2] - lo[e][2];
+            const float* b = reinterpret_cast<const float*>(nodes + 10ull * entry[e]);
+            const float dx = b[1] - b[0], dy = b[3] - b[2], dz = b[5] - b[4];
             const float area = dx * dy + dy * dz + dz * dx;
             if (pick < 0 || area > best) { pick = e; best = area; }
         }
         if (pick < 0) break;
         const uint32_t k = entry[pick];
-        const uint32_t c[2] = { nodes[10ull * k + 7], nodes[10ull * k + 6] };
-        float cl[2][3], chh[2][3]; bool ok[2];
-        for (int j = 0; j < 2; j++) ok[j] = entry_box(c[j], cl[j], chh[j]);
-        const int add = (ok[0] ? 1 : 0) + (ok[1] ? 1 : 0);
-        if (cnt - 1 + add > 4) break;                          // both children are real and the record is full: X stays an entry
-        // replace entry `pick` by its real children (in visiting order); an only child takes its place, none removes it
-        for (int e = pick; e + 1 < cnt; e++) { entry[e] = entry[e + 1]; for (int a = 0; a < 3; a++) { lo[e][a] = lo[e + 1][a]; hi[e][a] = hi[e + 1][a]; } }
-        cnt--;
-        for (int j = 1; j >= 0; j--) {
-            if (!ok[j]) continue;
-            for (int e = cnt; e > pick; e--) { entry[e] = entry[e - 1]; for (int a = 0; a < 3; a++) { lo[e][a] = lo[e - 1][a]; hi[e][a] = hi[e - 1][a]; } }
-            entry[pick] = c[j]; for (int a = 0; a < 3; a++) { lo[pick][a] = cl[j][a]; hi[pick][a] = chh[j][a]; }
-            cnt++;
-        }
-        if (!hoist && cnt >= 4) break;
+        for (int e = cnt; e > pick + 1; e--) entry[e] = entry[e - 1];
+        entry[pick] = nodes[10ull * k + 7]; entry[pick + 1] = nodes[10ull * k + 6];
+        cnt++;
     }
+    float lo[4][3], hi[4][3];
     uint32_t leafMask = 0;
     for (int e = 0; e < cnt; e++) {
+        const float* b = reinterpret_cast<const float*>(nodes + 10ull * entry[e]);
         const float eta = slackOk ? etaNode[entry[e]] : 0.0f;                          // largest hit-point slack in the entry's subtree
-        for (int k = 0; k < 3; k++) { lo[e][k] = __fsub_rd(lo[e][k], eta); hi[e][k] = __fadd_ru(hi[e][k], eta); }
+        for (int k = 0; k < 3; k++) { lo[e][k] = __fsub_rd(b[2 * k], eta); hi[e][k] = __fadd_ru(b[2 * k + 1], eta); }
         if (entry[e] >= leafOffset) leafMask |= 1u << e;
     }
     store_wide_record(wide + 4ull * i, cnt, lo, hi, entry, leafMask);
-}
-
-// The records in front of the root that present the hoisted big leaves to every ray: record k (at index n - 1 + k) = big leaves 3k .. 3k+2 and
-// a link to record k + 1, the last one to the root's own record.  One thread: at most 15 records.
-__global__ void pack_top_records_kernel(const uint32_t* __restrict__ nodes, uint32_t n, uint4* wide, const float* __restrict__ etaNode,
-                                        unsigned int* flags, const HoistInfo h) {
-    if (blockIdx.x != 0 || threadIdx.x != 0 || n < 2 || !h.tight) return;
-    const unsigned int nb = *h.bigCount;
-    if (nb == 0u || nb > MAX_BIG) return;
-    const float etaRoot = etaNode[0];
-    const bool slackOk = etaRoot >= 0.0f && etaRoot < 3.0e38f;
-    const uint32_t leafOffset = n - 1, K = (nb + 2u) / 3u;
-    for (uint32_t k = 0; k < K; k++) {
-        float lo[4][3], hi[4][3]; uint32_t ids[4]; int cnt = 0; uint32_t leafMask = 0;
-        for (uint32_t j = 3u * k; j < nb && j < 3u * k + 3u; j++) {
-            const uint32_t e = leafOffset + h.bigList[j];
-            const float* b = reinterpret_cast<const float*>(nodes + 10ull * e);
-            const float eta = slackOk ? etaNode[e] : 0.0f;
-            for (int a = 0; a < 3; a++) { lo[cnt][a] = __fsub_rd(b[2 * a], eta); hi[cnt][a] = __fadd_ru(b[2 * a + 1], eta); }
-            ids[cnt] = e; leafMask |= 1u << cnt; cnt++;
-        }
-        {   // the link: everything else lies inside the root's (reference) box
-            const float* b = reinterpret_cast<const float*>(nodes);
-            const float eta = slackOk ? etaRoot : 0.0f;
-            for (int a = 0; a < 3; a++) { lo[cnt][a] = __fsub_rd(b[2 * a], eta); hi[cnt][a] = __fadd_ru(b[2 * a + 1], eta); }
-            ids[cnt] = k + 1u < K ? leafOffset + k + 1u : 0u; cnt++;
-        }
-        store_wide_record(wide + 4ull * (leafOffset + k), cnt, lo, hi, ids, leafMask);
-    }
-    flags[1] = leafOffset;                                       // the walk starts at the first of them
 }
 
 #ifdef RTB_SMEM_TOP
@@ -853,18 +706,18 @@ void launch_hlbvh(cudaStream_t st, const void* tris, uint32_t T, const void* sph
 // K5 of the fused build: also writes the exact leaf boxes, the packed primitive records and the per-primitive hit-point slack
 void launch_hlbvh_fused(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const uint32_t* codes, void* nodes,
                         void* cinfo, void* leafBox, void* ptris, void* psphs, void* sphMat, float* etaNode, const uint32_t* primBounds,
-                        void* originRegion, const float* camPos, unsigned int* bigCount, uint32_t* bigList) {
+                        void* originRegion, const float* camPos, unsigned int* bigCount, uint32_t* bigList, uint32_t* smallBounds) {
     Codes c{ codes, 1, (int)(T + S) };
     cudaMemsetAsync(bigCount, 0, sizeof(unsigned int), st);
+    cudaMemsetAsync(smallBounds, 0xFF, 3 * sizeof(uint32_t), st);           // ordered-int minima start at the top, maxima at 0
+    cudaMemsetAsync(smallBounds + 3, 0, 3 * sizeof(uint32_t), st);
     LeafExtras ex{ (float4*)leafBox, (float4*)ptris, (float4*)psphs, (uint32_t*)sphMat, etaNode, primBounds, (float4*)originRegion,
-                   F3(camPos[0], camPos[1], camPos[2]), bigCount, bigList };
+                   F3(camPos[0], camPos[1], camPos[2]), bigCount, bigList, smallBounds };
     hlbvh_kernel<true><<<blocks_for((uint64_t)T + S, 256), 256, 0, st>>>((const float4*)tris, T, (const float4*)sphs, S, c,
                                                                          (uint32_t*)nodes, (uint2*)cinfo, ex);
 }
-void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox, float* etaNode, void* tight,
-                  const uint32_t* primBounds) {
-    refit_kernel<<<blocks_for(n, 256), 256, 0, st>>>((uint32_t*)nodes, (uint2*)cinfo, n, (float4*)pairs, (float4*)rootBox, etaNode,
-                                                     (float4*)tight, primBounds);
+void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox, float* etaNode) {
+    refit_kernel<<<blocks_for(n, 256), 256, 0, st>>>((uint32_t*)nodes, (uint2*)cinfo, n, (float4*)pairs, (float4*)rootBox, etaNode);
 }
 // K1 + K2 in one pass (fused build).  Returns #launches.
 int launch_model_to_world_enclosing(cudaStream_t st, const void* models, void* tris, uint32_t T, void* sphs, uint32_t S, uint32_t* red,
@@ -881,15 +734,9 @@ void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pai
 void launch_pack_cnodes(cudaStream_t st, const void* nodes, uint32_t n, void* cnodes, void* leafBox) {
     pack_cnodes_kernel<<<blocks_for(n, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)cnodes, (float4*)leafBox);
 }
-// tight != NULL: hoist the big leaves (see pack_wide_kernel); `wide` then needs room for n - 1 + 16 records.  Returns #launches.
-int launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode, unsigned int* flags, const void* tight,
-                     const unsigned int* bigCount, const uint32_t* bigList, const uint32_t* primBounds) {
-    if (n < 2) return 0;
-    const HoistInfo h{ (const float4*)tight, bigCount, bigList, primBounds };
-    pack_wide_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)wide, etaNode, flags, h);
-    if (!tight) return 1;
-    pack_top_records_kernel<<<1, 32, 0, st>>>((const uint32_t*)nodes, n, (uint4*)wide, etaNode, flags, h);
-    return 2;
+void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode, unsigned int* flags) {
+    if (n < 2) return;
+    pack_wide_kernel<<<blocks_for(n - 1, 256), 256, 0, st>>>((const uint32_t*)nodes, n, (uint4*)wide, etaNode, flags);
 }
 // etaNode[2n-1] <- per-node hit-point slack; parent[2n-1], arrivals[n-1] are scratch.  Returns #launches.
 int launch_eta(cudaStream_t st, const void* nodes, uint32_t n, const void* ptris, uint32_t T, const void* psphs, uint32_t S,

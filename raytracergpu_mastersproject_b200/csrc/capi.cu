@@ -89,12 +89,11 @@ int derive_records(rtb_ctx* c, int nodesMode, const float* camPos) {
         // tight and the walk drops nothing by t; pack_wide_kernel decides that on the device (walkFlag), no read-back.
         const size_t nn = 2ull * c->bN - 1;
         if (ensure(c, c->wide, 64ull * (c->bN - 1)) || ensure(c, c->etaNode, 4 * nn) || ensure(c, c->etaParent, 4 * nn) ||
-            ensure(c, c->etaArrivals, 4ull * c->bN) || ensure(c, c->walkFlag, 32)) return -1;
+            ensure(c, c->etaArrivals, 4ull * c->bN) || ensure(c, c->walkFlag, 64)) return -1;
         extra += launch_eta(c->stream, c->boundNodesPtr, c->bN, c->ptris.p, c->bT, c->psphs.p, c->bS, c->rootBox.p, camPos,
                             (float*)c->etaNode.p, (uint32_t*)c->etaParent.p, (unsigned int*)c->etaArrivals.p);
-        extra += launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wide.p, (const float*)c->etaNode.p, (unsigned int*)c->walkFlag.p,
-                                  nullptr, nullptr, nullptr, nullptr);
-        c->wideReady = true;
+        launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wide.p, (const float*)c->etaNode.p, (unsigned int*)c->walkFlag.p);
+        c->wideReady = true; extra++;
 #ifdef RTB_SMEM_TOP
         if (ensure(c, c->topTable, 64ull * RTB_SMEM_TOP) || ensure(c, c->topGlobal, 4ull * RTB_SMEM_TOP)) return -1;
         launch_build_top_table(c->stream, c->wide.p, c->bN, c->topTable.p, c->topGlobal.p, (const unsigned int*)c->walkFlag.p); extra++;
@@ -167,7 +166,7 @@ int rtb_ctx_destroy(rtb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (Scratch* s : { &c->sortKeys[0], &c->sortKeys[1], &c->sortVals[0], &c->sortVals[1], &c->sortCounts, &c->encRed, &c->enclosing,
                         &c->cinfo, &c->nodes, &c->pairs, &c->ptris, &c->psphs, &c->psphMat, &c->pmats, &c->rootBox, &c->workCounter,
-                        &c->errFlag, &c->walkFlag, &c->tightBox, &c->bigList, &c->wideRef, &c->topTable, &c->topGlobal, &c->gatherBuf, &c->bandRgba8, &c->etaNode, &c->etaParent, &c->etaArrivals, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->activeXY, &c->sampleBuf, &c->primaryHits, &c->poolSlot, &c->poolColor,
+                        &c->errFlag, &c->walkFlag, &c->bigList, &c->wideRef, &c->ttChild, &c->ttParent, &c->ttArrivals, &c->ttBox, &c->ttEta, &c->topTable, &c->topGlobal, &c->gatherBuf, &c->bandRgba8, &c->etaNode, &c->etaParent, &c->etaArrivals, &c->cnodes, &c->leafBox, &c->wide, &c->activePix, &c->activeXY, &c->sampleBuf, &c->primaryHits, &c->poolSlot, &c->poolColor,
                         &c->poolAtt, &c->poolOrg, &c->poolDir, &c->poolNrm, &c->poolList, &c->poolCnt, &c->parkBuf })
         release(*s);
     cudaEventDestroy(c->ev0);
@@ -359,8 +358,9 @@ int rtb_build_bvh(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void* tria
         const size_t nn = 2ull * N - 1;
         if (ensure(c, c->pairs, sizeof(float4) * 4ull * (N - 1)) || ensure(c, c->rootBox, sizeof(float4) * 4) || ensure(c, c->ptris, sizeof(float4) * 4ull * T) ||
             ensure(c, c->psphs, sizeof(float4) * (size_t)S) || ensure(c, c->psphMat, sizeof(uint32_t) * (size_t)S) || ensure(c, c->leafBox, 32ull * N) ||
-            ensure(c, c->wide, 64ull * (N - 1 + 16)) || ensure(c, c->etaNode, 4 * nn) || ensure(c, c->walkFlag, 32) ||
-            ensure(c, c->tightBox, 32ull * (N - 1)) || ensure(c, c->bigList, 4ull * 64)) return 1;
+            ensure(c, c->wide, 64ull * (N - 1 + 16)) || ensure(c, c->etaNode, 4 * nn) || ensure(c, c->walkFlag, 64) ||
+            ensure(c, c->bigList, 4ull * 64) || ensure(c, c->ttChild, 8ull * (N - 1)) || ensure(c, c->ttParent, 4 * nn) ||
+            ensure(c, c->ttArrivals, 4ull * (N - 1)) || ensure(c, c->ttBox, 32ull * (N - 1)) || ensure(c, c->ttEta, 4ull * (N - 1))) return 1;
         launches += launch_model_to_world_enclosing(c->stream, models, triangles, T, spheres, S, (uint32_t*)c->encRed.p, enclosing,
                                                     (flags & RTB_TRACE_ENCLOSING_INF) ? 1 : 0);                   // K1 + K2
         launch_morton(c->stream, triangles, T, spheres, S, enclosing, nullptr, k0, v0); launches++;              // K3 (SoA out)
@@ -368,13 +368,15 @@ int rtb_build_bvh(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void* tria
         if (morton1) { launch_morton_repack(c->stream, k0, v0, N, T, morton1); launches++; }
         launch_hlbvh_fused(c->stream, triangles, T, spheres, S, k0, nodes, cinfo, c->leafBox.p, c->ptris.p, c->psphs.p, c->psphMat.p,
                            (float*)c->etaNode.p, (const uint32_t*)c->encRed.p + 6, (float4*)c->rootBox.p + 2, ubo->camPos,
-                           (unsigned int*)c->walkFlag.p + 2, (uint32_t*)c->bigList.p); launches++;                  // K5
-        launch_refit(c->stream, nodes, cinfo, N, c->pairs.p, c->rootBox.p, (float*)c->etaNode.p, c->tightBox.p,
-                     (const uint32_t*)c->encRed.p + 6); launches++;                                                // K6 (+ pair records, slack, tight boxes)
+                           (unsigned int*)c->walkFlag.p + 2, (uint32_t*)c->bigList.p, (uint32_t*)c->walkFlag.p + 8); launches++;   // K5
+        launch_refit(c->stream, nodes, cinfo, N, c->pairs.p, c->rootBox.p, (float*)c->etaNode.p); launches++;    // K6 (+ pair records, slack)
         if (check_launch(c, launches, "BVH build kernels")) return 1;
         if (bind_internal(c, T, S, ubo->numMaterials, triangles, spheres, materials, nodes, /*pairsDone=*/true, /*primsDone=*/true)) return 1;
-        int packs = launch_pack_wide(c->stream, nodes, N, c->wide.p, (const float*)c->etaNode.p, (unsigned int*)c->walkFlag.p, c->tightBox.p,
-                                     (const unsigned int*)c->walkFlag.p + 2, (const uint32_t*)c->bigList.p, (const uint32_t*)c->encRed.p + 6);
+        // the hierarchy the order-free walk descends (traversal_tree.cu): its own, better tree over the same leaves, big leaves in front of the root
+        const TraversalTreeBuffers tb{ k0, v0, k1, v1, (uint32_t*)c->sortCounts.p, (uint2*)c->ttChild.p, (uint32_t*)c->ttParent.p, (unsigned int*)c->ttArrivals.p,
+                                       (float4*)c->ttBox.p, (float*)c->ttEta.p, (unsigned int*)c->walkFlag.p, (const uint32_t*)c->bigList.p,
+                                       (const uint32_t*)c->encRed.p + 6, (const uint32_t*)c->walkFlag.p + 8 };
+        int packs = launch_traversal_tree(c->stream, N, c->leafBox.p, (const float*)c->etaNode.p, tb, c->wide.p);
         c->leafBoxReady = true; c->wideReady = true; c->hoisted = true;
 #ifdef RTB_SMEM_TOP
         if (ensure(c, c->topTable, 64ull * RTB_SMEM_TOP) || ensure(c, c->topGlobal, 4ull * RTB_SMEM_TOP)) return 1;
@@ -505,10 +507,9 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
                 // the reference-order walk (and the segment-box extension on top of it) needs the records in the reference's visiting
                 // order with every leaf in its place: an un-hoisted set, derived on first use
                 if (!c->wideRefReady) {
-                    if (ensure(c, c->wideRef, 64ull * (c->bN - 1)) || ensure(c, c->walkFlag, 32)) return 1;
-                    extra += launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wideRef.p, (const float*)c->etaNode.p,
-                                              (unsigned int*)c->walkFlag.p + 4, nullptr, nullptr, nullptr, nullptr);
-                    c->wideRefReady = true;
+                    if (ensure(c, c->wideRef, 64ull * (c->bN - 1)) || ensure(c, c->walkFlag, 64)) return 1;
+                    launch_pack_wide(c->stream, c->boundNodesPtr, c->bN, c->wideRef.p, (const float*)c->etaNode.p, (unsigned int*)c->walkFlag.p + 4);
+                    c->wideRefReady = true; extra++;
                 }
                 p.sc.wide = (const uint4*)c->wideRef.p;
             }

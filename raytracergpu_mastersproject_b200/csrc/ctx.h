@@ -49,7 +49,8 @@ struct rtb_ctx {
     rtb::Scratch etaNode, etaParent, etaArrivals;   // per-node hit-point slack (launch_eta) and its scratch
     rtb::Scratch topTable, topGlobal; // A/B build RTB_SMEM_TOP
     rtb::Scratch walkFlag;            // device word: 1 = records grown by a finite slack, t-culling allowed (pack_wide_kernel)
-    rtb::Scratch tightBox, bigList, wideRef;   // hoisting of big leaves (pack_wide_kernel); un-hoisted records for the reference-order walk
+    rtb::Scratch bigList, wideRef;    // traversal hierarchy (traversal_tree.cu): list of big leaves; records over the reference's tree for the reference-order walk
+    rtb::Scratch ttChild, ttParent, ttArrivals, ttBox, ttEta;   // its topology, boxes and subtree slack
     bool wideRefReady = false, hoisted = false;
     rtb::Scratch cnodes, leafBox, wide;    // compressed 32-byte / wide 64-byte traversal records + exact leaf boxes
     rtb::Scratch activePix, activeXY, sampleBuf, primaryHits;     // wave kernel: active-pixel list and per-(sample, pixel) colour slots

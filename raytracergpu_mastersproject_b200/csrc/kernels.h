@@ -19,18 +19,25 @@ void launch_morton_unpack(cudaStream_t st, const void* morton, uint32_t n, uint3
 void launch_morton_repack(cudaStream_t st, const uint32_t* keys, const uint32_t* vals, uint32_t n, uint32_t T, void* morton);
 void launch_hlbvh(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const uint32_t* codes,
                   uint32_t codeStrideWords, void* nodes, void* cinfo);
-void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox, float* etaNode, void* tight = nullptr,
-                  const uint32_t* primBounds = nullptr);   // pairs != NULL: also emit traversal records; etaNode != NULL: also climb the hit-point slack
+void launch_refit(cudaStream_t st, void* nodes, void* cinfo, uint32_t n, void* pairs, void* rootBox, float* etaNode);   // pairs != NULL: also emit traversal records; etaNode != NULL: also climb the hit-point slack
 void launch_hlbvh_fused(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const uint32_t* codes, void* nodes,
                         void* cinfo, void* leafBox, void* ptris, void* psphs, void* sphMat, float* etaNode, const uint32_t* primBounds,
-                        void* originRegion, const float* camPos, unsigned int* bigCount, uint32_t* bigList);
+                        void* originRegion, const float* camPos, unsigned int* bigCount, uint32_t* bigList, uint32_t* smallBounds);
 void launch_build_top_table(cudaStream_t st, const void* wide, uint32_t n, void* top, void* topGlobal, const unsigned int* flags);   // RTB_SMEM_TOP builds only
 int launch_model_to_world_enclosing(cudaStream_t st, const void* models, void* tris, uint32_t T, void* sphs, uint32_t S, uint32_t* red,
                                     void* enclosing, int initInf);
 void launch_pack_pairs(cudaStream_t st, const void* nodes, uint32_t n, void* pairs, void* rootBox);
 void launch_pack_cnodes(cudaStream_t st, const void* nodes, uint32_t n, void* cnodes, void* leafBox);
-int launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode, unsigned int* flags, const void* tight,
-                     const unsigned int* bigCount, const uint32_t* bigList, const uint32_t* primBounds);   // tight != NULL: big leaves hoisted
+void launch_pack_wide(cudaStream_t st, const void* nodes, uint32_t n, void* wide, const float* etaNode, unsigned int* flags);
+// traversal_tree.cu: the hierarchy the order-free walk descends (built by rtb_build_bvh behind the reference's tree).  Returns #launches.
+struct TraversalTreeBuffers {
+    uint32_t *keys0, *vals0, *keys1, *vals1, *sortCounts;   // sort scratch (the reference build's, free again)
+    uint2* child; uint32_t* parent; unsigned int* arrivals; // topology of the n2 - 1 internal nodes
+    float4* box; float* eta;                                 // [n2-1][2] boxes, subtree slack
+    unsigned int* flags;                                     // [0] cull allowed [1] start record [2] big count [3] n2
+    const uint32_t* bigList; const uint32_t* primBounds; const uint32_t* smallBounds;
+};
+int launch_traversal_tree(cudaStream_t st, uint32_t N, const void* leafBox, const float* etaNode, const TraversalTreeBuffers& b, void* wide);
 int launch_eta(cudaStream_t st, const void* nodes, uint32_t n, const void* ptris, uint32_t T, const void* psphs, uint32_t S,
                void* rootBox /* [4]: box + origin region out */, const float* camPos, float* etaNode, uint32_t* parent, unsigned int* arrivals);
 void launch_pack_prims(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* mats, uint32_t M,

@@ -14,7 +14,7 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "raytracergpu_mastersproject_b200", "csrc")
-UNITS = ["capi.cu", "comm.cu", "probe.cu", "bvh_build.cu", "radix_sort.cu", "trace.cu", "trace_wave.cu"]
+UNITS = ["capi.cu", "comm.cu", "probe.cu", "bvh_build.cu", "traversal_tree.cu", "radix_sort.cu", "trace.cu", "trace_wave.cu"]
 
 
 def _match_back(s, end):
