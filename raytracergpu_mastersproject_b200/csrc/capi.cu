@@ -150,6 +150,7 @@ int rtb_ctx_create(int device, void* stream, rtb_ctx** out) {
     if (const char* e = getenv("RTB_WAVE_TMIN")) c->knobs.tMin = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_SORTED_PUSH")) c->knobs.sortedPush = atoi(e);
     if (const char* e = getenv("RTB_WAVE_QGATE")) c->knobs.qGate = (uint32_t)atoi(e);
+    if (const char* e = getenv("RTB_WAVE_SMIN")) c->knobs.sMin = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_COOP")) c->knobs.coopMax = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_COOP_TURNS")) c->knobs.coopTurns = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_TAIL_SPIN_US")) c->knobs.tailSpinUs = (uint32_t)atoi(e);
@@ -449,7 +450,10 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     p.workCounter = (unsigned int*)c->workCounter.p;
     p.errFlag = (unsigned int*)c->errFlag.p;
     p.tMin = c->knobs.tMin;
-    p.sortedPush = c->knobs.sortedPush >= 0 ? (uint32_t)c->knobs.sortedPush : (c->bS > c->bT ? 1u : 0u);   // measured: +16 % C3, -2..7 % C2/C4/C5
+    // farthest-first stacking of the waiting entries: +16 % on C3 over the reference-tree records in round 1, but -1.6 % there (and -3 % on
+    // C2 / C4) once the big leaves were hoisted (profiles/r02_knob_sweep_after_hoisting.txt): off unless RTB_WAVE_SORTED_PUSH=1
+    p.sortedPush = c->knobs.sortedPush > 0 ? 1u : 0u;
+    p.sMin = c->knobs.sMin ? c->knobs.sMin : 1u;
     p.qGate = c->knobs.qGate; p.coopMax = c->knobs.coopMax; p.coopTurns = c->knobs.coopTurns; p.tailSpinUs = c->knobs.tailSpinUs;
     const bool walk = (a->flags & RTB_TRACE_WALK_COUNT) != 0;
     const bool count = (a->flags & RTB_TRACE_COUNT) != 0 || walk, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;

@@ -68,6 +68,7 @@ struct rtb_ctx {
         uint32_t tMin = 0;            // RTB_WAVE_TMIN: lanes needed to stay in the traverse phase (0 = kernel default)
         int sortedPush = -1;          // RTB_WAVE_SORTED_PUSH: -1 = by scene (sphere-majority scenes stack waiting entries farthest-first)
         uint32_t qGate = 4;           // RTB_WAVE_QGATE
+        uint32_t sMin = 1;            // RTB_WAVE_SMIN: lanes that must wait for the S phase before a warp enters it
         uint32_t coopMax = 8;         // RTB_WAVE_COOP: tail hand-over threshold (live lanes per warp)
         uint32_t coopTurns = 32;      // RTB_WAVE_COOP_TURNS: long-ray hand-over threshold (turns)
         uint32_t tailSpinUs = 20000;  // RTB_WAVE_TAIL_SPIN_US: polling bound of the experimental concurrent tail launch

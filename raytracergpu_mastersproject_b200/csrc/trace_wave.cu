@@ -194,7 +194,15 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             }
         }
         // =========================================== S: shade / generate =========================================
-        while (!dead && (!rayActive || (travDone && qCount == 0))) {
+        // The S phase costs the warp ~450 instructions however few lanes need it (5-8 on average when every finished ray is served at
+        // once: a quarter of all instructions once the traverse phase got short).  It is therefore entered only when at least sMin lanes
+        // wait for it -- or nothing else can run (no lane can step; the T loop below keeps stepping meanwhile).
+        bool runS = true;
+        if (p.sMin > 1u) {
+            const unsigned sBal = __ballot_sync(FULL, !dead && (!rayActive || (travDone && qCount == 0)));
+            runS = (unsigned)__popc(sBal) >= p.sMin || !__any_sync(FULL, rayActive && !travDone && qCount <= qGate);
+        }
+        while (runS && !dead && (!rayActive || (travDone && qCount == 0))) {
             bool needItem = !rayActive;
             if (rayActive && p.primaryMode == 1u) {                       // primary-hit launch: keep the hit record, no shading
                 rayActive = false; needItem = true;
@@ -323,8 +331,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
             const unsigned bal = __ballot_sync(FULL, can);
             if (bal == 0) break;
             if (__popc(bal) < (int)p.tMin) {
-                const bool waiting = !dead && !can;                       // lanes that L or S could put back to work
-                if (__any_sync(FULL, waiting)) break;
+                // lanes that L could put back to work (candidates queued), or enough lanes waiting for S to make it worth entering
+                const bool needS = !dead && (!rayActive || (travDone && qCount == 0));
+                const bool needL = !dead && !can && !needS;
+                if (__any_sync(FULL, needL) || (unsigned)__popc(__ballot_sync(FULL, needS)) >= p.sMin) break;
             }
 #ifdef RTB_TAIL_PROBE
             if (can) prSteps++;

@@ -132,3 +132,54 @@ def test_hoisted_big_primitives(device, n_big):
             rt.clear_image(); rt.raytrace(ubo, spp, flags=fl); device.wait_idle()
             bad = int((_bits(rt.read_image()) != _bits(exact)).any(axis=-1).sum())
             assert bad == 0, f"{n_big} big primitives, camera {cam}, flags {fl}: {bad} pixels differ from the exact-record walk"
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_traversal_hierarchy_fuzz(device, seed):
+    """Scenes of >= 8192 primitives are walked over the library's own traversal hierarchy (traversal_tree.cu: adaptive-axis codes relative to
+    the true bounds, big leaves in front of the root).  Adversarial inputs for THAT build: clouds far from the origin (|coordinate| up to 1e6:
+    the reference's coord / span codes saturate there, the hierarchy's must not care), flat and needle-shaped extents (all code bits on one or
+    two axes), thousands of coincident centres (equal codes: index tie-break), every primitive big (nothing hoisted), slivers, nested spheres.
+    The frame must equal the exact-record walk's bit for bit, shared and unshared primaries and in the reference's order."""
+    from raytracergpu_mastersproject_b200 import Raytracer, capi
+    rng = np.random.default_rng(4000 + seed)
+    off_mag = [0.0, 1.0e3, 1.0e5, 1.0e6, 0.0][seed % 5]
+    shape = [(1, 1, 1), (1, 0.02, 1), (1, 1e-4, 1e-4), (1, 1, 0.0), (0.3, 1, 0.05)][(seed // 2) % 5]     # extent of the cloud per axis
+    ext = max(400.0, off_mag * 0.01)
+    offset = rng.normal(size=3); offset = offset / np.linalg.norm(offset) * off_mag
+    nt, ns = 8300 + int(rng.integers(0, 600)), int(rng.integers(0, 300))
+    T = np.zeros(nt + 2, O.TRIANGLE); S = np.zeros(ns, O.SPHERE)
+    c = offset + rng.uniform(-0.5, 0.5, (nt, 3)) * ext * np.array(shape)
+    if seed % 3 == 1:
+        c[: nt // 3] = c[0]                                                  # thousands of coincident centres
+    size = ext * 10.0 ** rng.uniform(-3.2, -1.2 if seed != 7 else 0.2, (nt, 1))      # seed 7: most triangles are BIG (nothing can be hoisted)
+    v0 = c + rng.normal(size=(nt, 3)) * size; v1 = c + rng.normal(size=(nt, 3)) * size; v2 = c + rng.normal(size=(nt, 3)) * size
+    sl = rng.random(nt) < 0.1
+    v2 = np.where(sl[:, None], v0 + (v1 - v0) * rng.uniform(0.2, 0.8, (nt, 1)) + rng.normal(size=(nt, 3)) * size * 10.0 ** rng.uniform(-2.7, -1, (nt, 1)), v2)
+    T["v0"][:nt, :3] = v0; T["v1"][:nt, :3] = v1; T["v2"][:nt, :3] = v2
+    T["materialIndex"][:nt] = rng.integers(1, 4, nt)
+    lo, hi = offset - 0.6 * ext, offset + 0.6 * ext
+    T["v0"][nt, :3] = (lo[0], hi[1], lo[2]); T["v1"][nt, :3] = (hi[0], hi[1], lo[2]); T["v2"][nt, :3] = (hi[0], hi[1], hi[2])
+    T["v0"][nt + 1, :3] = (lo[0], hi[1], lo[2]); T["v1"][nt + 1, :3] = (hi[0], hi[1], hi[2]); T["v2"][nt + 1, :3] = (lo[0], hi[1], hi[2])
+    if ns:
+        S["center"][:, :3] = offset + rng.uniform(-0.45, 0.45, (ns, 3)) * ext * np.array(shape)
+        S["radius"] = ext * 10.0 ** rng.uniform(-2.5, -1.0, ns); S["materialIndex"] = rng.integers(1, 4, ns)
+        S["center"][ns // 2:, :3] = S["center"][: ns - ns // 2, :3]           # nested / concentric
+    M = np.zeros(1, O.MODEL); M["m"][0] = np.eye(4, dtype=np.float32).reshape(16)
+    MT = np.zeros(4, O.MATERIAL)
+    for i, (a, t) in enumerate([((12, 12, 12), 0), ((0.7, 0.7, 0.7), 1), ((0.6, 0.3, 0.2), 1), ((0.2, 0.5, 0.7), 2 if seed % 2 else 1)]):
+        MT["albedo"][i, :3] = a; MT["materialType"][i] = t
+    sc = dict(models=M, triangles=T, spheres=S, materials=MT)
+    d = rng.normal(size=3); d /= np.linalg.norm(d)
+    W, H, spp = 56, 40, 3
+    for cam, look in [(offset + d * ext * 1.5, offset), (offset + rng.uniform(-0.1, 0.1, 3) * ext * np.array(shape), offset + d * ext)]:
+        ubo = SU.ubo_with_camera(sc, cam, look, max_depth=8, random_state=seed + 11)
+        rt = Raytracer(device, W, H)
+        rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
+        rt.build_bvh(ubo)
+        rt.clear_image(); rt.raytrace(ubo, spp, flags=capi.TRACE_EXACT_NODES | capi.TRACE_NO_PRIMARY_SHARING); device.wait_idle()
+        exact = rt.read_image()
+        for fl in (0, capi.TRACE_NO_PRIMARY_SHARING, capi.TRACE_REFERENCE_ORDER):
+            rt.clear_image(); rt.raytrace(ubo, spp, flags=fl); device.wait_idle()
+            bad = int((_bits(rt.read_image()) != _bits(exact)).any(axis=-1).sum())
+            assert bad == 0, f"seed {seed}, camera {cam}, flags {fl}: {bad} pixels differ from the exact-record walk"
