@@ -46,6 +46,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 BAND_ROWS = 8
+FRAMES_IN_FLIGHT = 1
 METRIC = "Mrays/s per scene (path segments = hitBVH calls per second)"
 VALUE_COUNTS = ("reference-equivalent rays: the hitBVH calls the reference shader executes for this frame (bit-identical output); "
                 "rays really walked are reported as mrays_traversed_per_s")
@@ -80,6 +81,11 @@ def parse_args():
     ap.add_argument("--mode", default="exact", choices=["exact", "culled"],
                     help="exact = the reference's traversal (default, the headline); culled = extension RTB_TRACE_CULLED")
     ap.add_argument("--no-frame-check", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true", help="experiment: skip the 256 MiB write between steps (a C2 frame's own working set, "
+                                                                "2.3 GB of sample slots + records, is 18x the L2 in any case)")
+    ap.add_argument("--frames-in-flight", type=int, default=FRAMES_IN_FLIGHT,
+                    help="timed / sustained / e2e legs: this many frames are in flight, each on its own library context + stream + buffers "
+                         "(frame k+1's BVH build runs while frame k's trace launch drains); 1 = strictly one frame after the other")
     return ap.parse_args()
 
 
@@ -282,6 +288,24 @@ class Session:
             self.dev.comm_init(self.world, self.rank, ids[0])
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.tdev)      # > 126 MB L2
         self._aux = {}
+        self._lanes = [self]
+
+    def lanes(self, n):
+        """n views of this rank, one per frame in flight: lane 0 is the session itself, the others own a further library context
+        (and communicator) on a stream of their own.  Collective: every rank calls it with the same n."""
+        import copy
+        from raytracergpu_mastersproject_b200 import Device
+        while len(self._lanes) < n:
+            ln = copy.copy(self)
+            ln.stream = self.torch.cuda.Stream(device=self.tdev)
+            ln.dev = Device(self.local_rank, stream=ln.stream.cuda_stream)
+            ln.h = ln.dev.handle
+            if self.world > 1:
+                ids = [Device.comm_unique_id() if self.rank == 0 else None]
+                self.dist.broadcast_object_list(ids, src=0)
+                ln.dev.comm_init(self.world, self.rank, ids[0])
+            self._lanes.append(ln)
+        return self._lanes[:n]
 
     def aux_device(self, name):
         """a second context of the same GPU on its own stream (H2D / D2H copy engines overlap the compute stream)"""
@@ -319,6 +343,8 @@ class Session:
     def close(self):
         for d, _ in self._aux.values():
             d.close()
+        for ln in self._lanes[1:]:
+            ln.dev.close()
         if self.world > 1:
             self.dist.barrier()
             self.dist.destroy_process_group()
@@ -384,6 +410,36 @@ class Frame:
 
     def vp(self, t):
         return self.C.c_void_p(t.data_ptr())
+
+    def twin(self, lane):
+        """the same frame for another lane (Session.lanes): shares the read-only inputs, owns what a frame writes"""
+        import copy
+        torch, t = self.S.torch, copy.copy(self)
+        t.S = lane
+        t.d_tris, t.d_sphs = torch.empty_like(self.d_tris0), torch.empty_like(self.d_sphs0)
+        t.image = torch.empty_like(self.image)
+        t.final = torch.empty_like(self.final) if self.S.world > 1 else t.image
+        t.rgba8 = torch.empty_like(self.rgba8)
+        t.targs = type(self.targs).from_buffer_copy(self.targs)
+        t._twins = [t]
+        return t
+
+    def in_flight(self, n):
+        """[self, twins...]: the frames that alternate in the timed legs"""
+        if not hasattr(self, "_twins"):
+            self._twins = [self]
+        lanes = self.S.lanes(n)
+        while len(self._twins) < n:
+            self._twins.append(self.twin(lanes[len(self._twins)]))
+        return self._twins[:n]
+
+    def flushed_frame(self, **kw):
+        """one timed step on this frame's lane: L2 flush, then the frame"""
+        S = self.S
+        with S.torch.cuda.stream(S.stream):
+            if not self.args.no_l2_flush:
+                S.flush.zero_()
+            self.frame(**kw)
 
     # -- the frame: restore -> clear -> S1 -> S2 -> (exchange) -> resolve ------------------------------------------------
     def build(self, tris=None, sphs=None, models=None, mats=None):
@@ -498,58 +554,84 @@ class Frame:
         return hashlib.sha256(self.rgba8.cpu().numpy().tobytes()).hexdigest()
 
     # -- timed legs ---------------------------------------------------------------------------------------------------------
-    def timed(self, steps, warmup):
+    def timed(self, steps, warmup, in_flight=1):
+        """K steps.  in_flight == 1: one frame after the other on one stream, each step and each rtb_raytrace call bracketed by events.
+        in_flight > 1: the frames alternate over that many lanes; the K steps are bracketed as a whole (first lane's start -> last
+        lane's end) -- every frame is complete inside the region, none is skipped or shared."""
         S = self.S
-        for _ in range(max(warmup, 0)):
-            S.flush.zero_(); self.frame()
+        fl = self.in_flight(in_flight)
+        for i in range(max(warmup, 0) * len(fl)):
+            fl[i % len(fl)].flushed_frame()
         S.barrier()
         t0 = ClockSampler.now()
-        launches0 = S.dev.launch_count()
-        step_ev, trace_ev = [], []
-        for _ in range(steps):
-            S.flush.zero_()
-            e0, e1, a, b = S.ev(), S.ev(), S.ev(), S.ev()
-            e0.record(S.stream)
-            self.frame(events=(a, b))
-            e1.record(S.stream)
-            step_ev.append((e0, e1)); trace_ev.append((a, b))
-        S.barrier()
+        launches0 = sum(f.S.dev.launch_count() for f in fl)
+        if len(fl) == 1:
+            step_ev, trace_ev = [], []
+            for _ in range(steps):
+                if not self.args.no_l2_flush:
+                    S.flush.zero_()
+                e0, e1, a, b = S.ev(), S.ev(), S.ev(), S.ev()
+                e0.record(S.stream)
+                self.frame(events=(a, b))
+                e1.record(S.stream)
+                step_ev.append((e0, e1)); trace_ev.append((a, b))
+            S.barrier()
+            step_ms = sum(a.elapsed_time(b) for a, b in step_ev)
+            trace_ms = sum(a.elapsed_time(b) for a, b in trace_ev) / steps
+        else:
+            e0 = S.ev(); e0.record(S.stream)
+            for f in fl[1:]:
+                f.S.stream.wait_event(e0)
+            for i in range(steps):
+                fl[i % len(fl)].flushed_frame()
+            ends = []
+            for f in fl:
+                e = S.ev(); e.record(f.S.stream); ends.append(e)
+            S.barrier()
+            step_ms = max(e0.elapsed_time(e) for e in ends)
+            trace_ms = 0.0
         t1 = ClockSampler.now()
-        launches = S.dev.launch_count() - launches0
-        step_ms = sum(a.elapsed_time(b) for a, b in step_ev)
-        trace_ms = sum(a.elapsed_time(b) for a, b in trace_ev) / steps
+        launches = sum(f.S.dev.launch_count() for f in fl) - launches0
         step_ms, trace_ms = S.max_over_ranks(step_ms, trace_ms)
         return dict(ms_per_step=step_ms / steps, trace_ms=trace_ms, launches=launches, t0=t0, t1=t1)
 
-    def sustained(self, seconds):
+    def sustained(self, seconds, in_flight=1):
         """the same step, back to back, for at least `seconds` (clocks settle well below the burst clock under a long load)"""
         S = self.S
+        fl = self.in_flight(in_flight)
         S.barrier()
         t0 = ClockSampler.now()
-        e0, e1 = S.ev(), S.ev()
+        e0 = S.ev()
         w0 = time.perf_counter()
         e0.record(S.stream)
+        for f in fl[1:]:
+            f.S.stream.wait_event(e0)
         n = 0
         while True:
-            for _ in range(4):
-                S.flush.zero_(); self.frame(); n += 1
+            for _ in range(4 * len(fl)):
+                fl[n % len(fl)].flushed_frame(); n += 1
             S.torch.cuda.synchronize()
             go = time.perf_counter() - w0 < seconds
             if S.world > 1:
                 go = not S.all_ok(not go)          # everybody continues while anybody has to
             if not go:
                 break
-        e1.record(S.stream)
+        ends = []
+        for f in fl:
+            e = S.ev(); e.record(f.S.stream); ends.append(e)
         S.barrier()
         t1 = ClockSampler.now()
-        ms = S.max_over_ranks(e0.elapsed_time(e1))[0]
+        ms = S.max_over_ranks(max(e0.elapsed_time(e) for e in ends))[0]
         return dict(steps=n, ms_per_step=ms / n, seconds=ms * 1e-3, t0=t0, t1=t1)
 
-    def e2e(self, steps):
+    def e2e(self, steps, in_flight=1):
         """Host buffers in, RGBA8 frame out, through the C-ABI, pipelined over three streams: H2D uploads (rtb_upload on a copy
         context; each rank its 1/N slice of the primitive arrays, completed over NVLink by rtb_comm_all_gather), the frame, and the
-        D2H read-back of the resolved frame (rtb_download_async on a second copy context).  Two buffer sets alternate."""
+        D2H read-back of the resolved frame (rtb_download_async on a second copy context).  Two buffer sets alternate (in_flight > 1:
+        one per lane, and the frames alternate over the lanes like in the timed leg)."""
         S, capi, torch, C = self.S, self.S.capi, self.S.torch, self.C
+        fl = self.in_flight(in_flight)
+        nset = max(2, len(fl))
         world, rank = S.world, S.rank
         up, up_st = S.aux_device("h2d")
         dn, dn_st = S.aux_device("d2h")
@@ -561,12 +643,14 @@ class Frame:
             parts[k] = (lo, pin(self.host[k][lo:hi]) if hi > lo else None)
         sets = [dict(tris=torch.zeros_like(self.d_tris0), sphs=torch.zeros_like(self.d_sphs0), rgba8=torch.empty_like(self.rgba8),
                      models=torch.zeros_like(self.d_models), mats=torch.zeros_like(self.d_mats),
-                     out=torch.empty((self.H, self.W, 4), dtype=torch.uint8).pin_memory(), done=None, read=None) for _ in range(2)]
+                     out=torch.empty((self.H, self.W, 4), dtype=torch.uint8).pin_memory(), done=None, read=None) for _ in range(nset)]
         h2d = hm.numel() + hmat.numel() + sum(p[1].numel() for p in parts.values() if p[1] is not None)
         d2h = sets[0]["out"].numel() if rank == 0 else 0
 
         def step(i):
-            s = sets[i % 2]
+            s = sets[i % nset]
+            f = fl[i % len(fl)]
+            st, dev = f.S.stream, f.S.dev
             if s["done"] is not None:
                 up_st.wait_event(s["done"])                      # the frame that used this set two steps ago has finished
             capi.check(S.L.rtb_upload(up.handle, self.vp(s["models"]), C.c_void_p(hm.data_ptr()), hm.numel()))
@@ -575,21 +659,21 @@ class Frame:
                 lo, hp = parts[k]
                 if hp is not None:
                     capi.check(S.L.rtb_upload(up.handle, C.c_void_p(buf.data_ptr() + lo), C.c_void_p(hp.data_ptr()), hp.numel()))
-            S.stream.wait_event(up_st.record_event())
+            st.wait_event(up_st.record_event())
             if world > 1:                                        # the other ranks' slices arrive over NVLink
-                S.dev.comm_all_gather(s["tris"].data_ptr(), self.slice["triangles"])
-                S.dev.comm_all_gather(s["sphs"].data_ptr(), self.slice["spheres"])
+                dev.comm_all_gather(s["tris"].data_ptr(), self.slice["triangles"])
+                dev.comm_all_gather(s["sphs"].data_ptr(), self.slice["spheres"])
             if s["read"] is not None:
-                S.stream.wait_event(s["read"])                   # this set's RGBA8 frame has been read back
-            S.flush.zero_()
-            self.frame(tris=s["tris"], sphs=s["sphs"], rgba8=s["rgba8"], models=s["models"], mats=s["mats"])
-            s["done"] = S.stream.record_event()
+                st.wait_event(s["read"])                         # this set's RGBA8 frame has been read back
+            f.flushed_frame(tris=s["tris"], sphs=s["sphs"], rgba8=s["rgba8"], models=s["models"], mats=s["mats"])
+            s["done"] = st.record_event()
             if rank == 0:
                 dn_st.wait_event(s["done"])
                 capi.check(S.L.rtb_download_async(dn.handle, C.c_void_p(s["out"].data_ptr()), self.vp(s["rgba8"]), s["out"].numel()))
                 s["read"] = dn_st.record_event()
 
-        step(0); step(1)                                          # warm both buffer sets
+        for i in range(nset):                                     # warm every buffer set
+            step(i)
         S.barrier()
         w0 = time.perf_counter()
         for i in range(steps):
@@ -599,7 +683,7 @@ class Frame:
         wall_ms = (time.perf_counter() - w0) * 1e3
         wall_ms = S.max_over_ranks(wall_ms)[0]
         h2d_all, d2h_all = S.sum_over_ranks([h2d, d2h])
-        self.e2e_frame = sets[(steps - 1) % 2]["out"].numpy().copy() if rank == 0 else None
+        self.e2e_frame = sets[(steps - 1) % nset]["out"].numpy().copy() if rank == 0 else None
         return dict(ms_per_step=wall_ms / steps, h2d=h2d_all, d2h=d2h_all)
 
     # -- roofline ------------------------------------------------------------------------------------------------------------
@@ -670,6 +754,8 @@ class Frame:
         return out
 
     def close(self):
+        for t in getattr(self, "_twins", [self])[1:]:
+            t.close()
         for k in list(self.__dict__):
             if k.startswith("d_") or k in ("image", "final", "rgba8"):
                 delattr(self, k)
@@ -710,12 +796,20 @@ def run_b200(args):
     if not args.no_frame_check:
         f.check_assembled()
     t_load = ClockSampler.now()
-    t = f.timed(args.steps, args.warmup)
-    ms_per_step, trace_ms = t["ms_per_step"], t["trace_ms"]
+    fif = max(1, args.frames_in_flight)
+    serial = f.timed(args.steps if fif == 1 else min(args.steps, 10), args.warmup)      # one frame after the other: frame latency + the trace launches' duration
+    t = serial if fif == 1 else f.timed(args.steps, args.warmup, in_flight=fif)
+    ms_per_step, trace_ms = t["ms_per_step"], serial["trace_ms"]
     value = f.rays / (ms_per_step * 1e-3) / 1e6
+    S.torch.cuda.synchronize()
     sha_timed = f.frame_sha() if rank == 0 else None
+    if fif > 1 and rank == 0:            # every lane renders the same frame
+        shas = {hashlib.sha256(x.rgba8.cpu().numpy().tobytes()).hexdigest() for x in f.in_flight(fif)}
+        chk["frames_in_flight"] = "the RGBA8 frames of all lanes are identical" if shas == {sha_timed} else "MISMATCH between lanes"
+        if shas != {sha_timed}:
+            chk["status"] = "MISMATCH"
 
-    e = f.e2e(args.steps)
+    e = f.e2e(args.steps, in_flight=fif)
     e2e_value = f.rays / (e["ms_per_step"] * 1e-3) / 1e6
     if rank == 0 and f.e2e_frame is not None:
         chk["e2e_frame"] = ("RGBA8 frame read back by the e2e leg == the timed leg's frame" if hashlib.sha256(f.e2e_frame.tobytes()).hexdigest() == sha_timed
@@ -723,7 +817,7 @@ def run_b200(args):
         if chk["e2e_frame"].startswith("MISMATCH"):
             chk["status"] = "MISMATCH"
 
-    sus = f.sustained(args.min_seconds) if args.min_seconds > 0 else None
+    sus = f.sustained(args.min_seconds, in_flight=fif) if args.min_seconds > 0 else None
 
     # build-only timing (reported, explains the step)
     b0, b1 = S.ev(), S.ev()
@@ -770,6 +864,9 @@ def run_b200(args):
                                f"samples{world}: sample ranges of {f.spp // world} spp per rank, scene replicated, rtb_reduce_samples (NCCL sum-reduce + fused resolve)" if f.by_samples else
                                f"tile{world}: 8-row bands interleaved over {world} rank(s), scene replicated, rtb_gather_tiles (resolve -> NCCL all-gather of RGBA8 -> re-assembly)")
         desc["l2"] = "256 MiB buffer written between timed steps (L2 flush)"
+        desc["frames_in_flight"] = (f"{fif}: consecutive frames alternate over {fif} library contexts (own stream, BVH and frame buffers), so a frame's BVH build "
+                                    "overlaps the previous frame's draining trace launch; ms_per_step = the K frames' bracket / K, frame_latency_ms = one frame alone"
+                                    if fif > 1 else "1: one frame after the other")
         desc["traversal"] = ("reference visiting order, no t-interval (--reference-order)" if args.reference_order or args.kernel != "wave" else
                              "library default: 4-ary records walked nearest-first with t-culling (scenes of >= 8192 primitives), else the exact child pairs in the reference's order")
         desc["primary_sharing"] = ("off" if (args.no_primary_sharing or args.kernel != "wave") else
@@ -780,7 +877,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "Mrays/s", "value_counts": VALUE_COUNTS,
             "mrays_traversed_per_s": f.rays_traversed / (ms_per_step * 1e-3) / 1e6,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_per_step, "frame_latency_ms": serial["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": desc, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(e["h2d"]), "d2h_bytes_per_step": int(e["d2h"]),
                     "ms_per_step": e["ms_per_step"],
@@ -794,7 +891,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "breakdown": {"rays_per_step": f.rays, "rays_traversed_per_step": f.rays_traversed,
                           "samples_per_step": f.cnt["samples"], "msamples_per_s": f.cnt["samples"] / (ms_per_step * 1e-3) / 1e6,
-                          "bvh_build_ms": build_ms, "trace_ms": trace_ms, "counters": f.cnt, "configs": configs},
+                          "bvh_build_ms": build_ms, "trace_ms": trace_ms, "serial_ms_per_step": serial["ms_per_step"], "counters": f.cnt, "configs": configs},
         }
         print(json.dumps(line), flush=True)
     f.close()

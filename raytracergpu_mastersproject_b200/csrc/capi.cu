@@ -138,6 +138,9 @@ int rtb_ctx_create(int device, void* stream, rtb_ctx** out) {
     }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    cudaStreamCreateWithFlags(&c->buildStream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->evBuildFork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->evBuildJoin, cudaEventDisableTiming);
     // RTB_WAVE_TAIL_OVERLAP=1 (experimental, default off): trace_tail_kernel is additionally launched on a second stream beside the
     // main trace launch, so that parked long rays are worked off while it drains.  Measured on B200 (profiles/r02_tail_overlap.txt):
     // correct but slower (36.1 -> 62.4 ms per C2 frame), so the tail launch stays strictly behind the main launch.
@@ -151,6 +154,8 @@ int rtb_ctx_create(int device, void* stream, rtb_ctx** out) {
     if (const char* e = getenv("RTB_WAVE_SORTED_PUSH")) c->knobs.sortedPush = atoi(e);
     if (const char* e = getenv("RTB_WAVE_QGATE")) c->knobs.qGate = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_SMIN")) c->knobs.sMin = (uint32_t)atoi(e);
+    if (const char* e = getenv("RTB_WAVE_MAIN_CTAS")) c->knobs.mainCtas = (uint32_t)atoi(e);
+    if (const char* e = getenv("RTB_WAVE_TAIL_THREADS")) c->knobs.tailThreads = atoi(e) == 64 ? 64u : 128u;
     if (const char* e = getenv("RTB_WAVE_COOP")) c->knobs.coopMax = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_COOP_TURNS")) c->knobs.coopTurns = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_TAIL_SPIN_US")) c->knobs.tailSpinUs = (uint32_t)atoi(e);
@@ -172,6 +177,7 @@ int rtb_ctx_destroy(rtb_ctx* c) {
         release(*s);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    if (c->buildStream) { cudaStreamSynchronize(c->buildStream); cudaStreamDestroy(c->buildStream); cudaEventDestroy(c->evBuildFork); cudaEventDestroy(c->evBuildJoin); }
     if (c->auxStream) { cudaStreamSynchronize(c->auxStream); cudaStreamDestroy(c->auxStream); cudaEventDestroy(c->evFork); cudaEventDestroy(c->evJoin); }
     if (c->ownStream) cudaStreamDestroy(c->stream);
     delete c;
@@ -370,14 +376,19 @@ int rtb_build_bvh(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void* tria
         launch_hlbvh_fused(c->stream, triangles, T, spheres, S, k0, nodes, cinfo, c->leafBox.p, c->ptris.p, c->psphs.p, c->psphMat.p,
                            (float*)c->etaNode.p, (const uint32_t*)c->encRed.p + 6, (float4*)c->rootBox.p + 2, ubo->camPos,
                            (unsigned int*)c->walkFlag.p + 2, (uint32_t*)c->bigList.p, (uint32_t*)c->walkFlag.p + 8); launches++;   // K5
-        launch_refit(c->stream, nodes, cinfo, N, c->pairs.p, c->rootBox.p, (float*)c->etaNode.p); launches++;    // K6 (+ pair records, slack)
+        // K6 (+ pair records, slack) on the build stream: the climb is a chain of dependent atomics that leaves the GPU nearly idle, and
+        // the first half of the traversal hierarchy's build (keys, sort, topology, its own climb) needs only what K5 wrote
+        cudaEventRecord(c->evBuildFork, c->stream);
+        cudaStreamWaitEvent(c->buildStream, c->evBuildFork, 0);
+        launch_refit(c->buildStream, nodes, cinfo, N, c->pairs.p, c->rootBox.p, (float*)c->etaNode.p); launches++;
+        cudaEventRecord(c->evBuildJoin, c->buildStream);
         if (check_launch(c, launches, "BVH build kernels")) return 1;
         if (bind_internal(c, T, S, ubo->numMaterials, triangles, spheres, materials, nodes, /*pairsDone=*/true, /*primsDone=*/true)) return 1;
         // the hierarchy the order-free walk descends (traversal_tree.cu): its own, better tree over the same leaves, big leaves in front of the root
         const TraversalTreeBuffers tb{ k0, v0, k1, v1, (uint32_t*)c->sortCounts.p, (uint2*)c->ttChild.p, (uint32_t*)c->ttParent.p, (unsigned int*)c->ttArrivals.p,
                                        (float4*)c->ttBox.p, (float*)c->ttEta.p, (unsigned int*)c->walkFlag.p, (const uint32_t*)c->bigList.p,
                                        (const uint32_t*)c->encRed.p + 6, (const uint32_t*)c->walkFlag.p + 8 };
-        int packs = launch_traversal_tree(c->stream, N, c->leafBox.p, (const float*)c->etaNode.p, tb, c->wide.p);
+        int packs = launch_traversal_tree(c->stream, N, c->leafBox.p, (const float*)c->etaNode.p, tb, c->wide.p, c->evBuildJoin);
         c->leafBoxReady = true; c->wideReady = true; c->hoisted = true;
 #ifdef RTB_SMEM_TOP
         if (ensure(c, c->topTable, 64ull * RTB_SMEM_TOP) || ensure(c, c->topGlobal, 4ull * RTB_SMEM_TOP)) return 1;
@@ -454,6 +465,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
     // C2 / C4) once the big leaves were hoisted (profiles/r02_knob_sweep_after_hoisting.txt): off unless RTB_WAVE_SORTED_PUSH=1
     p.sortedPush = c->knobs.sortedPush > 0 ? 1u : 0u;
     p.sMin = c->knobs.sMin ? c->knobs.sMin : 1u;
+    p.mainCtas = c->knobs.mainCtas; p.tailThreads = c->knobs.tailThreads;
     p.qGate = c->knobs.qGate; p.coopMax = c->knobs.coopMax; p.coopTurns = c->knobs.coopTurns; p.tailSpinUs = c->knobs.tailSpinUs;
     const bool walk = (a->flags & RTB_TRACE_WALK_COUNT) != 0;
     const bool count = (a->flags & RTB_TRACE_COUNT) != 0 || walk, ext = (a->flags & RTB_TRACE_EXT_MATERIALS) != 0;

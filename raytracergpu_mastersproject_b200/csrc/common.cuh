@@ -147,6 +147,7 @@ struct TraceParams {
     uint32_t sortedPush;               // nearest-first kernel: pick the variant that stacks waiting entries farthest-first
     uint32_t qGate;                    // nearest-first kernel: a lane keeps stepping while its FIFO holds <= qGate candidates
     uint32_t tMin;                     // wave kernel: minimum stepping lanes to stay in the traverse phase (0 = default)
+    uint32_t mainCtas, tailThreads;    // wave kernel: cap on resident CTAs per SM (0 = none) / CTA size of the tail launch (host-side launch shape)
     uint32_t sMin;                     // wave kernel: lanes that must wait for the shade / generate phase before it is entered (1 = every time)
     // tail hand-over (trace_wave.cu): once the work queue is drained, a warp with <= coopMax live lanes parks the paths whose next
     // ray is about to start; trace_tail_kernel finishes them one ray per WARP (0 = off)

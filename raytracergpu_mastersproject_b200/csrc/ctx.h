@@ -39,6 +39,8 @@ struct rtb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t auxStream = nullptr;             // the tail launch runs here, concurrently with the main trace launch
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaStream_t buildStream = nullptr;           // the reference tree's refit runs here, beside the first half of the traversal hierarchy's build
+    cudaEvent_t evBuildFork = nullptr, evBuildJoin = nullptr;
     uint64_t launches = 0;
     char name[256] = { 0 };
     // build scratch (grow-only)
@@ -68,6 +70,9 @@ struct rtb_ctx {
         uint32_t tMin = 0;            // RTB_WAVE_TMIN: lanes needed to stay in the traverse phase (0 = kernel default)
         int sortedPush = -1;          // RTB_WAVE_SORTED_PUSH: -1 = by scene (sphere-majority scenes stack waiting entries farthest-first)
         uint32_t qGate = 4;           // RTB_WAVE_QGATE
+        uint32_t mainCtas = 0;        // RTB_WAVE_MAIN_CTAS: resident CTAs per SM of the persistent trace launch (0 = all that fit, 7); fewer leave room for
+                                      // the launches of another context's frame (frames in flight) to run beside it
+        uint32_t tailThreads = 128;   // RTB_WAVE_TAIL_THREADS: CTA size of trace_tail_kernel (64 fits the slot RTB_WAVE_MAIN_CTAS=6 leaves)
         uint32_t sMin = 1;            // RTB_WAVE_SMIN: lanes that must wait for the S phase before a warp enters it
         uint32_t coopMax = 8;         // RTB_WAVE_COOP: tail hand-over threshold (live lanes per warp)
         uint32_t coopTurns = 32;      // RTB_WAVE_COOP_TURNS: long-ray hand-over threshold (turns)

@@ -37,7 +37,7 @@ struct TraversalTreeBuffers {
     unsigned int* flags;                                     // [0] cull allowed [1] start record [2] big count [3] n2
     const uint32_t* bigList; const uint32_t* primBounds; const uint32_t* smallBounds;
 };
-int launch_traversal_tree(cudaStream_t st, uint32_t N, const void* leafBox, const float* etaNode, const TraversalTreeBuffers& b, void* wide);
+int launch_traversal_tree(cudaStream_t st, uint32_t N, const void* leafBox, const float* etaNode, const TraversalTreeBuffers& b, void* wide, cudaEvent_t etaRootReady);
 int launch_eta(cudaStream_t st, const void* nodes, uint32_t n, const void* ptris, uint32_t T, const void* psphs, uint32_t S,
                void* rootBox /* [4]: box + origin region out */, const float* camPos, float* etaNode, uint32_t* parent, unsigned int* arrivals);
 void launch_pack_prims(cudaStream_t st, const void* tris, uint32_t T, const void* sphs, uint32_t S, const void* mats, uint32_t M,

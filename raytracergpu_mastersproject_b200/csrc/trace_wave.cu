@@ -463,7 +463,7 @@ __device__ __forceinline__ void tail_item(const TraceParams& p, const uint32_t i
                 const uint32_t my = lane < take ? stk[n - 1u - lane] : 0xFFFFFFFFu;
                 n -= take;
                 __syncwarp();
-                uint32_t intMask = 0, id0 = 0, id1 = 0, id2 = 0, id3 = 0;
+                uint32_t intMask = 0, enqMask = 0, id0 = 0, id1 = 0, id2 = 0, id3 = 0;
                 if (my != 0xFFFFFFFFu) {
                     if (COUNT) { tl.rec++; tl.recUnique++; }      // the lanes of a tail warp expand distinct entries of one ray
                     const uint4* rp = sc.wide + 4ull * my;
@@ -497,14 +497,21 @@ __device__ __forceinline__ void tail_item(const TraceParams& p, const uint32_t i
                     passMask &= meta >> 4;
                     const uint32_t leafMask = meta & 0xFu;
                     intMask = passMask & ~leafMask;
-                    const uint32_t enqMask = passMask & leafMask;
+                    enqMask = passMask & leafMask;
+                }
+                // the leaf candidates of all lanes are dealt out evenly (ballot-ranked list behind the pending set): a turn's critical path is
+                // one record fetch + ceil(candidates / 32) leaf tests, not the largest per-lane candidate count (up to 4) of them
+                uint32_t nLeaf = 0;
+                { const bool b = enqMask & 1u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[COOP_CAP + nLeaf + __popc(bal & ((1u << lane) - 1u))] = id0 - leafOffset; nLeaf += __popc(bal); }
+                { const bool b = enqMask & 2u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[COOP_CAP + nLeaf + __popc(bal & ((1u << lane) - 1u))] = id1 - leafOffset; nLeaf += __popc(bal); }
+                { const bool b = enqMask & 4u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[COOP_CAP + nLeaf + __popc(bal & ((1u << lane) - 1u))] = id2 - leafOffset; nLeaf += __popc(bal); }
+                { const bool b = enqMask & 8u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[COOP_CAP + nLeaf + __popc(bal & ((1u << lane) - 1u))] = id3 - leafOffset; nLeaf += __popc(bal); }
+                __syncwarp();
 #pragma unroll 1
-                    for (int k = 0; k < 4; k++) {
-                        if (!((enqMask >> k) & 1u)) continue;
-                        const uint32_t g = (k == 0 ? id0 : k == 1 ? id1 : k == 2 ? id2 : id3) - leafOffset;
-                        if (COUNT) tl.lbox++;
-                        if (leaf_box_passes(sc, g, o, d, rinv, false)) leaf_test_unordered<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl, poison);
-                    }
+                for (uint32_t base = lane; base < nLeaf; base += 32u) {
+                    const uint32_t g = stk[COOP_CAP + base];
+                    if (COUNT) tl.lbox++;
+                    if (leaf_box_passes(sc, g, o, d, rinv, false)) leaf_test_unordered<COUNT>(sc, g, o, d, T_MIN_RAY, closest, hit, rec, tl, poison);
                 }
                 if (n + 128u > COOP_CAP) { fit = false; break; }      // warp-uniform
                 { const bool b = intMask & 1u; const unsigned bal = __ballot_sync(FULL, b); if (b) stk[n + __popc(bal & ((1u << lane) - 1u))] = id0; n += __popc(bal); }
@@ -596,7 +603,7 @@ __device__ __forceinline__ void tail_item(const TraceParams& p, const uint32_t i
 
 template <bool EXT, bool COUNT>
 __global__ void __launch_bounds__(WAVE_THREADS) trace_tail_kernel(const TraceParams p) {
-    __shared__ uint32_t coopStack[WAVE_THREADS / 32][COOP_CAP];
+    __shared__ uint32_t coopStack[WAVE_THREADS / 32][COOP_CAP + 128];     // per warp: pending set + the turn's leaf candidates
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31;
     const LinearStack stk{ coopStack[threadIdx.x >> 5] };
@@ -663,6 +670,7 @@ template <bool COUNT, bool EXT, bool CULL, int NODES>
 static void launch_wave_variant(cudaStream_t st, TraceParams& p, int smCount, uint64_t need) {
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_wave_kernel<COUNT, EXT, CULL, NODES>, WAVE_THREADS, 0);
+    if (p.mainCtas != 0u && nb > (int)p.mainCtas) nb = (int)p.mainCtas;
     uint64_t grid = (uint64_t)smCount * (nb > 0 ? nb : 1);                 // persistent: resident CTAs per SM x SM count
     if (grid > need) grid = need;
     p.mainWarps = (uint32_t)grid * (WAVE_THREADS / 32);                    // what the concurrent tail launch waits for
@@ -743,11 +751,12 @@ int launch_trace_wave(cudaStream_t st, TraceParams p, bool count, bool ext, bool
             int nb = 0;
             if (ext) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_tail_kernel<true, false>, WAVE_THREADS, 0);
             else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_tail_kernel<false, false>, WAVE_THREADS, 0);
-            const unsigned grid = (unsigned)smCount * (unsigned)(nb > 0 ? nb : 1);
+            const unsigned tt = p.tailThreads == 64u ? 64u : (unsigned)WAVE_THREADS;       // same warps in total, in CTAs half the size
+            const unsigned grid = (unsigned)smCount * (unsigned)(nb > 0 ? nb : 1) * ((unsigned)WAVE_THREADS / tt);
             auto go = [&](cudaStream_t ts) {
-                if (walk) { if (ext) trace_tail_kernel<true, true><<<grid, WAVE_THREADS, 0, ts>>>(p); else trace_tail_kernel<false, true><<<grid, WAVE_THREADS, 0, ts>>>(p); }
-                else if (ext) trace_tail_kernel<true, false><<<grid, WAVE_THREADS, 0, ts>>>(p);
-                else trace_tail_kernel<false, false><<<grid, WAVE_THREADS, 0, ts>>>(p);
+                if (walk) { if (ext) trace_tail_kernel<true, true><<<grid, tt, 0, ts>>>(p); else trace_tail_kernel<false, true><<<grid, tt, 0, ts>>>(p); }
+                else if (ext) trace_tail_kernel<true, false><<<grid, tt, 0, ts>>>(p);
+                else trace_tail_kernel<false, false><<<grid, tt, 0, ts>>>(p);
                 launches++;
             };
             if (ov.aux) {      // concurrent launch on the second stream (may start while the main launch, just enqueued on `st`, is running) ...

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) tt_refit_kernel(const unsigned int* __res
 }
 
 // 4-ary records of the tree (greedy surface-area cut, as pack_wide_kernel); a leaf entry carries the reference's leaf index N - 1 + primitive
-__global__ void __launch_bounds__(256) tt_pack_kernel(const unsigned int* __restrict__ flags, const uint2* __restrict__ child, const uint32_t* __restrict__ vals,
+__global__ void __launch_bounds__(128) tt_pack_kernel(const unsigned int* __restrict__ flags, const uint2* __restrict__ child, const uint32_t* __restrict__ vals,
                                                       const float4* __restrict__ leafBox, const float* __restrict__ etaLeaf, const float4* __restrict__ box,
                                                       const float* __restrict__ eta, const float* __restrict__ etaRootAll, uint32_t N, uint4* wide) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,16 +196,20 @@ unsigned blocks_of(uint64_t n) { return (unsigned)((n + 255) / 256); }
 }  // namespace
 
 // etaNode: the reference tree's per-node slack (leaf values at [N-1 + g], the maximum over all primitives at [0]); wide: room for
-// N - 1 + 16 records.  Returns #launches.
-int launch_traversal_tree(cudaStream_t st, uint32_t N, const void* leafBox, const float* etaNode, const TraversalTreeBuffers& b, void* wide) {
-    if (N < 2) return 0;
+// N - 1 + 16 records.  etaRootReady: recorded behind the reference tree's climb (which may run on another stream); the pack kernels --
+// the first readers of etaNode[0] -- wait for it.  Returns #launches.
+int launch_traversal_tree(cudaStream_t st, uint32_t N, const void* leafBox, const float* etaNode, const TraversalTreeBuffers& b, void* wide,
+                          cudaEvent_t etaRootReady) {
+    if (N < 2) { if (etaRootReady) cudaStreamWaitEvent(st, etaRootReady, 0); return 0; }
     const float* etaLeaf = etaNode + (N - 1);
     cudaMemsetAsync(b.arrivals, 0, sizeof(unsigned int) * (N - 1), st);
     tt_keys_kernel<<<blocks_of(N), 256, 0, st>>>((const float4*)leafBox, N, b.primBounds, b.smallBounds, b.flags, b.keys0, b.vals0);
     const int sortLaunches = launch_radix_sort(st, b.keys0, b.vals0, b.keys1, b.vals1, N, b.sortCounts);
     tt_topology_kernel<<<blocks_of(N), 256, 0, st>>>(b.keys0, b.flags, b.child, b.parent);
     tt_refit_kernel<<<blocks_of(N), 256, 0, st>>>(b.flags, b.child, b.parent, b.arrivals, b.vals0, (const float4*)leafBox, etaLeaf, b.box, b.eta);
-    tt_pack_kernel<<<blocks_of(N), 256, 0, st>>>(b.flags, b.child, b.vals0, (const float4*)leafBox, etaLeaf, b.box, b.eta, etaNode, N, (uint4*)wide);
+    if (etaRootReady) cudaStreamWaitEvent(st, etaRootReady, 0);
+    tt_pack_kernel<<<(unsigned)(((uint64_t)N + 127) / 128), 128, 0, st>>>(      // (56 registers: CTAs of 128 fit beside a resident trace launch)
+        b.flags, b.child, b.vals0, (const float4*)leafBox, etaLeaf, b.box, b.eta, etaNode, N, (uint4*)wide);
     tt_top_kernel<<<1, 32, 0, st>>>(b.flags, b.flags, b.bigList, b.primBounds, (const float4*)leafBox, etaLeaf, etaNode, b.box, b.eta, N, (uint4*)wide);
     return sortLaunches + 5;
 }

@@ -557,15 +557,15 @@ def test_tail_handover_off_equals_on(make_device):
     W, H, spp = 160, 90, 8
     ubo = make_ubo(len(sc["triangles"]), len(sc["spheres"]), len(sc["materials"]), sc["max_depth"], 11, sc["vfov"])
     frames = []
-    for coop, turns in ((0, 0), (8, 32), (32, 2)):
-        device = make_device(RTB_WAVE_COOP=coop, RTB_WAVE_COOP_TURNS=turns)
+    for coop, turns, shape in ((0, 0, {}), (8, 32, {}), (32, 2, {}), (32, 2, dict(RTB_WAVE_MAIN_CTAS=6, RTB_WAVE_TAIL_THREADS=64))):
+        device = make_device(RTB_WAVE_COOP=coop, RTB_WAVE_COOP_TURNS=turns, **shape)     # shape: launch-shape knobs (frames in flight)
         rt = _rt(device, W, H)
         rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
         rt.build_bvh(ubo)
         rt.clear_image(); rt.raytrace(ubo, spp); device.wait_idle()
         frames.append(rt.read_image())
         del rt
-    assert np.array_equal(_bits(frames[0]), _bits(frames[1])) and np.array_equal(_bits(frames[0]), _bits(frames[2]))
+    assert all(np.array_equal(_bits(frames[0]), _bits(f)) for f in frames[1:])
 
 
 @pytest.mark.parametrize("spec,spp,ext", [("meshRoom:70:5", 6, False), ("heightField:90:70:6:40", 4, True), ("sphereField:9000:7", 3, False)])
