@@ -72,7 +72,7 @@ def parse_args():
     ap.add_argument("--no-primary-sharing", action="store_true",
                     help="trace every sample's (identical, un-jittered) primary ray separately like the shader does (A/B switch, same results)")
     ap.add_argument("--nodes", default="auto", choices=["auto", "exact", "wide"],
-                    help="traversal records: auto (library default: 4-ary for >= 8192 primitives), exact 64-byte child pairs, "
+                    help="traversal records: auto (library default: 4-ary for >= 512 primitives), exact 64-byte child pairs, "
                          "64-byte 4-ary (A/B switch, same results)")
     ap.add_argument("--emulate-rank", default="", help="debugging: 'r/n' renders only the bands rank r of n would own, on one GPU, "
                                                          "without the collective (the per-rank workload of a tile-mode run, e.g. for ncu)")
@@ -868,7 +868,7 @@ def run_b200(args):
                                     "overlaps the previous frame's draining trace launch; ms_per_step = the K frames' bracket / K, frame_latency_ms = one frame alone"
                                     if fif > 1 else "1: one frame after the other")
         desc["traversal"] = ("reference visiting order, no t-interval (--reference-order)" if args.reference_order or args.kernel != "wave" else
-                             "library default: 4-ary records walked nearest-first with t-culling (scenes of >= 8192 primitives), else the exact child pairs in the reference's order")
+                             "library default: 4-ary records walked nearest-first with t-culling (scenes of >= 512 primitives), else the exact child pairs in the reference's order")
         desc["primary_sharing"] = ("off" if (args.no_primary_sharing or args.kernel != "wave") else
                                    "on: the samples of a pixel share one traversal of their identical (un-jittered) primary ray")
         if args.mode == "culled":

@@ -66,7 +66,7 @@ enum {
                                            (0.1,0.1,0.3) (:43).  Needs no BVH: bind with nodes = NULL. */
     RTB_TRACE_STREAM_KERNEL = 1u << 6,  /* run the streaming (wavefront) kernel trace_stream.cu instead of trace_wave.cu; same
                                            results (A/B switch while both exist) */
-    /* Traversal records.  Default (no flag): 64-byte 4-ary records with conservative 8-bit boxes for scenes of >= 8192
+    /* Traversal records.  Default (no flag): 64-byte 4-ary records with conservative 8-bit boxes for scenes of >= 512
      * primitives (two binary levels per step; exactness is restored at the leaves), the exact 64-byte child
      * pairs below that (the derivation of the 4-ary records costs more than it saves on tiny scenes).  The flags force
      * one representation (A/B measurements); results are identical in all cases.  The instrumented variant
@@ -78,7 +78,7 @@ enum {
      * same primary ray, whose hitBVH result is therefore traced once per pixel per rtb_raytrace call and shared by the samples
      * (identical results; nothing is kept between calls).  This flag traces it once per sample like the shader does. */
     RTB_TRACE_NO_PRIMARY_SHARING = 1u << 10,
-    /* Default for >= 8192 primitives when the scene's hit-point slack is small (DESIGN.md "nearest-first traversal"): the
+    /* Default for >= 512 primitives when the scene's hit-point slack is small (DESIGN.md "nearest-first traversal"): the
      * 4-ary records are walked nearest-first and entries that cannot change the result (beyond the closest hit so far, or
      * before tMin) are dropped; equal-t ties are resolved as the reference's visiting order would.  This flag keeps the
      * reference's visiting order with no t-interval, like the shader. */

@@ -20,7 +20,6 @@ std::string& last_error() { thread_local std::string e; return e; }
 
 namespace {
 
-constexpr uint32_t WIDE_MIN_PRIMITIVES = 8192;   // below: the exact child pairs (deriving the 4-ary records costs more than it saves)
 
 // Camera globals of raytraceBVH.comp:50-81, evaluated once on the host in binary32 with the shader's operation
 // order (compiled with -ffp-contract=off); tan() is libm's tanf.
@@ -153,6 +152,7 @@ int rtb_ctx_create(int device, void* stream, rtb_ctx** out) {
     if (const char* e = getenv("RTB_WAVE_TMIN")) c->knobs.tMin = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_SORTED_PUSH")) c->knobs.sortedPush = atoi(e);
     if (const char* e = getenv("RTB_WAVE_QGATE")) c->knobs.qGate = (uint32_t)atoi(e);
+    if (const char* e = getenv("RTB_WIDE_MIN")) c->knobs.wideMin = (uint32_t)(atoi(e) > 64 ? atoi(e) : 64);
     if (const char* e = getenv("RTB_WAVE_SMIN")) c->knobs.sMin = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_MAIN_CTAS")) c->knobs.mainCtas = (uint32_t)atoi(e);
     if (const char* e = getenv("RTB_WAVE_TAIL_THREADS")) c->knobs.tailThreads = atoi(e) == 64 ? 64u : 128u;
@@ -358,7 +358,7 @@ int rtb_build_bvh(rtb_ctx* c, const rtb_ubo* ubo, const void* models, void* tria
     uint32_t *k0 = (uint32_t*)c->sortKeys[0].p, *k1 = (uint32_t*)c->sortKeys[1].p;
     uint32_t *v0 = (uint32_t*)c->sortVals[0].p, *v1 = (uint32_t*)c->sortVals[1].p;
     int launches = 0;
-    if (N >= WIDE_MIN_PRIMITIVES) {
+    if (N >= c->knobs.wideMin) {
         // Fused build for scenes that are walked over the 4-ary records: K1 + K2 in one pass, the K5 leaf pass also emits the exact leaf
         // boxes / packed primitives / per-primitive hit-point slack, the K6 climb also carries the slack and the child-pair records.
         // The reference-layout outputs (nodes, morton1, enclosing, cinfo) are the same bits as the stage-by-stage entry points produce.
@@ -513,7 +513,7 @@ int rtb_raytrace(rtb_ctx* c, const rtb_ubo* ubo, void* image, const rtb_trace_ar
 #endif
             const bool derived = c->boundNodes && c->bN > 1 && (!count || walk);
             int nodesMode = !derived ? 0 : (a->flags & RTB_TRACE_EXACT_NODES) ? 0 : (a->flags & RTB_TRACE_WIDE_NODES) ? 2
-                                : (a->flags & RTB_TRACE_COMPRESSED_NODES) ? 1 : (c->bN >= WIDE_MIN_PRIMITIVES ? 2 : 0);
+                                : (a->flags & RTB_TRACE_COMPRESSED_NODES) ? 1 : (c->bN >= c->knobs.wideMin ? 2 : 0);
             int extra = derive_records(c, nodesMode, ubo->camPos);
             if (extra < 0) return 1;
             if (nodesMode) { p.sc.cnodes = nodesMode == 1 ? (const uint4*)c->cnodes.p : nullptr; p.sc.leafBox = (const float4*)c->leafBox.p; }

@@ -73,6 +73,7 @@ struct rtb_ctx {
         uint32_t mainCtas = 0;        // RTB_WAVE_MAIN_CTAS: resident CTAs per SM of the persistent trace launch (0 = all that fit, 7); fewer leave room for
                                       // the launches of another context's frame (frames in flight) to run beside it
         uint32_t tailThreads = 128;   // RTB_WAVE_TAIL_THREADS: CTA size of trace_tail_kernel (64 fits the slot RTB_WAVE_MAIN_CTAS=6 leaves)
+        uint32_t wideMin = 512;       // RTB_WIDE_MIN: scenes of fewer primitives keep the exact child pairs in the reference's order (C1, 1.1 k primitives: 1.01 -> 0.96 ms over the hierarchy)
         uint32_t sMin = 1;            // RTB_WAVE_SMIN: lanes that must wait for the S phase before a warp enters it
         uint32_t coopMax = 8;         // RTB_WAVE_COOP: tail hand-over threshold (live lanes per warp)
         uint32_t coopTurns = 32;      // RTB_WAVE_COOP_TURNS: long-ray hand-over threshold (turns)

@@ -90,7 +90,7 @@ def test_culled_walk_equals_exact_walk_and_hits_stay_within_eta(device, block):
 
 @pytest.mark.parametrize("n_big", [0, 1, 3, 4, 7, 45, 46, 120])
 def test_hoisted_big_primitives(device, n_big):
-    """Scenes of >= 8192 primitives take the fused build, whose derived records hoist the BIG leaves (boxes above 1/256 of the scene's
+    """Scenes of >= 512 primitives take the fused build, whose derived records hoist the BIG leaves (boxes above 1/256 of the scene's
     surface area) out of the hierarchy into a chain of records in front of the root (bvh_build.cu pack_wide_kernel): none, fewer than one
     record's worth, exactly full records, the maximum (45), one too many (nothing is hoisted) and far too many; big triangles AND big
     spheres, overlapping each other and the small geometry, duplicated (equal-t ties between a hoisted and an in-tree primitive).  The
@@ -136,7 +136,7 @@ def test_hoisted_big_primitives(device, n_big):
 
 @pytest.mark.parametrize("seed", range(10))
 def test_traversal_hierarchy_fuzz(device, seed):
-    """Scenes of >= 8192 primitives are walked over the library's own traversal hierarchy (traversal_tree.cu: adaptive-axis codes relative to
+    """Scenes of >= 512 primitives are walked over the library's own traversal hierarchy (traversal_tree.cu: adaptive-axis codes relative to
     the true bounds, big leaves in front of the root).  Adversarial inputs for THAT build: clouds far from the origin (|coordinate| up to 1e6:
     the reference's coord / span codes saturate there, the hierarchy's must not care), flat and needle-shaped extents (all code bits on one or
     two axes), thousands of coincident centres (equal codes: index tie-break), every primitive big (nothing hoisted), slivers, nested spheres.

@@ -147,7 +147,7 @@ def test_multi_pass_bit_identical(device, make_device):
     same image, hit ids and RNG states as one pass; the shared primary hits of pass 1 serve the later passes."""
     from raytracergpu_mastersproject_b200 import Buffer, capi
     W, H, spp = 128, 96, 20
-    sc = SU.random_scene(21, n_tris=9000, n_spheres=40)          # >= 8192 primitives: 4-ary records
+    sc = SU.random_scene(21, n_tris=9000, n_spheres=40)          # >= 512 primitives: 4-ary records
     ubo = SU.make_ubo(sc, random_state=77)
     rt = _rt(device, W, H)
     rt.update_scene(sc["models"], sc["triangles"], sc["spheres"], sc["materials"])
