@@ -85,13 +85,26 @@ def library_path() -> str:
     return _SO
 
 
-def build(force: bool = False) -> str:
-    """Compile librtb200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+def _stale() -> bool:
     srcs = [os.path.join(_PKG, "csrc", f) for f in os.listdir(os.path.join(_PKG, "csrc"))] + [_HEADER,
                                                                                                os.path.join(_PKG, "Makefile")]
-    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
-    if force or stale:
-        subprocess.run(["make", "-C", _PKG, "-j8", "-s"], check=True)
+    return (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+
+
+def build(force: bool = False) -> str:
+    """Compile librtb200.so for sm_100a in-tree (nvcc cross-compiles without a GPU).  Several processes may call this at once (the
+    ranks of a torchrun launch): an exclusive file lock lets one of them build while the others wait and then find the library fresh;
+    the Makefile links to a temporary name and renames, so a library that exists is always complete."""
+    if not (force or _stale()):
+        return _SO
+    import fcntl
+    with open(os.path.join(_PKG, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or _stale():
+                subprocess.run(["make", "-C", _PKG, "-j8", "-s"], check=True)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 
