@@ -353,22 +353,35 @@ __global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinf
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const uint32_t leafOffset = n - 1;
-    uint32_t nodeId = __ldcg(&cinfo[leafOffset + g]).x;
+    // The climbing thread keeps the box (and slack) of the subtree it comes from in registers; a node's static words -- its children and
+    // its parent -- are fetched beside the arrival atomic: two dependent round trips per level (atomic, sibling box) instead of four.
+    uint32_t me = leafOffset + g;
+    uint32_t nodeId = __ldcg(&cinfo[me]).x;
+    float2 mx, my, mz;
+    { const float2* B = reinterpret_cast<const float2*>(nodes + 10ull * me); mx = __ldcg(B); my = __ldcg(B + 1); mz = __ldcg(B + 2); }
+    float me_eta = etaNode ? __ldcg(&etaNode[me]) : 0.f;
     while (true) {
+        uint32_t* nd = nodes + 10ull * nodeId;
+        const uint2 ch = __ldcg(reinterpret_cast<const uint2*>(nd) + 3);
+        const uint32_t up = __ldcg(&cinfo[nodeId]).x;
+        __threadfence();
         const int visitations = atomicAdd(reinterpret_cast<int*>(&cinfo[nodeId]) + 1, 1);
         if (visitations < 1) return;
         __threadfence();
-        uint32_t* nd = nodes + 10ull * nodeId;
-        const uint2 ch = __ldcg(reinterpret_cast<const uint2*>(nd) + 3);
-        const float2* L = reinterpret_cast<const float2*>(nodes + 10ull * ch.x);
-        const float2* R = reinterpret_cast<const float2*>(nodes + 10ull * ch.y);
-        const float2 lx = __ldcg(L), ly = __ldcg(L + 1), lz = __ldcg(L + 2);
-        const float2 rx = __ldcg(R), ry = __ldcg(R + 1), rz = __ldcg(R + 2);
+        const bool iAmLeft = ch.x == me;
+        const uint32_t sib = iAmLeft ? ch.y : ch.x;
+        const float2* S = reinterpret_cast<const float2*>(nodes + 10ull * sib);
+        const float2 sx = __ldcg(S), sy = __ldcg(S + 1), sz = __ldcg(S + 2);
+        const float2 lx = iAmLeft ? mx : sx, ly = iAmLeft ? my : sy, lz = iAmLeft ? mz : sz;
+        const float2 rx = iAmLeft ? sx : mx, ry = iAmLeft ? sy : my, rz = iAmLeft ? sz : mz;
         // combineAABB(left, right) :27-36
-        __stcg(reinterpret_cast<float2*>(nd), make_float2(gmin(lx.x, rx.x), gmax(lx.y, rx.y)));
-        __stcg(reinterpret_cast<float2*>(nd) + 1, make_float2(gmin(ly.x, ry.x), gmax(ly.y, ry.y)));
-        __stcg(reinterpret_cast<float2*>(nd) + 2, make_float2(gmin(lz.x, rz.x), gmax(lz.y, rz.y)));
-        if (etaNode) __stcg(&etaNode[nodeId], fmaxf(__ldcg(&etaNode[ch.x]), __ldcg(&etaNode[ch.y])));   // largest hit-point slack of the subtree
+        mx = make_float2(gmin(lx.x, rx.x), gmax(lx.y, rx.y));
+        my = make_float2(gmin(ly.x, ry.x), gmax(ly.y, ry.y));
+        mz = make_float2(gmin(lz.x, rz.x), gmax(lz.y, rz.y));
+        __stcg(reinterpret_cast<float2*>(nd), mx);
+        __stcg(reinterpret_cast<float2*>(nd) + 1, my);
+        __stcg(reinterpret_cast<float2*>(nd) + 2, mz);
+        if (etaNode) { me_eta = fmaxf(me_eta, __ldcg(&etaNode[sib])); __stcg(&etaNode[nodeId], me_eta); }   // largest hit-point slack of the subtree
         if (pairs) {    // the thread that unions a node holds both child boxes: emit the node's 64-byte traversal record here
             float4* out = pairs + 4ull * nodeId;
             out[0] = make_float4(lx.x, ly.x, lz.x, __uint_as_float(ch.x));
@@ -376,13 +389,12 @@ __global__ void __launch_bounds__(256) refit_kernel(uint32_t* nodes, uint2* cinf
             out[2] = make_float4(rx.x, ry.x, rz.x, 0.f);
             out[3] = make_float4(rx.y, ry.y, rz.y, 0.f);
             if (nodeId == 0) {
-                rootBox[0] = make_float4(gmin(lx.x, rx.x), gmin(ly.x, ry.x), gmin(lz.x, rz.x), 0.f);
-                rootBox[1] = make_float4(gmax(lx.y, rx.y), gmax(ly.y, ry.y), gmax(lz.y, rz.y), 0.f);
+                rootBox[0] = make_float4(mx.x, my.x, mz.x, 0.f);
+                rootBox[1] = make_float4(mx.y, my.y, mz.y, 0.f);
             }
         }
         if (nodeId == 0) return;
-        __threadfence();
-        nodeId = __ldcg(&cinfo[nodeId]).x;
+        me = nodeId; nodeId = up;
     }
 }
 

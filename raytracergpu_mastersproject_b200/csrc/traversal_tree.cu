@@ -86,7 +86,9 @@ __device__ __forceinline__ void tt_node_box(const uint32_t c, const uint32_t lea
     }
 }
 
-// bottom-up union of boxes and slack: one thread per leaf climbs, the second arrival at a node continues (as refit_kernel)
+// bottom-up union of boxes and slack: one thread per leaf climbs, the second arrival at a node continues (as refit_kernel).  The climbing
+// thread keeps the box of the subtree it comes from in registers and the (static) topology words of a node are fetched beside the arrival
+// atomic, so a level costs two dependent memory round trips -- the atomic, then the sibling's box -- instead of four.
 __global__ void __launch_bounds__(256) tt_refit_kernel(const unsigned int* __restrict__ flags, const uint2* __restrict__ child, const uint32_t* __restrict__ parent,
                                                        unsigned int* arrivals, const uint32_t* __restrict__ vals, const float4* __restrict__ leafBox,
                                                        const float* __restrict__ etaLeaf, float4* box, float* eta) {
@@ -94,20 +96,26 @@ __global__ void __launch_bounds__(256) tt_refit_kernel(const unsigned int* __res
     const uint32_t n2 = flags[3];
     if (j >= n2 || n2 < 2u) return;
     const uint32_t leafOffset2 = n2 - 1u;
-    uint32_t node = parent[leafOffset2 + j];
+    uint32_t me = leafOffset2 + j;
+    uint32_t node = parent[me];
+    float4 lo, hi; float e;
+    tt_node_box(me, leafOffset2, vals, leafBox, etaLeaf, box, eta, lo, hi, e);
     while (true) {
-        __threadfence();
+        const uint2 ch = child[node];
+        const uint32_t up = node ? parent[node] : 0u;
+        __threadfence();                                                    // my subtree's box (stored below) before my arrival
         if (atomicAdd(&arrivals[node], 1u) == 0u) return;                // the sibling subtree is not finished yet
         __threadfence();
-        const uint2 ch = child[node];
-        float4 l0, h0, l1, h1; float e0, e1;
-        tt_node_box(ch.x, leafOffset2, vals, leafBox, etaLeaf, box, eta, l0, h0, e0);
-        tt_node_box(ch.y, leafOffset2, vals, leafBox, etaLeaf, box, eta, l1, h1, e1);
-        __stcg(&box[2ull * node], make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f));
-        __stcg(&box[2ull * node + 1], make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f));
-        __stcg(&eta[node], fmaxf(e0, e1));
+        float4 l1, h1; float e1;
+        tt_node_box(ch.x == me ? ch.y : ch.x, leafOffset2, vals, leafBox, etaLeaf, box, eta, l1, h1, e1);
+        lo = make_float4(fminf(lo.x, l1.x), fminf(lo.y, l1.y), fminf(lo.z, l1.z), 0.f);
+        hi = make_float4(fmaxf(hi.x, h1.x), fmaxf(hi.y, h1.y), fmaxf(hi.z, h1.z), 0.f);
+        e = fmaxf(e, e1);
+        __stcg(&box[2ull * node], lo);
+        __stcg(&box[2ull * node + 1], hi);
+        __stcg(&eta[node], e);
         if (node == 0u) return;
-        node = parent[node];
+        me = node; node = up;
     }
 }
 

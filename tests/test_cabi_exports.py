@@ -43,3 +43,21 @@ def test_record_sizes_match_reference_layouts():
              capi.ENCLOSING_BOX.itemsize, capi.UBO.itemsize]
     assert sizes == [64, 64, 32, 32, 40, 12, 8, 32, 80]
     assert ctypes.sizeof(capi.TraceArgs) == 80
+
+
+def test_concurrent_builds_are_serialised(tmp_path):
+    """The ranks of a torchrun launch all call capi.lib() -> build(): with a stale library they must not race (one builds under a
+    file lock and renames the finished library into place, the others wait and load it)."""
+    import subprocess
+    import sys
+    import time
+    from raytracergpu_mastersproject_b200 import capi
+    capi.build()
+    src = os.path.join(os.path.dirname(capi.library_path()), "csrc", "probe.cu")
+    time.sleep(0.05); os.utime(src)                              # the smallest translation unit: stale by mtime only
+    code = ("from raytracergpu_mastersproject_b200 import capi; import ctypes; capi.build(); L = ctypes.CDLL(capi.library_path()); "
+            "assert L.rtb_version() >= 200; assert not capi._stale()")
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    procs = [subprocess.Popen([sys.executable, "-c", code], env=env, stderr=subprocess.PIPE) for _ in range(4)]
+    errs = [(p.wait(), p.stderr.read().decode()[-400:]) for p in procs]
+    assert all(rc == 0 for rc, _ in errs), errs
