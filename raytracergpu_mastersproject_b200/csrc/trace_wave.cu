@@ -62,11 +62,6 @@ struct LinearStack {
     uint32_t* s;
     __device__ __forceinline__ uint32_t& operator[](uint32_t i) const { return s[i]; }
 };
-struct StridedStack {
-    uint32_t (*s)[WAVE_THREADS];
-    unsigned base;
-    __device__ __forceinline__ uint32_t& operator[](uint32_t i) const { return s[i >> 5][base + (i & 31u)]; }
-};
 template <bool EXT, bool COUNT, class STK>
 __device__ __forceinline__ void tail_item(const TraceParams& p, const uint32_t item, const STK stk, const unsigned lane, Tally& tl, unsigned& err);
 // A/B build RTB_SMEM_TOP: stack entries of the main kernel may be table indices; the tail kernel walks global records only

@@ -170,6 +170,17 @@ def test_multi_pass_bit_identical(device, make_device):
     assert np.array_equal(_bits(one), _bits(rr["image"]))
 
 
+@pytest.mark.parametrize("n_prims", [511, 512, 513, 640])
+def test_wide_threshold_boundary(device, n_prims):
+    """Scenes around RTB_WIDE_MIN (512 primitives): just below, the exact child pairs in the reference's order; from 512 on, the fused
+    build and the walk's own hierarchy.  The frame, primary hit ids and RNG states are the oracle's on both sides of the switch."""
+    sc = SU.random_scene(300 + n_prims, n_tris=n_prims - 46, n_spheres=40, sort_morton=True)
+    N = len(sc["triangles"]) + len(sc["spheres"])
+    assert N == n_prims, N
+    ubo = SU.make_ubo(sc, random_state=5)
+    _check_against_oracle(device, sc, ubo, 72, 48, 3, [0])
+
+
 def test_progressive_equals_fused(device):
     """spp dispatches one at a time (the reference's loop) == one fused launch == skip+count split."""
     W, H = 64, 48
