@@ -307,12 +307,18 @@ class Session:
             self._lanes.append(ln)
         return self._lanes[:n]
 
-    def aux_device(self, name):
-        """a second context of the same GPU on its own stream (H2D / D2H copy engines overlap the compute stream)"""
+    def aux_device(self, name, comm=False):
+        """a second context of the same GPU on its own stream (H2D / D2H copy engines overlap the compute stream); comm: with a
+        communicator of its own (collective: every rank asks for it at the same point)"""
         if name not in self._aux:
             from raytracergpu_mastersproject_b200 import Device
             st = self.torch.cuda.Stream(device=self.tdev)
-            self._aux[name] = (Device(self.local_rank, stream=st.cuda_stream), st)
+            d = Device(self.local_rank, stream=st.cuda_stream)
+            if comm and self.world > 1:
+                ids = [Device.comm_unique_id() if self.rank == 0 else None]
+                self.dist.broadcast_object_list(ids, src=0)
+                d.comm_init(self.world, self.rank, ids[0])
+            self._aux[name] = (d, st)
         return self._aux[name]
 
     def ev(self):
@@ -626,14 +632,14 @@ class Frame:
 
     def e2e(self, steps, in_flight=1):
         """Host buffers in, RGBA8 frame out, through the C-ABI, pipelined over three streams: H2D uploads (rtb_upload on a copy
-        context; each rank its 1/N slice of the primitive arrays, completed over NVLink by rtb_comm_all_gather), the frame, and the
+        context; each rank its 1/N slice of the primitive arrays, completed over NVLink by rtb_comm_all_gather on the same stream), the frame, and the
         D2H read-back of the resolved frame (rtb_download_async on a second copy context).  Two buffer sets alternate (in_flight > 1:
         one per lane, and the frames alternate over the lanes like in the timed leg)."""
         S, capi, torch, C = self.S, self.S.capi, self.S.torch, self.C
         fl = self.in_flight(in_flight)
         nset = max(2, len(fl))
         world, rank = S.world, S.rank
-        up, up_st = S.aux_device("h2d")
+        up, up_st = S.aux_device("h2d", comm=True)
         dn, dn_st = S.aux_device("d2h")
         pin = lambda a: torch.from_numpy(a.copy()).pin_memory()  # noqa: E731
         hm, hmat = pin(self.host["models"]), pin(self.host["materials"])
@@ -650,7 +656,7 @@ class Frame:
         def step(i):
             s = sets[i % nset]
             f = fl[i % len(fl)]
-            st, dev = f.S.stream, f.S.dev
+            st = f.S.stream
             if s["done"] is not None:
                 up_st.wait_event(s["done"])                      # the frame that used this set two steps ago has finished
             capi.check(S.L.rtb_upload(up.handle, self.vp(s["models"]), C.c_void_p(hm.data_ptr()), hm.numel()))
@@ -659,10 +665,10 @@ class Frame:
                 lo, hp = parts[k]
                 if hp is not None:
                     capi.check(S.L.rtb_upload(up.handle, C.c_void_p(buf.data_ptr() + lo), C.c_void_p(hp.data_ptr()), hp.numel()))
+            if world > 1:                                        # the other ranks' slices arrive over NVLink, still on the upload stream
+                up.comm_all_gather(s["tris"].data_ptr(), self.slice["triangles"])
+                up.comm_all_gather(s["sphs"].data_ptr(), self.slice["spheres"])
             st.wait_event(up_st.record_event())
-            if world > 1:                                        # the other ranks' slices arrive over NVLink
-                dev.comm_all_gather(s["tris"].data_ptr(), self.slice["triangles"])
-                dev.comm_all_gather(s["sphs"].data_ptr(), self.slice["spheres"])
             if s["read"] is not None:
                 st.wait_event(s["read"])                         # this set's RGBA8 frame has been read back
             f.flushed_frame(tris=s["tris"], sphs=s["sphs"], rgba8=s["rgba8"], models=s["models"], mats=s["mats"])
