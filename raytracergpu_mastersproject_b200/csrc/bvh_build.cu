@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(256) pack_wide_kernel(const uint32_t* __restri
 __global__ void build_top_table_kernel(const uint4* __restrict__ wide, uint32_t n, uint4* top, uint32_t* topGlobal, const unsigned int* flags) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     uint32_t count = 1;
-    topGlobal[0] = flags[1];                                     // the record the walk starts at (pack_top_records_kernel)
+    topGlobal[0] = flags[1];                                     // the record the walk starts at (tt_top_kernel)
     for (uint32_t i = 0; i < RTB_SMEM_TOP; i++) {
         if (i >= count) { for (int j = 0; j < 4; j++) top[4 * i + j] = make_uint4(0, 0, 0, 0); topGlobal[i] = 0; continue; }
         uint4 r[4];

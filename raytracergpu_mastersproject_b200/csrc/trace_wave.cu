@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, NODES >= 2 ? WIDE_MIN_BLOCKS : W
 #define RTB_ROOT_RECORD() (NODES >= 3 ? 0x80000000u : 0u)          /* entry 0 of the table = the record the walk starts at */
 #else
     const uint4* smTop = nullptr;
-    // the record the walk starts at: the root's, or the first of the records that hold the hoisted big leaves (pack_top_records_kernel);
+    // the record the walk starts at: the root's, or the first of the records that hold the hoisted big leaves (tt_top_kernel);
     // re-read per ray (an L1 hit) rather than held in a register: the kernel sits exactly at its 72-register budget
 #define RTB_ROOT_RECORD() (NODES >= 3 ? __ldg(p.cullAllowed + 1) : 0u)
 #endif
@@ -450,7 +450,7 @@ __device__ __forceinline__ void tail_item(const TraceParams& p, const uint32_t i
                     rec.mat = __float_as_uint(q6.x); rec.prim = __float_as_uint(q6.y); rec.back = (int)__float_as_uint(q6.z);
                 }
                 resume = 0;
-            } else if (lane == 0) stk[0] = p.cullAllowed[1];              // the record the walk starts at (pack_top_records_kernel)
+            } else if (lane == 0) stk[0] = p.cullAllowed[1];              // the record the walk starts at (tt_top_kernel)
             __syncwarp();
             while (n > 0) {
                 if (COUNT && lane == 0) tl.tailTurns++;
