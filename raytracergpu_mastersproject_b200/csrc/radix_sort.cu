@@ -162,9 +162,78 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const uint32
     }
 }
 
+// Small arrays (<= 2048 elements: complexScene-sized scenes, where the build is a chain of launch latencies): all four passes in ONE
+// block, ping-ponging between two shared-memory copies -- 1 launch instead of 12.  Same stable ranking as sort_scatter_kernel (element
+// = warp * 256 + row * 32 + lane), hence the same result.
+constexpr int SORT_SMALL_N = 2048;
+constexpr int SORT_SMALL_ROWS = SORT_SMALL_N / SORT_THREADS;
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_small_kernel(uint32_t* keys, uint32_t* vals, uint32_t n) {
+    __shared__ uint32_t sk[2][SORT_SMALL_N], sv[2][SORT_SMALL_N];
+    __shared__ uint32_t warpCnt[SORT_THREADS / 32][256];
+    __shared__ uint32_t digitStart[256];
+    __shared__ uint32_t wsum[8];
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < n; i += SORT_THREADS) { sk[0][i] = keys[i]; sv[0][i] = vals[i]; }
+    __syncthreads();
+    for (uint32_t pass = 0; pass < 4; pass++) {
+        const uint32_t src = pass & 1u, dst = src ^ 1u, shift = 8u * pass;
+#pragma unroll
+        for (int w = 0; w < SORT_THREADS / 32; w++) warpCnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t key[SORT_SMALL_ROWS], rank[SORT_SMALL_ROWS];
+#pragma unroll
+        for (int k = 0; k < SORT_SMALL_ROWS; k++) {
+            const uint32_t i = warp * (SORT_SMALL_ROWS * 32u) + (uint32_t)k * 32u + lane;
+            const bool valid = i < n;
+            key[k] = valid ? sk[src][i] : 0u;
+            const uint32_t digit = valid ? (key[k] >> shift) & 255u : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(FULL, digit);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && (int)lane == leader) { old = warpCnt[warp][digit]; warpCnt[warp][digit] = old + (uint32_t)__popc(peers); }
+            __syncwarp();
+            old = __shfl_sync(FULL, old, leader);
+            rank[k] = old + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < SORT_THREADS / 32; w++) { const uint32_t c = warpCnt[w][threadIdx.x]; warpCnt[w][threadIdx.x] = run; run += c; }
+            uint32_t incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            uint32_t before = 0;
+            for (uint32_t w = 0; w < warp; w++) before += wsum[w];
+            digitStart[threadIdx.x] = before + incl - run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SORT_SMALL_ROWS; k++) {
+            const uint32_t i = warp * (SORT_SMALL_ROWS * 32u) + (uint32_t)k * 32u + lane;
+            if (i < n) {
+                const uint32_t digit = (key[k] >> shift) & 255u;
+                const uint32_t p = digitStart[digit] + warpCnt[warp][digit] + rank[k];
+                sk[dst][p] = key[k];
+                sv[dst][p] = sv[src][i];
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += SORT_THREADS) { keys[i] = sk[0][i]; vals[i] = sv[0][i]; }
+}
+
 // 4 passes; keys/vals[0] hold the input and (after an even number of passes) the result.  Returns #launches.
 int launch_radix_sort(cudaStream_t st, uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1, uint32_t n, uint32_t* counts) {
     if (n == 0) return 0;
+    if (n <= (uint32_t)SORT_SMALL_N) { sort_small_kernel<<<1, SORT_THREADS, 0, st>>>(keys0, vals0, n); return 1; }
     const uint32_t numTiles = (n + SORT_TILE - 1) / SORT_TILE;
     uint32_t *kin = keys0, *vin = vals0, *kout = keys1, *vout = vals1;
     for (uint32_t pass = 0; pass < 4; pass++) {       // ITERATIONS 4 x BITS_PER_ITERATION 8 (RadixSortSimple.comp:11-12)

@@ -9,7 +9,8 @@ from raytracergpu_mastersproject_b200 import Device, Raytracer  # noqa: E402
 from oracle import oracle as O                                  # noqa: E402  (checker only)
 
 W, H, spp = 96, 64, 3
-sc = SU.random_scene(77, n_tris=3000, n_spheres=200, sort_morton=True)
+n_tris = int(sys.argv[1]) if len(sys.argv) > 1 else 3000        # <= 1800: the single-block sort; default: the tiled sort
+sc = SU.random_scene(77, n_tris=n_tris, n_spheres=200, sort_morton=True)
 ubo = SU.make_ubo(sc, random_state=9)
 dev = Device(0)
 rt = Raytracer(dev, W, H)
